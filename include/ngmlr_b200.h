@@ -1,0 +1,137 @@
+/* include/ngmlr_b200.h -- C ABI of the B200-native ngmlr alignment hot path.
+ *
+ * libngmlr_b200.so exports two surfaces:
+ *
+ *  (1) The reference's dormant plugin contract, src/IAlignment.h:249-250:
+ *          typedef IAlignment* (*pfCreateAlignment)(int const gpu_id);
+ *          typedef void        (*pfDeleteAlignment)(IAlignment*);
+ *      as  extern "C" IAlignment* CreateAlignment(int gpu_id) / void DeleteAlignment(IAlignment*).
+ *      The object implements every virtual of `class IAlignment` (src/IAlignment.h:211-247)
+ *      with the reference's argument meaning and error behaviour; the ABI-compatible C++
+ *      declarations are in include/ngmlr_b200_ialignment.h. See INTEGRATION.md for the two
+ *      construction sites a maintainer switches (src/AlignmentBuffer.h:345-363, src/NGM.cpp:350-362).
+ *
+ *  (2) The plain-C batch interface below (pointers + sizes only), which the C++ plugin object,
+ *      the Python host layer (ctypes) and any other FFI bind. Each entry point names the reference
+ *      interface it replaces.
+ *
+ * All calls on one context must come from one thread at a time (the reference uses one aligner
+ * object per worker thread). Functions return 0 on success, <0 on error;
+ * ngmlr_b200_last_error() describes the failure. There is NO CPU fallback: without a CUDA device
+ * ngmlr_b200_create() fails.
+ */
+#ifndef NGMLR_B200_H
+#define NGMLR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NGMLR_B200_ABI_VERSION 1
+
+/* Convex scoring parameters = ConvexAlignFast's constructor arguments
+ * (src/ConvexAlignFast.h:20-27, src/ConvexAlignFast.cpp:29-43; CLI defaults src/IConfig.h:23-71):
+ * --match 2 --mismatch -5 --gap-open -5 --gap-extend-max -5 --gap-extend-min -1 --gap-decay 0.15 */
+typedef struct {
+  float match, mismatch, gap_open, gap_extend, gap_extend_min, gap_decay;
+} ngmlr_b200_scoring;
+
+typedef struct ngmlr_b200_ctx ngmlr_b200_ctx;
+
+/* Result of one convex alignment = the fields ConvexAlignFast::SingleAlign fills in `Align`
+ * (src/IAlignment.h:112-191) plus its return value. Text and position buffers are owned by the
+ * context and stay valid until the next *_align_batch / *_fetch call on it. */
+typedef struct {
+  int32_t ret;              /* SingleAlign return value: read bases covered by CIGAR incl. clips, or -1 */
+  int32_t threw;            /* 1 where the reference would `throw` (caller maps to "unmapped") */
+  float score;              /* Align::Score (-1.0f when ret < 0) */
+  float identity;           /* Align::Identity */
+  int32_t position_offset;  /* Align::PositionOffset */
+  int32_t qstart, qend;     /* Align::QStart / QEnd (incl. externalQStart/End) */
+  int32_t nm;               /* Align::NM */
+  int32_t alignment_length; /* Align::alignmentLength */
+  int32_t cigar_op_count;   /* Align::cigarOpCount */
+  int32_t sv_type;          /* Align::svType */
+  int32_t first_ref, first_read, last_ref, last_read; /* Align::firstPosition / lastPosition */
+  int32_t nm_count;         /* entries written to Align::nmPerPosition */
+  int32_t cigar_len, md_len;
+  const char* cigar;        /* Align::pBuffer1, NUL-terminated */
+  const char* md;           /* Align::pBuffer2, NUL-terminated */
+  const int32_t* nm_positions; /* nm_count x {refPosition, readPosition, nm} */
+  int64_t cells;            /* DP cells evaluated (SURVEY.md section 8d unit of work) */
+} ngmlr_b200_align_result;
+
+/* Aggregate device-side statistics of the last convex batch (for roofline accounting). */
+typedef struct {
+  int64_t cells;            /* DP cells evaluated by the fill kernel */
+  int64_t dir_bytes;        /* direction bytes written to HBM (2 bit/cell, blocked layout incl. padding) */
+  int64_t seq_bytes;        /* sequence bytes staged */
+  int64_t path_steps;       /* traceback steps */
+  int64_t cigar_runs;       /* binary CIGAR runs emitted */
+  float fill_ms, traceback_ms, compact_ms; /* CUDA-event durations on the context's stream */
+  int32_t fill_launches, traceback_launches, compact_launches;
+  int64_t h2d_bytes, d2h_bytes;
+} ngmlr_b200_batch_stats;
+
+int ngmlr_b200_abi_version(void);
+int ngmlr_b200_device_count(void);
+
+/* Creates a context on CUDA device gpu_id. Replaces `new ConvexAlignFast(...)` + `new StrippedSW()`
+ * (src/AlignmentBuffer.h:355-368) / `_NGM::CreateAlignment` (src/NGM.cpp:350-362). */
+int ngmlr_b200_create(int gpu_id, const ngmlr_b200_scoring* scoring, ngmlr_b200_ctx** out);
+void ngmlr_b200_destroy(ngmlr_b200_ctx* ctx);
+const char* ngmlr_b200_last_error(const ngmlr_b200_ctx* ctx); /* ctx may be NULL: last create error */
+
+/* Use an externally owned CUDA stream (e.g. torch's current stream) for all work; 0 = own stream. */
+int ngmlr_b200_set_stream(ngmlr_b200_ctx* ctx, void* cuda_stream);
+void* ngmlr_b200_get_stream(ngmlr_b200_ctx* ctx);
+
+/* ---- convex banded alignment: IAlignment::SingleAlign(mode, CorridorLine*, ...) batched -------
+ * Replaces ConvexAlignFast::SingleAlign (src/ConvexAlignFast.cpp:452-559) for n independent
+ * problems. Problem i: refs[i]/qrys[i] are the reference window and read part (need not be
+ * NUL-terminated; lengths given), corridor rows i are offsets[row_start[i] .. row_start[i+1]) and
+ * the matching lengths (CorridorLine::offset / ::length); row count must equal qry_lens[i].
+ * ext_qstart/ext_qend may be NULL (zeros). Host buffers; H2D/D2H happen inside the call. */
+int ngmlr_b200_convex_align_batch(ngmlr_b200_ctx* ctx, int n, const char* const* refs,
+                                  const int32_t* ref_lens, const char* const* qrys,
+                                  const int32_t* qry_lens, const int32_t* corridor_offsets,
+                                  const int32_t* corridor_lengths, const int64_t* row_start,
+                                  const int32_t* ext_qstart, const int32_t* ext_qend,
+                                  ngmlr_b200_align_result* results);
+
+/* The same work split into its three phases, so that benchmarks can time the kernels with the
+ * inputs already resident in HBM:
+ *   upload : pack + H2D (no kernels)
+ *   run    : fill -> traceback -> compact kernels on resident inputs (no host<->device copies
+ *            except the 16-byte allocation counters); may be called repeatedly on one upload
+ *   fetch  : D2H of the binary CIGARs + host CIGAR/MD text, fills results[n] */
+int ngmlr_b200_convex_upload(ngmlr_b200_ctx* ctx, int n, const char* const* refs,
+                             const int32_t* ref_lens, const char* const* qrys,
+                             const int32_t* qry_lens, const int32_t* corridor_offsets,
+                             const int32_t* corridor_lengths, const int64_t* row_start,
+                             const int32_t* ext_qstart, const int32_t* ext_qend);
+int ngmlr_b200_convex_run(ngmlr_b200_ctx* ctx);
+int ngmlr_b200_convex_fetch(ngmlr_b200_ctx* ctx, ngmlr_b200_align_result* results);
+int ngmlr_b200_convex_stats(ngmlr_b200_ctx* ctx, ngmlr_b200_batch_stats* out);
+
+/* Debug/parity aid: after convex_run, decode problem i's direction matrix into the reference's
+ * row-major layout (AlignmentMatrixFast::directionMatrix, src/AlignmentMatrixFast.h:261): one
+ * byte per corridor cell, values CIGAR_EQ 7 / X 8 / I 1 / D 2 / STOP 10, 0xFF = never written.
+ * dirs must hold sum(lengths) bytes. Also returns the forward-fill best cell. */
+int ngmlr_b200_convex_debug_directions(ngmlr_b200_ctx* ctx, int i, uint8_t* dirs, size_t dirs_cap,
+                                       float* best_score, int32_t* best_ref, int32_t* best_read);
+
+/* ---- sub-read scoring: IAlignment::BatchScore / SingleScore -----------------------------------
+ * Replaces StrippedSW::BatchScore (src/StrippedSW.cpp:118-160). Strings must be NUL-terminated
+ * (the reference scores strlen+1 characters). results[i] = best local score as float, or -1.0f
+ * when a length is >= 100000. Returns n. */
+int ngmlr_b200_sw_score_batch(ngmlr_b200_ctx* ctx, int n, const char* const* refs,
+                              const char* const* qrys, float* results);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NGMLR_B200_H */

@@ -1,0 +1,5 @@
+"""ngmlr_b200 -- B200-native (sm_100a CUDA) implementation of ngmlr's alignment hot path behind the
+reference's IAlignment plugin surface. See DESIGN.md / INTEGRATION.md."""
+from .aligner import Align, B200Aligner, PackedBatch, DEFAULT_SCORING  # noqa: F401
+
+__all__ = ["Align", "B200Aligner", "PackedBatch", "DEFAULT_SCORING"]

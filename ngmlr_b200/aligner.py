@@ -1,0 +1,196 @@
+"""Host-side mirror of ngmlr's aligner interface over the C ABI (include/ngmlr_b200.h).
+
+`B200Aligner` plays the role of the reference's two IAlignment implementations on the hot path:
+  convex alignment  <- Convex::ConvexAlignFast::SingleAlign  (src/ConvexAlignFast.cpp:452-559)
+  sub-read scoring  <- StrippedSW::BatchScore / SingleScore   (src/StrippedSW.cpp:118-202)
+Method names and argument meaning follow `class IAlignment` (src/IAlignment.h:211-247); the
+batched convex entry point is what the reference's BatchAlign would be had it been implemented
+(src/ConvexAlignFast.cpp:441-450 throws "Not implemented").
+
+All compute happens in the CUDA library; nothing here (or anywhere in the package) computes an
+alignment on the CPU.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+
+DEFAULT_SCORING = (2.0, -5.0, -5.0, -5.0, -1.0, 0.15)
+
+
+@dataclass
+class Align:
+    """The fields of the reference's `Align` that SingleAlign fills (src/IAlignment.h:112-191)."""
+    ret: int = -1
+    threw: bool = False
+    Score: float = -1.0
+    Identity: float = 0.0
+    PositionOffset: int = 0
+    QStart: int = 0
+    QEnd: int = 0
+    NM: int = 0
+    alignmentLength: int = 0
+    cigarOpCount: int = 0
+    svType: int = 0
+    firstPosition: tuple = (0, 0)
+    lastPosition: tuple = (0, 0)
+    pBuffer1: str = ""   # CIGAR
+    pBuffer2: str = ""   # MD
+    nmPerPosition: np.ndarray = field(default_factory=lambda: np.zeros((0, 3), np.int32))
+    cells: int = 0
+
+    def as_dict(self):
+        """Same keys as tests/oracle_lib.py results, for bit-exact comparison."""
+        return dict(ret=self.ret, status=int(self.threw),
+                    score_bits=int(np.float32(self.Score).view(np.uint32)),
+                    identity_bits=int(np.float32(self.Identity).view(np.uint32)),
+                    position_offset=self.PositionOffset, qstart=self.QStart, qend=self.QEnd,
+                    nm=self.NM, alignment_length=self.alignmentLength,
+                    cigar_op_count=self.cigarOpCount, sv_type=self.svType,
+                    first_ref=self.firstPosition[0], first_read=self.firstPosition[1],
+                    last_ref=self.lastPosition[0], last_read=self.lastPosition[1],
+                    nm_count=len(self.nmPerPosition), cigar=self.pBuffer1, md=self.pBuffer2,
+                    nm_positions=self.nmPerPosition, score=self.Score)
+
+
+class PackedBatch:
+    """A batch of SingleAlign problems laid out for the C ABI (host buffers)."""
+
+    def __init__(self, refs, qrys, offsets, lengths, ext_qstart=None, ext_qend=None):
+        n = len(refs)
+        self.n = n
+        self.refs = [bytes(r) for r in refs]
+        self.qrys = [bytes(q) for q in qrys]
+        self.ref_arr = (C.c_char_p * n)(*self.refs)
+        self.qry_arr = (C.c_char_p * n)(*self.qrys)
+        self.ref_lens = np.array([len(r) for r in self.refs], dtype=np.int32)
+        self.qry_lens = np.array([len(q) for q in self.qrys], dtype=np.int32)
+        self.row_start = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(self.qry_lens, out=self.row_start[1:])
+        self.offsets = (np.ascontiguousarray(np.concatenate([np.asarray(o, np.int32) for o in offsets]))
+                        if n else np.zeros(0, np.int32))
+        self.lengths = (np.ascontiguousarray(np.concatenate([np.asarray(l, np.int32) for l in lengths]))
+                        if n else np.zeros(0, np.int32))
+        assert self.offsets.size == self.row_start[-1] == self.lengths.size, \
+            "corridorHeight must equal the read length of every problem"
+        self.ext_qstart = np.zeros(n, np.int32) if ext_qstart is None else np.asarray(ext_qstart, np.int32)
+        self.ext_qend = np.zeros(n, np.int32) if ext_qend is None else np.asarray(ext_qend, np.int32)
+        self.read_bases = int(self.qry_lens.sum())
+
+    @classmethod
+    def from_problems(cls, problems):
+        return cls([p.ref for p in problems], [p.qry for p in problems], [p.offsets for p in problems],
+                   [p.lengths for p in problems], [p.ext_qstart for p in problems],
+                   [p.ext_qend for p in problems])
+
+    def c_args(self):
+        i32p, i64p = C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+        return (self.n, self.ref_arr, self.ref_lens.ctypes.data_as(i32p), self.qry_arr,
+                self.qry_lens.ctypes.data_as(i32p), self.offsets.ctypes.data_as(i32p),
+                self.lengths.ctypes.data_as(i32p), self.row_start.ctypes.data_as(i64p),
+                self.ext_qstart.ctypes.data_as(i32p), self.ext_qend.ctypes.data_as(i32p))
+
+
+class B200Aligner:
+    def __init__(self, gpu_id=0, scoring=DEFAULT_SCORING, stream=None):
+        self.lib = _lib.load()
+        sc = _lib.Scoring(*scoring)
+        h = C.c_void_p()
+        if self.lib.ngmlr_b200_create(gpu_id, C.byref(sc), C.byref(h)) != 0:
+            raise RuntimeError(self.lib.ngmlr_b200_last_error(None).decode())
+        self.h = h
+        if stream is not None:
+            self.lib.ngmlr_b200_set_stream(self.h, C.c_void_p(stream))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ngmlr_b200_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc < 0:
+            raise RuntimeError(self.lib.ngmlr_b200_last_error(self.h).decode())
+        return rc
+
+    # ---- IAlignment surface -------------------------------------------------------------
+    def GetScoreBatchSize(self):
+        return 1024
+
+    def GetAlignBatchSize(self):
+        return 1024
+
+    def BatchScore(self, refSeqList, qrySeqList):
+        n = len(refSeqList)
+        refs = (C.c_char_p * n)(*[bytes(r) for r in refSeqList])
+        qrys = (C.c_char_p * n)(*[bytes(q) for q in qrySeqList])
+        out = np.full(n, -1.0, dtype=np.float32)
+        self._check(self.lib.ngmlr_b200_sw_score_batch(self.h, n, refs, qrys,
+                                                       out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
+    def SingleScore(self, refSeq, qrySeq):
+        return float(self.BatchScore([refSeq], [qrySeq])[0])
+
+    def SingleAlign(self, refSeq, qrySeq, corridor_offsets, corridor_lengths, externalQStart=0,
+                    externalQEnd=0):
+        b = PackedBatch([refSeq], [qrySeq], [corridor_offsets], [corridor_lengths], [externalQStart],
+                        [externalQEnd])
+        return self.BatchAlign(b)[0]
+
+    def BatchAlign(self, batch):
+        res = (_lib.AlignResult * max(batch.n, 1))()
+        self._check(self.lib.ngmlr_b200_convex_align_batch(self.h, *batch.c_args(), res))
+        return self._collect(res, batch.n)
+
+    # ---- phased interface (bench: inputs resident in HBM) ---------------------------------
+    def upload(self, batch):
+        self._n = batch.n
+        self._check(self.lib.ngmlr_b200_convex_upload(self.h, *batch.c_args()))
+
+    def run(self):
+        self._check(self.lib.ngmlr_b200_convex_run(self.h))
+
+    def fetch(self):
+        res = (_lib.AlignResult * max(self._n, 1))()
+        self._check(self.lib.ngmlr_b200_convex_fetch(self.h, res))
+        return self._collect(res, self._n)
+
+    def stats(self):
+        s = _lib.BatchStats()
+        self._check(self.lib.ngmlr_b200_convex_stats(self.h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in s._fields_}
+
+    def force_raw(self, v):
+        self.lib.ngmlr_b200_set_force_raw(self.h, int(v))
+
+    def debug_directions(self, i, total_cells):
+        dirs = np.zeros(total_cells + 1, dtype=np.uint8)
+        bs, bx, by = C.c_float(), C.c_int32(), C.c_int32()
+        self._check(self.lib.ngmlr_b200_convex_debug_directions(
+            self.h, i, dirs.ctypes.data_as(C.POINTER(C.c_uint8)), total_cells, C.byref(bs),
+            C.byref(bx), C.byref(by)))
+        return dirs[:total_cells], bs.value, bx.value, by.value
+
+    def sw_kernel_ms(self):
+        return float(self.lib.ngmlr_b200_sw_last_kernel_ms(self.h))
+
+    @staticmethod
+    def _collect(res, n):
+        out = []
+        for i in range(n):
+            r = res[i]
+            nm = (np.ctypeslib.as_array(r.nm_positions, shape=(r.nm_count * 3,)).reshape(-1, 3).copy()
+                  if r.nm_count > 0 else np.zeros((0, 3), np.int32))
+            out.append(Align(ret=r.ret, threw=bool(r.threw), Score=float(r.score),
+                             Identity=float(r.identity), PositionOffset=r.position_offset,
+                             QStart=r.qstart, QEnd=r.qend, NM=r.nm,
+                             alignmentLength=r.alignment_length, cigarOpCount=r.cigar_op_count,
+                             svType=r.sv_type, firstPosition=(r.first_ref, r.first_read),
+                             lastPosition=(r.last_ref, r.last_read),
+                             pBuffer1=(r.cigar or b"").decode(), pBuffer2=(r.md or b"").decode(),
+                             nmPerPosition=nm, cells=r.cells))
+        return out

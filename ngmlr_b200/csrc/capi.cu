@@ -1,0 +1,695 @@
+// ngmlr_b200/csrc/capi.cu -- host runtime + plain-C ABI (include/ngmlr_b200.h).
+//
+// Owns the device arenas (sequences, corridor rows, descriptors, direction arena, traceback
+// strips), the pinned staging buffers and the stream; packs a batch of SingleAlign problems,
+// launches fill -> traceback -> compact, and turns the binary CIGARs into the reference's `Align`
+// fields. There is no CPU compute path: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/ngmlr_b200.h"
+#include "cigar_text.h"
+#include "device_types.h"
+#include "kernels.h"
+
+namespace {
+
+using namespace nb;
+
+std::string g_create_error;
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;  // elements
+  cudaError_t reserve(size_t n, bool keep = false, cudaStream_t st = 0) {
+    if (n <= cap) return cudaSuccess;
+    size_t want = std::max(n, cap + cap / 2);
+    T* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, want * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (keep && p && cap) cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, st);
+    if (p) {
+      cudaStreamSynchronize(st);
+      cudaFree(p);
+    }
+    p = q;
+    cap = want;
+    return cudaSuccess;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+template <typename T>
+struct PinBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    size_t want = std::max(n, cap + cap / 2);
+    T* q = nullptr;
+    cudaError_t e = cudaMallocHost(&q, want * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (p) cudaFreeHost(p);
+    p = q;
+    cap = want;
+    return cudaSuccess;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Scorings for which the as-coded SSE fill (raw indelRun in the run tests) can differ from the
+// scalar rule: a gap-open out of a cell that was itself reached through the *other* gap type
+// would have to tie with or beat the diagonal. Sufficient condition for equivalence, with a
+// margin far above float rounding at alignment-score magnitudes:
+//   open < 0 and max(open, ext_min) + open <= min(match, mismatch) - 0.25   (both gap kinds)
+// Default scoring (2,-5,-5,-5,-1,0.15): -6 <= -5.25 -> scalar kernel. Otherwise the RAW kernel.
+bool scoring_needs_raw(const Scoring& s) {
+  const float sub_min = std::min(s.mat, s.mis);
+  const bool ok = s.open_read < 0.0f && s.open_ref < 0.0f &&
+                  std::max(s.open_ref, s.ext_min) + s.open_read <= sub_min - 0.25f &&
+                  std::max(s.open_read, s.ext_min) + s.open_ref <= sub_min - 0.25f;
+  return !ok;
+}
+
+}  // namespace
+
+struct ngmlr_b200_ctx {
+  int device = 0;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  cudaEvent_t ev[6] = {};
+  Scoring sc{};
+  bool raw = false;
+  int force_raw = -1;
+  std::string error;
+
+  // ---- convex batch state ----
+  int n = 0;
+  size_t seq_bytes = 0, rows = 0, nblocks = 0, tb_ints = 0;
+  int max_len = 0;
+  PinBuf<uint8_t> h_seq;
+  PinBuf<int32_t> h_coff, h_clen, h_order;
+  PinBuf<AlnDesc> h_desc;
+  PinBuf<FillOut> h_fill;
+  PinBuf<TraceOut> h_trace;
+  PinBuf<int32_t> h_runs;
+  PinBuf<unsigned long long> h_counters;
+  std::vector<int32_t> ext_qs, ext_qe;
+  DevBuf<uint8_t> d_seq;
+  DevBuf<int32_t> d_coff, d_clen, d_order;
+  DevBuf<AlnDesc> d_desc;
+  DevBuf<BlockRec> d_blocks;
+  DevBuf<uint32_t> d_dir;
+  DevBuf<BndEntry> d_bnd;
+  DevBuf<FillOut> d_fill;
+  DevBuf<int32_t> d_scratch;
+  DevBuf<TraceOut> d_trace;
+  DevBuf<int32_t> d_runs;
+  DevBuf<unsigned long long> d_counters;  // [0] dir_alloc, [1] runs_alloc, [2] work counter (as int)
+  size_t dir_words_needed = 0;
+  bool ran = false;
+  unsigned long long runs_used = 0, dir_used = 0;
+  int fill_grid = 0;
+  ngmlr_b200_batch_stats stats{};
+  std::vector<AlignText> texts;
+
+  // ---- sw state ----
+  PinBuf<uint8_t> h_sw_seq;
+  PinBuf<uint64_t> h_sw_off;
+  PinBuf<int32_t> h_sw_len;
+  PinBuf<float> h_sw_out;
+  DevBuf<uint8_t> d_sw_seq;
+  DevBuf<uint64_t> d_sw_off;
+  DevBuf<int32_t> d_sw_len;
+  DevBuf<float> d_sw_out;
+  DevBuf<int32_t> d_sw_scratch;
+
+  int fail(const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    error = buf;
+    return -1;
+  }
+};
+
+#define CU(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e__ = (call);                                                             \
+    if (e__ != cudaSuccess)                                                               \
+      return ctx->fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+extern "C" {
+
+int ngmlr_b200_abi_version(void) { return NGMLR_B200_ABI_VERSION; }
+
+int ngmlr_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+const char* ngmlr_b200_last_error(const ngmlr_b200_ctx* ctx) {
+  return ctx ? ctx->error.c_str() : g_create_error.c_str();
+}
+
+int ngmlr_b200_create(int gpu_id, const ngmlr_b200_scoring* s, ngmlr_b200_ctx** out) {
+  if (!out) return -1;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    g_create_error = std::string("ngmlr_b200: no CUDA device available (") + cudaGetErrorString(e) +
+                     "); this library has no CPU fallback";
+    return -1;
+  }
+  if (gpu_id < 0 || gpu_id >= count) {
+    g_create_error = "ngmlr_b200: gpu_id out of range";
+    return -1;
+  }
+  ngmlr_b200_ctx* ctx = new ngmlr_b200_ctx();
+  ctx->device = gpu_id;
+  if ((e = cudaSetDevice(gpu_id)) != cudaSuccess) {
+    g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+    delete ctx;
+    return -1;
+  }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, gpu_id);
+  ctx->num_sms = prop.multiProcessorCount;
+  if (prop.major < 10) {
+    g_create_error = "ngmlr_b200: kernels are built for sm_100a only; device is sm_" +
+                     std::to_string(prop.major) + std::to_string(prop.minor);
+    delete ctx;
+    return -1;
+  }
+  cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+  ngmlr_b200_scoring d = {2.0f, -5.0f, -5.0f, -5.0f, -1.0f, 0.15f};
+  if (s) d = *s;
+  ctx->sc.mat = d.match;
+  ctx->sc.mis = d.mismatch;
+  ctx->sc.open_read = d.gap_open;  // gap_open_read = gap_open_ref = gapOpen (:39-40)
+  ctx->sc.open_ref = d.gap_open;
+  ctx->sc.gap_ext = d.gap_extend;
+  ctx->sc.ext_min = d.gap_extend_min;
+  ctx->sc.decay = d.gap_decay;
+  ctx->raw = scoring_needs_raw(ctx->sc);
+  *out = ctx;
+  return 0;
+}
+
+void ngmlr_b200_destroy(ngmlr_b200_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  ctx->h_seq.release(); ctx->h_coff.release(); ctx->h_clen.release(); ctx->h_order.release();
+  ctx->h_desc.release(); ctx->h_fill.release(); ctx->h_trace.release(); ctx->h_runs.release();
+  ctx->h_counters.release();
+  ctx->d_seq.release(); ctx->d_coff.release(); ctx->d_clen.release(); ctx->d_order.release();
+  ctx->d_desc.release(); ctx->d_blocks.release(); ctx->d_dir.release(); ctx->d_bnd.release();
+  ctx->d_fill.release(); ctx->d_scratch.release(); ctx->d_trace.release(); ctx->d_runs.release();
+  ctx->d_counters.release();
+  ctx->h_sw_seq.release(); ctx->h_sw_off.release(); ctx->h_sw_len.release(); ctx->h_sw_out.release();
+  ctx->d_sw_seq.release(); ctx->d_sw_off.release(); ctx->d_sw_len.release(); ctx->d_sw_out.release();
+  ctx->d_sw_scratch.release();
+  for (auto& ev : ctx->ev) cudaEventDestroy(ev);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int ngmlr_b200_set_stream(ngmlr_b200_ctx* ctx, void* s) {
+  if (!ctx) return -1;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (s) {
+    ctx->stream = (cudaStream_t)s;
+    ctx->own_stream = false;
+  } else {
+    cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    ctx->own_stream = true;
+  }
+  return 0;
+}
+
+void* ngmlr_b200_get_stream(ngmlr_b200_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+// force_raw: -1 auto (by scoring), 0 scalar-rule kernel, 1 as-coded (RAW) kernel. Test hook.
+int ngmlr_b200_set_force_raw(ngmlr_b200_ctx* ctx, int v) {
+  if (!ctx) return -1;
+  ctx->force_raw = v;
+  return 0;
+}
+
+int ngmlr_b200_convex_upload(ngmlr_b200_ctx* ctx, int n, const char* const* refs,
+                             const int32_t* ref_lens, const char* const* qrys,
+                             const int32_t* qry_lens, const int32_t* corridor_offsets,
+                             const int32_t* corridor_lengths, const int64_t* row_start,
+                             const int32_t* ext_qstart, const int32_t* ext_qend) {
+  if (!ctx) return -1;
+  if (n < 0) return ctx->fail("convex_upload: n < 0");
+  CU(cudaSetDevice(ctx->device));
+  ctx->ran = false;
+  ctx->n = n;
+  if (n == 0) return 0;
+  // ---- sizes ----
+  size_t seq_bytes = 0, rows = 0, nblocks = 0, tb_ints = 0;
+  for (int i = 0; i < n; ++i) {
+    if (ref_lens[i] < 0 || qry_lens[i] < 0) return ctx->fail("convex_upload: negative length at %d", i);
+    if (row_start[i + 1] - row_start[i] != (int64_t)qry_lens[i])
+      return ctx->fail("convex_upload: problem %d has %lld corridor rows for a %d-base read "
+                       "(corridorHeight must equal qryLen)", i,
+                       (long long)(row_start[i + 1] - row_start[i]), qry_lens[i]);
+    seq_bytes += align_up((size_t)ref_lens[i] + 64, 16) + align_up((size_t)qry_lens[i] + 64, 16);
+    rows += (size_t)qry_lens[i];
+    nblocks += ((size_t)qry_lens[i] + 31) / 32;
+  }
+  CU(ctx->h_seq.reserve(seq_bytes + 64));
+  CU(ctx->h_coff.reserve(rows + 32));
+  CU(ctx->h_clen.reserve(rows + 32));
+  CU(ctx->h_desc.reserve(n));
+  CU(ctx->h_order.reserve(n));
+  ctx->ext_qs.assign(n, 0);
+  ctx->ext_qe.assign(n, 0);
+  // ---- pack ----
+  const int64_t r0 = row_start[0];
+  if (rows) {
+    memcpy(ctx->h_coff.p, corridor_offsets + r0, rows * sizeof(int32_t));
+    memcpy(ctx->h_clen.p, corridor_lengths + r0, rows * sizeof(int32_t));
+  }
+  size_t so = 0, bo = 0;
+  int max_len_all = 0;
+  size_t dir_words = 0;
+  std::vector<unsigned long long> est(n);
+  for (int i = 0; i < n; ++i) {
+    AlnDesc& d = ctx->h_desc.p[i];
+    memset(&d, 0, sizeof(d));
+    const int rl = ref_lens[i], ql = qry_lens[i];
+    d.ref_off = so;
+    memcpy(ctx->h_seq.p + so, refs[i], rl);
+    memset(ctx->h_seq.p + so + rl, 0, align_up((size_t)rl + 64, 16) - rl);
+    so += align_up((size_t)rl + 64, 16);
+    d.qry_off = so;
+    memcpy(ctx->h_seq.p + so, qrys[i], ql);
+    memset(ctx->h_seq.p + so + ql, 0, align_up((size_t)ql + 64, 16) - ql);
+    so += align_up((size_t)ql + 64, 16);
+    d.row_off = (uint64_t)(row_start[i] - r0);
+    d.blk_off = bo;
+    bo += ((size_t)ql + 31) / 32;
+    d.ref_len = rl;
+    d.height = ql;
+    d.ref_cap = ql > 200000 ? ql + 1 : 200000;  // maxBinaryCigarLength (:480-485)
+    const long long worst = (long long)ql + rl + 4;
+    d.tb_cap = (int)std::min<long long>(worst, d.ref_cap);
+    d.tb_off = tb_ints;
+    tb_ints += (size_t)d.tb_cap;
+    const int32_t* lens = ctx->h_clen.p + d.row_off;
+    const int32_t* offs = ctx->h_coff.p + d.row_off;
+    int ml = 0;
+    unsigned long long sum = 0;
+    for (int y = 0; y < ql; ++y) {
+      ml = std::max(ml, lens[y]);
+      sum += (unsigned long long)std::max(lens[y], 0);
+    }
+    d.max_len = ml;
+    max_len_all = std::max(max_len_all, std::min(ml, rl));
+    est[i] = sum;
+    // direction arena estimate: per 32-row block, steps = row width + 31 (stagger) + corridor
+    // advance over the block; the exact figure is computed by the kernel (bump allocation) and an
+    // overflow triggers a re-run with a larger arena.
+    if (ql > 0) {
+      const long long adv_total = std::max<long long>(0, (long long)offs[ql - 1] - offs[0]);
+      const long long adv = (adv_total * 32 + std::max(ql - 1, 1) - 1) / std::max(ql - 1, 1) + 2;
+      const long long w = std::min<long long>(ml, (long long)rl);
+      const long long steps = w + 31 + adv;
+      dir_words += (size_t)(((size_t)ql + 31) / 32) * (size_t)((steps + 15) / 16 + 1) * 32;
+    }
+    if (ext_qstart) ctx->ext_qs[i] = ext_qstart[i];
+    if (ext_qend) ctx->ext_qe[i] = ext_qend[i];
+  }
+  std::iota(ctx->h_order.p, ctx->h_order.p + n, 0);
+  std::stable_sort(ctx->h_order.p, ctx->h_order.p + n,
+                   [&](int a, int b) { return est[a] > est[b]; });
+  ctx->seq_bytes = so;
+  ctx->rows = rows;
+  ctx->nblocks = bo;
+  ctx->tb_ints = tb_ints;
+  ctx->max_len = max_len_all;
+  ctx->dir_words_needed = dir_words + dir_words / 16 + 1024;
+  // ---- device arenas + H2D ----
+  cudaStream_t st = ctx->stream;
+  CU(ctx->d_seq.reserve(so + 64));
+  CU(ctx->d_coff.reserve(rows + 32));
+  CU(ctx->d_clen.reserve(rows + 32));
+  CU(ctx->d_desc.reserve(n));
+  CU(ctx->d_order.reserve(n));
+  CU(ctx->d_blocks.reserve(bo + 1));
+  CU(ctx->d_fill.reserve(n));
+  CU(ctx->d_trace.reserve(n));
+  CU(ctx->d_scratch.reserve(tb_ints + 32));
+  CU(ctx->d_runs.reserve(tb_ints / 4 + 4096));
+  CU(ctx->d_counters.reserve(4));
+  CU(ctx->h_counters.reserve(4));
+  CU(ctx->h_fill.reserve(n));
+  CU(ctx->h_trace.reserve(n));
+  CU(cudaMemcpyAsync(ctx->d_seq.p, ctx->h_seq.p, so, cudaMemcpyHostToDevice, st));
+  if (rows) {
+    CU(cudaMemcpyAsync(ctx->d_coff.p, ctx->h_coff.p, rows * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->d_clen.p, ctx->h_clen.p, rows * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  }
+  CU(cudaMemcpyAsync(ctx->d_desc.p, ctx->h_desc.p, (size_t)n * sizeof(AlnDesc), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->d_order.p, ctx->h_order.p, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  CU(cudaStreamSynchronize(st));
+  ctx->stats = ngmlr_b200_batch_stats();
+  ctx->stats.h2d_bytes = (int64_t)(so + rows * 8 + (size_t)n * (sizeof(AlnDesc) + 4));
+  ctx->stats.seq_bytes = (int64_t)so;
+  return 0;
+}
+
+int ngmlr_b200_convex_run(ngmlr_b200_ctx* ctx) {
+  if (!ctx) return -1;
+  if (ctx->n == 0) {
+    ctx->ran = true;
+    return 0;
+  }
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int n = ctx->n;
+  const bool raw = ctx->force_raw < 0 ? (ctx->raw || ctx->max_len > 32767) : (ctx->force_raw != 0);
+  static int ctas_per_sm[2] = {0, 0};
+  if (!ctas_per_sm[raw]) ctas_per_sm[raw] = std::max(1, fill_max_ctas_per_sm(raw));
+  const int max_grid = ctx->num_sms * ctas_per_sm[raw];
+  const int want_grid = (n + FILL_WARPS_PER_CTA - 1) / FILL_WARPS_PER_CTA;
+  const int grid = std::max(1, std::min(max_grid, want_grid));
+  ctx->fill_grid = grid;
+  const size_t warps = (size_t)grid * FILL_WARPS_PER_CTA;
+  const size_t bnd_stride = align_up((size_t)ctx->max_len + 2, 8);
+  CU(ctx->d_bnd.reserve(warps * 2 * bnd_stride));
+  size_t dir_words = std::max(ctx->dir_words_needed, (size_t)4096);
+  size_t runs_cap = ctx->d_runs.cap;
+
+  for (int attempt = 0; attempt < 6; ++attempt) {
+    CU(ctx->d_dir.reserve(dir_words));
+    CU(ctx->d_runs.reserve(runs_cap));
+    CU(cudaMemsetAsync(ctx->d_counters.p, 0, 4 * sizeof(unsigned long long), st));
+    FillParams fp;
+    fp.seq = ctx->d_seq.p;
+    fp.c_off = ctx->d_coff.p;
+    fp.c_len = ctx->d_clen.p;
+    fp.desc = ctx->d_desc.p;
+    fp.order = ctx->d_order.p;
+    fp.n = n;
+    fp.blocks = ctx->d_blocks.p;
+    fp.dir = ctx->d_dir.p;
+    fp.dir_capacity = ctx->d_dir.cap;
+    fp.dir_alloc = ctx->d_counters.p + 0;
+    fp.work_counter = reinterpret_cast<int*>(ctx->d_counters.p + 2);
+    fp.bnd = ctx->d_bnd.p;
+    fp.bnd_stride = bnd_stride;
+    fp.out = ctx->d_fill.p;
+    fp.sc = ctx->sc;
+    TraceParams tp;
+    tp.seq = ctx->d_seq.p;
+    tp.c_off = ctx->d_coff.p;
+    tp.c_len = ctx->d_clen.p;
+    tp.desc = ctx->d_desc.p;
+    tp.n = n;
+    tp.blocks = ctx->d_blocks.p;
+    tp.dir = ctx->d_dir.p;
+    tp.fill = ctx->d_fill.p;
+    tp.scratch = ctx->d_scratch.p;
+    tp.out = ctx->d_trace.p;
+    tp.runs = ctx->d_runs.p;
+    tp.runs_capacity = ctx->d_runs.cap;
+    tp.runs_alloc = ctx->d_counters.p + 1;
+
+    CU(cudaEventRecord(ctx->ev[0], st));
+    CU(launch_convex_fill(fp, raw, grid, st));
+    CU(cudaEventRecord(ctx->ev[1], st));
+    CU(launch_convex_traceback(tp, st));
+    CU(cudaEventRecord(ctx->ev[2], st));
+    CU(launch_convex_compact(tp, st));
+    CU(cudaEventRecord(ctx->ev[3], st));
+    CU(cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, 4 * sizeof(unsigned long long),
+                       cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    ctx->stats.fill_launches++;
+    ctx->stats.traceback_launches++;
+    ctx->stats.compact_launches++;
+    const unsigned long long dir_used = ctx->h_counters.p[0], runs_used = ctx->h_counters.p[1];
+    bool again = false;
+    if (dir_used > ctx->d_dir.cap) {
+      dir_words = (size_t)dir_used + (size_t)dir_used / 8 + 4096;
+      again = true;
+    }
+    if (runs_used > ctx->d_runs.cap) {
+      runs_cap = (size_t)runs_used + 4096;
+      again = true;
+    }
+    ctx->dir_used = dir_used;
+    ctx->runs_used = runs_used;
+    if (!again) break;
+    if (attempt == 5) return ctx->fail("convex_run: arena sizing did not converge");
+  }
+  ctx->dir_words_needed = std::max(ctx->dir_words_needed, (size_t)ctx->dir_used);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+  ctx->stats.fill_ms = ms;
+  cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]);
+  ctx->stats.traceback_ms = ms;
+  cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
+  ctx->stats.compact_ms = ms;
+  ctx->stats.dir_bytes = (int64_t)ctx->dir_used * 4;
+  ctx->stats.cigar_runs = (int64_t)ctx->runs_used;
+  ctx->ran = true;
+  return 0;
+}
+
+int ngmlr_b200_convex_fetch(ngmlr_b200_ctx* ctx, ngmlr_b200_align_result* results) {
+  if (!ctx) return -1;
+  if (!ctx->ran) return ctx->fail("convex_fetch: call convex_run first");
+  const int n = ctx->n;
+  if (n == 0) return 0;
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  CU(ctx->h_runs.reserve((size_t)ctx->runs_used + 16));
+  CU(cudaMemcpyAsync(ctx->h_fill.p, ctx->d_fill.p, (size_t)n * sizeof(FillOut), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(ctx->h_trace.p, ctx->d_trace.p, (size_t)n * sizeof(TraceOut), cudaMemcpyDeviceToHost, st));
+  if (ctx->runs_used)
+    CU(cudaMemcpyAsync(ctx->h_runs.p, ctx->d_runs.p, (size_t)ctx->runs_used * sizeof(int32_t),
+                       cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  ctx->stats.d2h_bytes = (int64_t)((size_t)n * (sizeof(FillOut) + sizeof(TraceOut)) + ctx->runs_used * 4);
+  ctx->texts.assign(n, AlignText());
+  int64_t cells = 0, steps = 0;
+  for (int i = 0; i < n; ++i) {
+    const AlnDesc& d = ctx->h_desc.p[i];
+    const FillOut& f = ctx->h_fill.p[i];
+    const TraceOut& t = ctx->h_trace.p[i];
+    ngmlr_b200_align_result& r = results[i];
+    memset(&r, 0, sizeof(r));
+    r.ret = -1;
+    r.score = -1.0f;  // align.Score = -1.0f on entry and on failure (:457, :537)
+    r.cigar = "";
+    r.md = "";
+    r.cells = (int64_t)f.cells;
+    cells += (int64_t)f.cells;
+    steps += t.steps;
+    if (t.status == ST_THROW) {
+      r.threw = 1;
+      continue;
+    }
+    if (t.status == ST_DIR_OVERFLOW) return ctx->fail("convex_fetch: internal arena overflow survived run()");
+    if (t.status != ST_OK) continue;
+    AlignText& tx = ctx->texts[i];
+    const char* ref = reinterpret_cast<const char*>(ctx->h_seq.p + d.ref_off);
+    if (!binary_cigar_to_text(ctx->h_runs.p + t.run_off, t.n_runs, ref, d.ref_len, t.ref_position,
+                              ctx->ext_qs[i], ctx->ext_qe[i], tx)) {
+      r.threw = 1;
+      continue;
+    }
+    r.ret = tx.ret;
+    r.score = f.best_score;
+    r.identity = tx.identity;
+    r.position_offset = t.ref_position;
+    r.qstart = tx.qstart;
+    r.qend = tx.qend;
+    r.nm = tx.nm;
+    r.alignment_length = tx.alignment_length;
+    r.cigar_op_count = tx.cigar_op_count;
+    r.sv_type = tx.sv_type;
+    r.first_ref = tx.first_ref;
+    r.first_read = tx.first_read;
+    r.last_ref = tx.last_ref;
+    r.last_read = tx.last_read;
+    r.nm_count = (int32_t)(tx.nm_positions.size() / 3);
+    r.cigar_len = (int32_t)tx.cigar.size();
+    r.md_len = (int32_t)tx.md.size();
+    r.cigar = tx.cigar.c_str();
+    r.md = tx.md.c_str();
+    r.nm_positions = tx.nm_positions.data();
+  }
+  ctx->stats.cells = cells;
+  ctx->stats.path_steps = steps;
+  return 0;
+}
+
+int ngmlr_b200_convex_align_batch(ngmlr_b200_ctx* ctx, int n, const char* const* refs,
+                                  const int32_t* ref_lens, const char* const* qrys,
+                                  const int32_t* qry_lens, const int32_t* corridor_offsets,
+                                  const int32_t* corridor_lengths, const int64_t* row_start,
+                                  const int32_t* ext_qstart, const int32_t* ext_qend,
+                                  ngmlr_b200_align_result* results) {
+  int rc = ngmlr_b200_convex_upload(ctx, n, refs, ref_lens, qrys, qry_lens, corridor_offsets,
+                                    corridor_lengths, row_start, ext_qstart, ext_qend);
+  if (rc) return rc;
+  rc = ngmlr_b200_convex_run(ctx);
+  if (rc) return rc;
+  return ngmlr_b200_convex_fetch(ctx, results);
+}
+
+int ngmlr_b200_convex_stats(ngmlr_b200_ctx* ctx, ngmlr_b200_batch_stats* out) {
+  if (!ctx || !out) return -1;
+  *out = ctx->stats;
+  return 0;
+}
+
+int ngmlr_b200_convex_debug_directions(ngmlr_b200_ctx* ctx, int i, uint8_t* dirs, size_t dirs_cap,
+                                       float* best_score, int32_t* best_ref, int32_t* best_read) {
+  if (!ctx) return -1;
+  if (!ctx->ran || i < 0 || i >= ctx->n) return ctx->fail("debug_directions: bad state/index");
+  CU(cudaSetDevice(ctx->device));
+  const AlnDesc& d = ctx->h_desc.p[i];
+  const int H = d.height;
+  const size_t nblk = ((size_t)H + 31) / 32;
+  std::vector<BlockRec> blocks(nblk);
+  FillOut f;
+  CU(cudaMemcpy(&f, ctx->d_fill.p + i, sizeof(f), cudaMemcpyDeviceToHost));
+  if (nblk) CU(cudaMemcpy(blocks.data(), ctx->d_blocks.p + d.blk_off, nblk * sizeof(BlockRec), cudaMemcpyDeviceToHost));
+  const int32_t* offs = ctx->h_coff.p + d.row_off;
+  const int32_t* lens = ctx->h_clen.p + d.row_off;
+  const char* ref = reinterpret_cast<const char*>(ctx->h_seq.p + d.ref_off);
+  const char* qry = reinterpret_cast<const char*>(ctx->h_seq.p + d.qry_off);
+  size_t total = 0;
+  for (int y = 0; y < H; ++y) total += (size_t)std::max(lens[y], 0);
+  if (total > dirs_cap) return ctx->fail("debug_directions: buffer too small (%zu > %zu)", total, dirs_cap);
+  memset(dirs, 0xFF, total);
+  std::vector<uint32_t> words;
+  size_t row_base = 0;
+  for (size_t b = 0; b < nblk; ++b) {
+    const BlockRec& br = blocks[b];
+    const size_t nw = (size_t)((br.nsteps + 15) / 16) * 32;
+    words.resize(nw);
+    if (nw) CU(cudaMemcpy(words.data(), ctx->d_dir.p + br.word_off, nw * 4, cudaMemcpyDeviceToHost));
+    for (int t = 0; t < 32; ++t) {
+      const int y = (int)b * 32 + t;
+      if (y >= H) break;
+      const int lo = std::max(offs[y], 0);
+      const int hi = (int)std::min<long long>((long long)offs[y] + lens[y], d.ref_len);
+      for (int x = lo; x < hi; ++x) {
+        const int s = x - br.base + t;
+        const uint32_t code = (words[(size_t)(s >> 4) * 32 + t] >> ((s & 15) * 2)) & 3u;
+        uint8_t v = OP_STOP;
+        if (code == DIR_DIAG) v = qry[y] == ref[x] ? OP_EQ : OP_X;
+        else if (code == DIR_I) v = OP_I;
+        else if (code == DIR_D) v = OP_D;
+        dirs[row_base + (size_t)(x - offs[y])] = v;
+      }
+      row_base += (size_t)std::max(lens[y], 0);
+    }
+  }
+  if (best_score) *best_score = f.best_score;
+  if (best_ref) *best_ref = f.best_x;
+  if (best_read) *best_read = f.best_y;
+  return 0;
+}
+
+int ngmlr_b200_sw_score_batch(ngmlr_b200_ctx* ctx, int n, const char* const* refs,
+                              const char* const* qrys, float* results) {
+  if (!ctx) return -1;
+  if (n <= 0) return 0;
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  CU(ctx->h_sw_off.reserve((size_t)2 * n));
+  CU(ctx->h_sw_len.reserve((size_t)2 * n));
+  CU(ctx->h_sw_out.reserve(n));
+  size_t bytes = 0;
+  int max_ref = 0, max_qry = 0;
+  for (int i = 0; i < n; ++i) {
+    const size_t rl = strlen(refs[i]) + 1, ql = strlen(qrys[i]) + 1;  // NUL included (:130-131)
+    ctx->h_sw_off.p[i] = bytes;
+    ctx->h_sw_len.p[i] = (int32_t)std::min<size_t>(rl, 1u << 30);
+    bytes += align_up(rl, 16);
+    ctx->h_sw_off.p[n + i] = bytes;
+    ctx->h_sw_len.p[n + i] = (int32_t)std::min<size_t>(ql, 1u << 30);
+    bytes += align_up(ql, 16);
+    if (rl < 100000 && ql < 100000) {
+      max_ref = std::max(max_ref, (int)rl);
+      max_qry = std::max(max_qry, (int)ql);
+    }
+  }
+  CU(ctx->h_sw_seq.reserve(bytes + 16));
+  for (int i = 0; i < n; ++i) {
+    memcpy(ctx->h_sw_seq.p + ctx->h_sw_off.p[i], refs[i], (size_t)ctx->h_sw_len.p[i]);
+    memcpy(ctx->h_sw_seq.p + ctx->h_sw_off.p[n + i], qrys[i], (size_t)ctx->h_sw_len.p[n + i]);
+  }
+  CU(ctx->d_sw_seq.reserve(bytes + 16));
+  CU(ctx->d_sw_off.reserve((size_t)2 * n));
+  CU(ctx->d_sw_len.reserve((size_t)2 * n));
+  CU(ctx->d_sw_out.reserve(n));
+  const int warps_per_cta = 4;
+  const int grid = std::max(1, std::min(ctx->num_sms * 8, (n + warps_per_cta - 1) / warps_per_cta));
+  const size_t stride = max_qry > 288 ? align_up((size_t)max_ref + 2, 4) : 4;
+  CU(ctx->d_sw_scratch.reserve((size_t)grid * warps_per_cta * stride * 2));
+  CU(cudaMemcpyAsync(ctx->d_sw_seq.p, ctx->h_sw_seq.p, bytes, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->d_sw_off.p, ctx->h_sw_off.p, (size_t)2 * n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->d_sw_len.p, ctx->h_sw_len.p, (size_t)2 * n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  SwParams sp;
+  sp.seq = ctx->d_sw_seq.p;
+  sp.ref_off = ctx->d_sw_off.p;
+  sp.qry_off = ctx->d_sw_off.p + n;
+  sp.ref_len = ctx->d_sw_len.p;
+  sp.qry_len = ctx->d_sw_len.p + n;
+  sp.out = ctx->d_sw_out.p;
+  sp.n = n;
+  sp.scratch = ctx->d_sw_scratch.p;
+  sp.scratch_stride = stride;
+  CU(cudaEventRecord(ctx->ev[4], st));
+  CU(launch_sw_score(sp, grid, st));
+  CU(cudaEventRecord(ctx->ev[5], st));
+  CU(cudaMemcpyAsync(ctx->h_sw_out.p, ctx->d_sw_out.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  memcpy(results, ctx->h_sw_out.p, (size_t)n * sizeof(float));
+  return n;
+}
+
+float ngmlr_b200_sw_last_kernel_ms(ngmlr_b200_ctx* ctx) {
+  float ms = 0;
+  if (ctx) cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]);
+  return ms;
+}
+
+}  // extern "C"

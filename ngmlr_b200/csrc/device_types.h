@@ -1,0 +1,108 @@
+// ngmlr_b200/csrc/device_types.h -- records shared between host runtime and sm_100a kernels.
+#pragma once
+#include <stdint.h>
+
+namespace nb {
+
+// Direction codes as stored in HBM: 2 bits per DP cell. EQ and X share code 0; the traceback
+// re-derives which one by comparing the two bases (raw byte equality, exactly the test the
+// reference's fill uses, src/ConvexAlignFast.cpp:657).
+enum : uint32_t { DIR_DIAG = 0, DIR_I = 1, DIR_D = 2, DIR_STOP = 3 };
+
+// Reference op codes (src/AlignmentMatrixFast.h:15-24) used in the binary CIGAR.
+enum : int { OP_I = 1, OP_D = 2, OP_S = 4, OP_EQ = 7, OP_X = 8, OP_STOP = 10 };
+
+enum : int {
+  ST_OK = 0,          // valid alignment
+  ST_INVALID = 1,     // reference returns -1 (path left corridor core / best row 0 / length mismatch)
+  ST_THROW = 2,       // reference would throw (binary CIGAR buffer exhausted)
+  ST_DIR_OVERFLOW = 3 // direction arena exhausted: host grows the arena and re-runs
+};
+
+struct Scoring {
+  float mat, mis, open_read, open_ref, gap_ext, ext_min, decay;
+};
+
+// One alignment problem (SingleAlign call). Offsets index the batch-wide arrays.
+struct alignas(16) AlnDesc {
+  uint64_t ref_off;   // byte offset of refSeq in the sequence arena (16-byte aligned)
+  uint64_t qry_off;   // byte offset of qrySeq
+  uint64_t row_off;   // first row in corridor_off[] / corridor_len[]
+  uint64_t blk_off;   // first BlockRec of this problem
+  uint64_t tb_off;    // first int of this problem's traceback scratch
+  int32_t ref_len;
+  int32_t height;     // rows = qryLen = corridorHeight
+  int32_t tb_cap;     // ints of traceback scratch
+  int32_t ref_cap;    // reference's binaryCigar capacity: max(200000, qryLen+1)  (:480-485)
+  int32_t max_len;    // max corridor row length
+  int32_t pad0, pad1, pad2;
+};
+
+// One 32-row block of a problem: where its direction words live and how steps map to columns.
+// Cell (x, y) of row y = 32*b + t was computed at step s = x - base + t; its 2-bit code is
+//   dir[word_off + (s >> 4) * 32 + t] >> ((s & 15) * 2).
+struct alignas(16) BlockRec {
+  uint64_t word_off;
+  int32_t base;
+  int32_t nsteps;
+};
+
+// Boundary row handed from lane 31 of one block to lane 0 of the next (through L2).
+struct alignas(16) BndEntry {
+  float S;        // score of the cell
+  float U;        // what the cell below receives as up_cell
+  uint32_t pack;  // run (low 16) | dir << 16
+  uint32_t pad;
+};
+
+struct alignas(16) FillOut {
+  float best_score;
+  int32_t best_x, best_y;
+  int32_t status;
+  unsigned long long cells;
+};
+
+struct alignas(16) TraceOut {
+  int32_t status;
+  int32_t n_runs;        // entries in the compact binary CIGAR incl. both clip entries
+  int32_t ref_position;  // FwdResults::ref_position
+  int32_t qstart, qend;
+  int32_t steps;
+  unsigned long long run_off;  // offset of the runs in the compact arena
+};
+
+struct FillParams {
+  const uint8_t* seq;
+  const int32_t* c_off;
+  const int32_t* c_len;
+  const AlnDesc* desc;
+  const int32_t* order;   // problem indices, largest first
+  int n;
+  BlockRec* blocks;
+  uint32_t* dir;                        // direction arena (32-bit words)
+  unsigned long long dir_capacity;      // words
+  unsigned long long* dir_alloc;        // bump pointer
+  int* work_counter;
+  BndEntry* bnd;                        // per-warp scratch: 2 * bnd_stride entries each
+  unsigned long long bnd_stride;
+  FillOut* out;
+  Scoring sc;
+};
+
+struct TraceParams {
+  const uint8_t* seq;
+  const int32_t* c_off;
+  const int32_t* c_len;
+  const AlnDesc* desc;
+  int n;
+  const BlockRec* blocks;
+  const uint32_t* dir;
+  const FillOut* fill;
+  int32_t* scratch;
+  TraceOut* out;
+  int32_t* runs;                       // compact arena
+  unsigned long long runs_capacity;
+  unsigned long long* runs_alloc;
+};
+
+}  // namespace nb

@@ -1,0 +1,32 @@
+// ngmlr_b200/csrc/kernels.h -- launchers of the sm_100a kernels (host-callable).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "device_types.h"
+
+namespace nb {
+
+constexpr int FILL_WARPS_PER_CTA = 4;
+constexpr int FILL_CTAS_PER_SM = 4;
+
+cudaError_t launch_convex_fill(const FillParams& p, bool raw, int grid, cudaStream_t stream);
+int fill_max_ctas_per_sm(bool raw);
+
+cudaError_t launch_convex_traceback(const TraceParams& p, cudaStream_t stream);
+cudaError_t launch_convex_compact(const TraceParams& p, cudaStream_t stream);
+
+// StrippedSW score-only kernel: one warp per (ref, qry) pair.
+struct SwParams {
+  const uint8_t* seq;          // arena holding all strings, NUL included
+  const uint64_t* ref_off;
+  const uint64_t* qry_off;
+  const int32_t* ref_len;      // strlen + 1 (the NUL is scored, StrippedSW.cpp:130-146)
+  const int32_t* qry_len;
+  float* out;
+  int n;
+  int32_t* scratch;            // per-warp H/E rows for queries longer than the register tile
+  unsigned long long scratch_stride;
+};
+cudaError_t launch_sw_score(const SwParams& p, int grid, cudaStream_t stream);
+
+}  // namespace nb

@@ -1,0 +1,221 @@
+// ngmlr_b200/csrc/plugin.cpp -- the IAlignment object behind ngmlr's plugin boundary.
+//
+// `class B200Alignment : public IAlignment` (interface: src/IAlignment.h:211-247) is what
+// CreateAlignment(gpu_id) returns. It serves both construction sites of the reference:
+//   * the convex aligner of AlignmentBuffer (src/AlignmentBuffer.h:345-363) -> SingleAlign with
+//     CorridorLine[] (ConvexAlignFast::SingleAlign, src/ConvexAlignFast.cpp:452-559), plus a real
+//     BatchAlign (the reference throws "Not implemented", :441-450);
+//   * the scorer of ScoreBuffer / NGM::CreateAlignment (src/NGM.cpp:350-362) -> BatchScore /
+//     SingleScore (StrippedSW, src/StrippedSW.cpp:118-202); GetScoreBatchSize() = 1024 like
+//     StrippedSW.h:53-55.
+// Argument meaning, buffer ownership and error behaviour follow SURVEY.md section 8(b).
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/ngmlr_b200.h"
+#include "../../include/ngmlr_b200_ialignment.h"
+
+namespace {
+
+ngmlr_b200_scoring g_scoring = {2.0f, -5.0f, -5.0f, -5.0f, -1.0f, 0.15f};
+
+class B200Alignment : public IAlignment {
+ public:
+  explicit B200Alignment(int gpu_id) {
+    if (ngmlr_b200_create(gpu_id, &g_scoring, &ctx_) != 0) ctx_ = nullptr;
+  }
+  ~B200Alignment() override { ngmlr_b200_destroy(ctx_); }
+  bool ok() const { return ctx_ != nullptr; }
+
+  int GetScoreBatchSize() const override { return 1024; }
+  int GetAlignBatchSize() const override { return 1024; }
+
+  int BatchScore(int const, int const batchSize, char const* const* const refSeqList,
+                 char const* const* const qrySeqList, float* const results, void*) override {
+    if (batchSize <= 0) return 0;
+    int rc = ngmlr_b200_sw_score_batch(ctx_, batchSize, refSeqList, qrySeqList, results);
+    if (rc < 0) throw ngmlr_b200_last_error(ctx_);
+    return rc;
+  }
+
+  int SingleScore(int const, int const, char const* const refSeq, char const* const qrySeq,
+                  float& result, void*) override {
+    float r = -1.0f;
+    int rc = ngmlr_b200_sw_score_batch(ctx_, 1, &refSeq, &qrySeq, &r);
+    if (rc < 0) throw ngmlr_b200_last_error(ctx_);
+    result = r;
+    return r == -1.0f ? 0 : 1;  // StrippedSW::SingleScore returns 0 for over-long input (:175-178)
+  }
+
+  // The (mode, int corridor) overload is "not implemented" in the reference (:561-567).
+  int SingleAlign(int const, int const, char const* const, char const* const, Align&, void*) override {
+    throw "Not implemented";
+  }
+
+  int SingleAlign(int const mode, CorridorLine* corridor, int const corridorHeight,
+                  char const* const refSeq, char const* const qrySeq, Align& result,
+                  int const externalQStart, int const externalQEnd, void*) override {
+    NgmlrB200BatchAlignArgs a = {corridor, corridorHeight, externalQStart, externalQEnd};
+    int ret = -1;
+    align_many(1, &refSeq, &qrySeq, &result, &a, &ret);
+    return ret;
+  }
+
+  // extData: NgmlrB200BatchAlignArgs[batchSize]. Returns batchSize; per-problem results (and the
+  // SingleAlign return value in Align::alignmentLength's sibling... see below) are in results[i].
+  int BatchAlign(int const, int const batchSize, char const* const* const refSeqList,
+                 char const* const* const qrySeqList, Align* const results, void* extData) override {
+    if (batchSize <= 0) return 0;
+    if (!extData) throw "BatchAlign: extData must point to NgmlrB200BatchAlignArgs[batchSize]";
+    std::vector<int> rets(batchSize);
+    align_many(batchSize, refSeqList, qrySeqList, results,
+               static_cast<NgmlrB200BatchAlignArgs*>(extData), rets.data());
+    // A failed problem is reported exactly like SingleAlign does: Score == -1.0f.
+    return batchSize;
+  }
+
+ private:
+  void align_many(int n, char const* const* refs, char const* const* qrys, Align* results,
+                  NgmlrB200BatchAlignArgs* args, int* rets) {
+    ref_len_.resize(n);
+    qry_len_.resize(n);
+    row_start_.resize(n + 1);
+    qs_.resize(n);
+    qe_.resize(n);
+    size_t rows = 0;
+    for (int i = 0; i < n; ++i) {
+      ref_len_[i] = (int32_t)strlen(refs[i]);  // lengths by strlen (:463-464)
+      qry_len_[i] = (int32_t)strlen(qrys[i]);
+      row_start_[i] = (int64_t)rows;
+      rows += (size_t)qry_len_[i];
+      qs_[i] = args[i].externalQStart;
+      qe_[i] = args[i].externalQEnd;
+    }
+    row_start_[n] = (int64_t)rows;
+    off_.resize(rows);
+    len_.resize(rows);
+    for (int i = 0; i < n; ++i) {
+      // matrix->prepare(): rows = qryLen; also publishes offsetInMatrix to the caller's lines
+      // (src/AlignmentMatrixFast.cpp:36-43)
+      CorridorLine* c = args[i].corridor;
+      int32_t* o = off_.data() + row_start_[i];
+      int32_t* l = len_.data() + row_start_[i];
+      unsigned long at = 0;
+      const int h = args[i].corridorHeight;
+      for (int y = 0; y < h; ++y) {
+        c[y].offsetInMatrix = at;
+        at += (unsigned long)c[y].length;
+      }
+      if (h < qry_len_[i]) throw "corridorHeight < read length";
+      for (int y = 0; y < qry_len_[i]; ++y) {
+        o[y] = c[y].offset;
+        l[y] = c[y].length;
+      }
+      // prepare() refuses matrices of >= maxMatrixSizeMB (10000) MB -> alignment fails (:45-58)
+      too_big_.push_back((unsigned long)((float)at / 1000.0f / 1000.0f) >= 10000ul);
+    }
+    res_.resize(n);
+    for (int i = 0; i < n; ++i) {
+      results[i].svType = 0;  // (:454-457)
+      results[i].Score = -1.0f;
+      rets[i] = -1;
+    }
+    int rc = ngmlr_b200_convex_align_batch(ctx_, n, refs, ref_len_.data(), qrys, qry_len_.data(),
+                                           off_.data(), len_.data(), row_start_.data(), qs_.data(),
+                                           qe_.data(), res_.data());
+    if (rc != 0) {
+      too_big_.clear();
+      throw ngmlr_b200_last_error(ctx_);
+    }
+    bool threw = false;
+    for (int i = 0; i < n; ++i) {
+      const ngmlr_b200_align_result& r = res_[i];
+      Align& a = results[i];
+      if (too_big_[i]) continue;
+      if (a.pBuffer2) a.pBuffer2[0] = '\0';  // (:469)
+      if (r.threw) {
+        threw = true;
+        continue;
+      }
+      if (r.ret < 0) continue;
+      // caller-owned buffers; grow MD / nmPerPosition like checkMdBufferLength / addPosition do
+      if (r.cigar_len + 1 > a.maxBufferLength || !a.pBuffer1) {
+        threw = true;  // "CIGAR/MD buffer not long enough" -> throw 1 (:289-294)
+        continue;
+      }
+      memcpy(a.pBuffer1, r.cigar, (size_t)r.cigar_len + 1);
+      if (r.md_len + 1 > a.maxMdBufferLength || !a.pBuffer2) {
+        int cap = a.maxMdBufferLength > 0 ? a.maxMdBufferLength : 1024;
+        while (cap < r.md_len + 1) cap *= 2;
+        delete[] a.pBuffer2;
+        a.pBuffer2 = new char[cap];
+        a.maxMdBufferLength = cap;
+      }
+      memcpy(a.pBuffer2, r.md, (size_t)r.md_len + 1);
+      if (r.nm_count > a.nmPerPostionLength || !a.nmPerPosition) {
+        int cap = a.nmPerPostionLength > 0 ? a.nmPerPostionLength : 64;
+        while (cap < r.nm_count) cap *= 2;
+        delete[] a.nmPerPosition;
+        a.nmPerPosition = new PositionNM[cap];
+        a.nmPerPostionLength = cap;
+      }
+      for (int k = 0; k < r.nm_count; ++k) {
+        a.nmPerPosition[k].refPosition = r.nm_positions[3 * k + 0];
+        a.nmPerPosition[k].readPosition = r.nm_positions[3 * k + 1];
+        a.nmPerPosition[k].nm = r.nm_positions[3 * k + 2];
+      }
+      a.QStart = r.qstart;
+      a.QEnd = r.qend;
+      a.firstPosition.refPosition = r.first_ref;
+      a.firstPosition.readPosition = r.first_read;
+      a.lastPosition.refPosition = r.last_ref;
+      a.lastPosition.readPosition = r.last_read;
+      a.Identity = r.identity;
+      a.NM = r.nm;
+      a.alignmentLength = r.alignment_length;
+      a.cigarOpCount = r.cigar_op_count;
+      a.PositionOffset = r.position_offset;
+      a.Score = r.score;
+      a.svType = r.sv_type;
+      rets[i] = r.ret;
+    }
+    too_big_.clear();
+    if (threw && n == 1) throw 1;  // caller wraps SingleAlign in try/catch(...) -> unmapped
+  }
+
+  ngmlr_b200_ctx* ctx_ = nullptr;
+  std::vector<int32_t> ref_len_, qry_len_, off_, len_, qs_, qe_;
+  std::vector<int64_t> row_start_;
+  std::vector<ngmlr_b200_align_result> res_;
+  std::vector<bool> too_big_;
+};
+
+}  // namespace
+
+extern "C" {
+
+IAlignment* CreateAlignment(int const gpu_id) {
+  B200Alignment* a = new B200Alignment(gpu_id);
+  if (!a->ok()) {  // fail loudly: no CPU fallback
+    delete a;
+    return nullptr;
+  }
+  return a;
+}
+
+void DeleteAlignment(IAlignment* aligner) { delete aligner; }
+
+void SetAlignmentScoring(float match, float mismatch, float gapOpen, float gapExtend,
+                         float gapExtendMin, float gapDecay) {
+  g_scoring.match = match;
+  g_scoring.mismatch = mismatch;
+  g_scoring.gap_open = gapOpen;
+  g_scoring.gap_extend = gapExtend;
+  g_scoring.gap_extend_min = gapExtendMin;
+  g_scoring.gap_decay = gapDecay;
+}
+
+int ngmlr_b200_plugin_cookie(void) { return 0x10201130; }  // cCookie, src/IAlignment.h:193
+
+}  // extern "C"

@@ -1,0 +1,125 @@
+// ngmlr_b200/csrc/sw_score.cu -- score-only local alignment of sub-read x candidate pairs (sm_100a).
+//
+// Replaces StrippedSW::BatchScore / SingleScore (src/StrippedSW.cpp:118-202) and the part of the
+// vendored SSW library they reach: ssw_init -> qP_word, ssw_align(flag=0) -> sw_sse2_word
+// (lib/Complete-Striped-Smith-Waterman-Library/src/ssw.c:964-989, 342-364, 997-1054, 366-538).
+//
+// Semantics kept bit-for-bit:
+//   * both sequences are scored INCLUDING their terminating NUL (lengths are strlen+1); the NUL
+//     and every non-ACGT byte map to code 4, which scores 0 against everything;
+//   * +1 match / -1 mismatch; gap open = gap extend = 255 (int32 -1 narrowed to uint8_t);
+//   * H = max(diag + s, E, F) with signed-saturating 16-bit adds; E/F updates use unsigned
+//     saturating subtraction (clamp at 0); result = max H as uint16 -> float.
+//
+// Mapping: one warp per pair. Lane t owns SW_ROWS consecutive query rows; the warp sweeps the
+// reference columns as a wavefront (lane t is one column behind lane t-1), passing the H and F of
+// its last row down with __shfl_up. Queries longer than 32*SW_ROWS rows are processed in several
+// passes; the bottom row of a pass is carried to the next through a per-warp strip in global
+// memory. 32-bit integer lanes emulate the int16 saturation (values never exceed 32767).
+#include <cuda_runtime.h>
+
+#include "device_types.h"
+#include "kernels.h"
+
+namespace nb {
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int SW_ROWS = 9;  // 32 * 9 = 288 >= 257 = 256-bp sub-read + NUL: one pass for the hot case
+constexpr int SW_GAP = 255;
+constexpr int SW_WARPS_PER_CTA = 4;
+
+__device__ __forceinline__ int nt_code(uint32_t c) {
+  // nt_table, src/StrippedSW.cpp:111-116
+  c &= 0xdfu;  // fold case
+  return c == 'A' ? 0 : (c == 'C' ? 1 : (c == 'G' ? 2 : (c == 'T' ? 3 : 4)));
+}
+
+__global__ void __launch_bounds__(SW_WARPS_PER_CTA * 32) sw_score_kernel(const SwParams p) {
+  const int lane = threadIdx.x & 31;
+  const int warp_global = blockIdx.x * SW_WARPS_PER_CTA + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * SW_WARPS_PER_CTA;
+  int2* strip = reinterpret_cast<int2*>(p.scratch) + (size_t)warp_global * p.scratch_stride;
+
+  for (int pair = warp_global; pair < p.n; pair += nwarps) {
+    const int qlen = p.qry_len[pair], rlen = p.ref_len[pair];
+    if (qlen >= 100000 || rlen >= 100000) {  // maxSeqLen, src/StrippedSW.h:88
+      if (lane == 0) p.out[pair] = -1.0f;
+      continue;
+    }
+    const uint8_t* __restrict__ ref = p.seq + p.ref_off[pair];
+    const uint8_t* __restrict__ qry = p.seq + p.qry_off[pair];
+    int best = 0;
+    const int rows_per_pass = 32 * SW_ROWS;
+    for (int row_base = 0; row_base < qlen; row_base += rows_per_pass) {
+      const bool first_pass = row_base == 0;
+      const bool last_pass = row_base + rows_per_pass >= qlen;
+      const int row0 = row_base + lane * SW_ROWS;
+      int qc[SW_ROWS], H[SW_ROWS], E[SW_ROWS];
+#pragma unroll
+      for (int r = 0; r < SW_ROWS; ++r) {
+        const int row = row0 + r;
+        // the NUL at qlen-1 is part of the query and maps to 4; rows >= qlen do not exist (-1)
+        qc[r] = row < qlen ? nt_code(qry[row]) : -1;
+        H[r] = 0;
+        E[r] = 0;
+      }
+      int outH = 0, outF = 0, diagTop = 0;
+      const int nsteps = rlen + 31;
+      for (int s = 0; s < nsteps; ++s) {
+        const int c = s - lane;
+        int upH = __shfl_up_sync(FULL, outH, 1);
+        int upF = __shfl_up_sync(FULL, outF, 1);
+        const bool in = c >= 0 && c < rlen;
+        if (lane == 0) {
+          upH = 0;
+          upF = 0;
+          if (!first_pass && in) {
+            const int2 v = __ldcg(strip + c);
+            upH = v.x;
+            upF = v.y;
+          }
+        }
+        if (in) {
+          const int rc = nt_code(ref[c]);
+          int diag = diagTop;
+          diagTop = upH;
+          int F = upF;
+#pragma unroll
+          for (int r = 0; r < SW_ROWS; ++r) {
+            const int hOld = H[r];
+            const int sub = ((rc | qc[r]) & 4) ? 0 : (rc == qc[r] ? 1 : -1);
+            int h = min(diag + sub, 32767);      // _mm_adds_epi16
+            h = max(h, E[r]);
+            h = max(h, F);
+            if (qc[r] < 0) h = 0;                // row beyond the query
+            best = max(best, h);
+            H[r] = h;
+            const int hg = max(h - SW_GAP, 0);   // _mm_subs_epu16
+            E[r] = max(max(E[r] - SW_GAP, 0), hg);
+            F = max(max(F - SW_GAP, 0), hg);
+            diag = hOld;
+          }
+          outH = H[SW_ROWS - 1];
+          outF = F;
+          if (lane == 31 && !last_pass) __stcg(strip + c, make_int2(outH, outF));
+        }
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(FULL, best, o));
+    if (lane == 0) p.out[pair] = (float)(best & 0xffff);
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_sw_score(const SwParams& p, int grid, cudaStream_t stream) {
+  if (p.n <= 0) return cudaSuccess;
+  sw_score_kernel<<<grid, SW_WARPS_PER_CTA * 32, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace nb
