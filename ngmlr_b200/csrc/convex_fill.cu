@@ -101,7 +101,9 @@ convex_fill_kernel(const FillParams p) {
       const long long hi64 = (long long)off + (long long)len;
       const int xhi = hi64 < (long long)ref_len ? (int)hi64 : ref_len;
       const unsigned rlen = xhi > xlo ? (unsigned)(xhi - xlo) : 0u;
-      const int lo_key = rlen ? xlo + lane : INT_MAX;
+      // base = leftmost column of the block: lane t first becomes active at step >= t, i.e. after the
+      // reference byte for its column has travelled down the shuffle chain from lane 0
+      const int lo_key = rlen ? xlo : INT_MAX;
       const int hi_key = rlen ? xhi + lane : INT_MIN;
       int base = __reduce_min_sync(FULL, lo_key);
       const int send = __reduce_max_sync(FULL, hi_key);
