@@ -75,6 +75,11 @@ struct PinBuf {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// bytes readable past the end of every staged sequence (the fill kernel stages whole 64-column
+// chunks, see convex_fill.cu) and slack of the per-warp boundary strip
+constexpr size_t SEQ_PAD = 192;
+constexpr size_t STRIP_SLACK = 192;
+
 // Scorings for which the as-coded SSE fill (raw indelRun in the run tests) can differ from the
 // scalar rule: a gap-open out of a cell that was itself reached through the *other* gap type
 // would have to tie with or beat the diagonal. Sufficient condition for equivalence, with a
@@ -106,6 +111,7 @@ struct ngmlr_b200_ctx {
   int n = 0;
   size_t seq_bytes = 0, rows = 0, nblocks = 0, tb_ints = 0;
   int max_len = 0;
+  int max_ref_len = 0;
   PinBuf<uint8_t> h_seq;
   PinBuf<int32_t> h_coff, h_clen, h_order;
   PinBuf<AlnDesc> h_desc;
@@ -283,7 +289,7 @@ int ngmlr_b200_convex_upload(ngmlr_b200_ctx* ctx, int n, const char* const* refs
       return ctx->fail("convex_upload: problem %d has %lld corridor rows for a %d-base read "
                        "(corridorHeight must equal qryLen)", i,
                        (long long)(row_start[i + 1] - row_start[i]), qry_lens[i]);
-    seq_bytes += align_up((size_t)ref_lens[i] + 64, 16) + align_up((size_t)qry_lens[i] + 64, 16);
+    seq_bytes += align_up((size_t)ref_lens[i] + SEQ_PAD, 16) + align_up((size_t)qry_lens[i] + SEQ_PAD, 16);
     rows += (size_t)qry_lens[i];
     nblocks += ((size_t)qry_lens[i] + 31) / 32;
   }
@@ -301,6 +307,7 @@ int ngmlr_b200_convex_upload(ngmlr_b200_ctx* ctx, int n, const char* const* refs
     memcpy(ctx->h_clen.p, corridor_lengths + r0, rows * sizeof(int32_t));
   }
   size_t so = 0, bo = 0;
+  ctx->max_ref_len = 0;
   int max_len_all = 0;
   size_t dir_words = 0;
   std::vector<unsigned long long> est(n);
@@ -310,12 +317,12 @@ int ngmlr_b200_convex_upload(ngmlr_b200_ctx* ctx, int n, const char* const* refs
     const int rl = ref_lens[i], ql = qry_lens[i];
     d.ref_off = so;
     memcpy(ctx->h_seq.p + so, refs[i], rl);
-    memset(ctx->h_seq.p + so + rl, 0, align_up((size_t)rl + 64, 16) - rl);
-    so += align_up((size_t)rl + 64, 16);
+    memset(ctx->h_seq.p + so + rl, 0, align_up((size_t)rl + SEQ_PAD, 16) - rl);
+    so += align_up((size_t)rl + SEQ_PAD, 16);
     d.qry_off = so;
     memcpy(ctx->h_seq.p + so, qrys[i], ql);
-    memset(ctx->h_seq.p + so + ql, 0, align_up((size_t)ql + 64, 16) - ql);
-    so += align_up((size_t)ql + 64, 16);
+    memset(ctx->h_seq.p + so + ql, 0, align_up((size_t)ql + SEQ_PAD, 16) - ql);
+    so += align_up((size_t)ql + SEQ_PAD, 16);
     d.row_off = (uint64_t)(row_start[i] - r0);
     d.blk_off = bo;
     bo += ((size_t)ql + 31) / 32;
@@ -336,6 +343,7 @@ int ngmlr_b200_convex_upload(ngmlr_b200_ctx* ctx, int n, const char* const* refs
     }
     d.max_len = ml;
     max_len_all = std::max(max_len_all, std::min(ml, rl));
+    ctx->max_ref_len = std::max(ctx->max_ref_len, rl);
     est[i] = sum;
     // direction arena estimate: per 32-row block, steps = row width + 31 (stagger) + corridor
     // advance over the block; the exact figure is computed by the kernel (bump allocation) and an
@@ -406,8 +414,8 @@ int ngmlr_b200_convex_run(ngmlr_b200_ctx* ctx) {
   const int grid = std::max(1, std::min(max_grid, want_grid));
   ctx->fill_grid = grid;
   const size_t warps = (size_t)grid * FILL_WARPS_PER_CTA;
-  const size_t bnd_stride = align_up((size_t)ctx->max_len + 2, 8);
-  CU(ctx->d_bnd.reserve(warps * 2 * bnd_stride));
+  const size_t bnd_stride = align_up((size_t)ctx->max_ref_len + STRIP_SLACK, 8);
+  CU(ctx->d_bnd.reserve(warps * bnd_stride));
   size_t dir_words = std::max(ctx->dir_words_needed, (size_t)4096);
   size_t runs_cap = ctx->d_runs.cap;
 

@@ -12,8 +12,12 @@
 //   left (x-1, y)    = this lane's previous cell             -> registers
 // The rolling rows of the reference (2 x W x 8 B, AlignmentMatrixFast.h:34-54) therefore never
 // leave the register file. Row 32*b+31 is handed to lane 0 of the next block through a per-warp
-// double-buffered strip in global memory that stays in L2 (one 16-byte store by lane 31 and one
-// 16-byte load by lane 0 per step, the load prefetched one step ahead).
+// strip in global memory indexed by absolute column (it stays in L2; ~16 B/column/block), staged
+// through shared memory in 64-step chunks: all 32 lanes copy a chunk of the strip (+ the reference
+// bytes for those columns, merged into the same 16-byte records) into shared memory one chunk
+// ahead, lane 0 then needs a single LDS.128 per step and lane 31 a single STS.128; finished
+// chunks are flushed back coalesced. Because lane 31 always trails lane 0 by 31 columns the strip
+// is updated in place for any corridor shape.
 //
 // HBM traffic. The only per-cell output is the traceback direction: 2 bits per cell (EQ/X are
 // re-derived by the traceback), 16 steps per 32-bit word, written as one fully coalesced 128-byte
@@ -37,33 +41,32 @@ namespace nb {
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int CHUNK = 64;        // steps staged through shared memory at a time
+constexpr int STRIP_PAD = 32;    // strip index = column + STRIP_PAD (lane 31 trails lane 0 by 31)
 
-__device__ __forceinline__ BndEntry ld_bnd(const BndEntry* p) {
-  uint4 v = __ldcg(reinterpret_cast<const uint4*>(p));
-  BndEntry e;
-  e.S = __uint_as_float(v.x);
-  e.U = __uint_as_float(v.y);
-  e.pack = v.z;
-  e.pad = 0;
-  return e;
-}
-
-__device__ __forceinline__ void st_bnd(BndEntry* p, float S, float U, uint32_t pack) {
-  __stcg(reinterpret_cast<uint4*>(p), make_uint4(__float_as_uint(S), __float_as_uint(U), pack, 0u));
-}
+__device__ __forceinline__ uint4 ld_strip(const uint4* p) { return __ldcg(p); }
+__device__ __forceinline__ void st_strip(uint4* p, uint4 v) { __stcg(p, v); }
 
 template <bool RAW>
 __global__ void __launch_bounds__(FILL_WARPS_PER_CTA * 32, FILL_CTAS_PER_SM)
 convex_fill_kernel(const FillParams p) {
+  __shared__ uint4 s_in[FILL_WARPS_PER_CTA][CHUNK];
+  __shared__ uint4 s_out[FILL_WARPS_PER_CTA][CHUNK];
   const int lane = threadIdx.x & 31;
-  const int warp_global = blockIdx.x * FILL_WARPS_PER_CTA + (threadIdx.x >> 5);
-  BndEntry* const bnd0 = p.bnd + (size_t)warp_global * 2 * p.bnd_stride;
+  const int wib = threadIdx.x >> 5;
+  const int warp_global = blockIdx.x * FILL_WARPS_PER_CTA + wib;
+  uint4* const in_s = s_in[wib];
+  uint4* const out_s = s_out[wib];
+  // strip[x + STRIP_PAD] = {S, U, pack, -} of column x of the last finished block's bottom row
+  uint4* const strip = reinterpret_cast<uint4*>(p.bnd) + (size_t)warp_global * p.bnd_stride + STRIP_PAD;
   const Scoring sc = p.sc;
   const uint32_t empty_pack = RAW ? (DIR_STOP << 16) : 0u;
+  const uint4 EMPTY = make_uint4(0u, __float_as_uint(sc.open_read), empty_pack, 0u);
+  const bool is0 = lane == 0, is31 = lane == 31;
 
   for (;;) {
     int w = 0;
-    if (lane == 0) w = atomicAdd(p.work_counter, 1);
+    if (is0) w = atomicAdd(p.work_counter, 1);
     w = __shfl_sync(FULL, w, 0);
     if (w >= p.n) break;
     const int ai = p.order[w];
@@ -80,21 +83,30 @@ convex_fill_kernel(const FillParams p) {
     unsigned long long cells = 0;
     int status = ST_OK;
 
-    // Row above the first block does not exist: an empty boundary (sentinel at index 0).
-    int pxlo = 0;
-    unsigned plen = 0;
-    int cur = 0;
-    if (lane == 0) st_bnd(bnd0, 0.0f, sc.open_read, empty_pack);
-    __syncwarp();
+    // columns of the strip that hold valid records of the row above the current block
+    int wlo = 0, whi = 0;  // nothing written yet: the row above block 0 does not exist
+
+    // rows of the next block are fetched one block ahead
+    int n_off = 0, n_len = 0;
+    uint32_t n_q = 0x100u;  // never equals a byte
+    if (lane < H) {
+      n_off = coff[lane];
+      n_len = clen[lane];
+      n_q = qry[lane];
+    }
 
     for (int b = 0; b < nblk; ++b) {
       const int y = (b << 5) + lane;
-      int off = 0, len = 0;
-      uint32_t q = 0x100u;  // never equals a byte
-      if (y < H) {
-        off = coff[y];
-        len = clen[y];
-        q = qry[y];
+      const int off = n_off, len = n_len;
+      const uint32_t q = n_q;
+      {
+        const int yn = y + 32;
+        n_off = 0; n_len = 0; n_q = 0x100u;
+        if (yn < H) {
+          n_off = coff[yn];
+          n_len = clen[yn];
+          n_q = qry[yn];
+        }
       }
       // columns of this row: [max(0,off), min(off+len, refLen))   (:943-950)
       const int xlo = off > 0 ? off : 0;
@@ -110,10 +122,11 @@ convex_fill_kernel(const FillParams p) {
       int nsteps = 0;
       if (base != INT_MAX) nsteps = send - base; else base = 0;
       const int ngroups = (nsteps + 15) >> 4;
+      const int nchunks = (ngroups + 3) >> 2;
       cells += rlen;
 
       unsigned long long word_off = 0;
-      if (lane == 0) {
+      if (is0) {
         word_off = atomicAdd(p.dir_alloc, (unsigned long long)ngroups * 32ull);
         BlockRec br;
         br.word_off = word_off;
@@ -127,12 +140,20 @@ convex_fill_kernel(const FillParams p) {
         break;
       }
       uint32_t* __restrict__ dwp = p.dir + word_off + lane;
-      const BndEntry* bin = bnd0 + (size_t)cur * p.bnd_stride;
-      BndEntry* bout = bnd0 + (size_t)(cur ^ 1) * p.bnd_stride;
 
-      int rel = base - lane - xlo;  // x - xlo at step 0; the cell is inside the corridor iff (unsigned)rel < rlen
-      const int t0rel = (int)rlen > 12 ? (int)rlen - 12 : 0;  // tail start max(x0, xMax-12) relative to xlo (:1179)
-      int brel = base - pxlo;       // lane 0: index of column `base` in the boundary strip
+      // The strip must hold a record of the row above for every column lane 0 will visit,
+      // [base-1, base + nchunks*64): what the previous block did not write is EMPTY.
+      {
+        const int need_lo = base - 1, need_hi = base + nchunks * CHUNK;
+        const int l_hi = wlo < need_hi ? wlo : need_hi;
+        for (int x = need_lo + lane; x < l_hi; x += 32) st_strip(strip + x, EMPTY);
+        const int r_lo = whi > need_lo ? whi : need_lo;
+        for (int x = r_lo + lane; x < need_hi; x += 32) st_strip(strip + x, EMPTY);
+      }
+      __syncwarp();
+
+      int rel = base - lane - xlo;  // x - xlo at step 0; inside the corridor iff (unsigned)rel < rlen
+      const int t0rel = (int)rlen > 12 ? (int)rlen - 12 : 0;  // tail start max(x0, xMax-12) - xlo (:1179)
 
       float oS = 0.0f, oU = sc.open_read;  // what this lane hands down: EMPTY = {0,0,STOP}
       uint32_t oPack = empty_pack;
@@ -140,100 +161,120 @@ convex_fill_kernel(const FillParams p) {
       float lL = sc.open_ref;              // left_cell contribution of (x-1, y)
       int lRun = 0;
       uint32_t lDir = DIR_STOP;
-      BndEntry pf;
-      pf.S = 0.0f; pf.U = 0.0f; pf.pack = 0u; pf.pad = 0u;
-      uint32_t pfr = 0;
-      if (lane == 0) {
-        const unsigned im1 = min((unsigned)(brel - 1), plen);
-        dS = ld_bnd(bin + im1).S;
-        pf = ld_bnd(bin + min((unsigned)brel, plen));
-        pfr = __ldg(ref + base);
-      }
+      if (is0) dS = __uint_as_float(ld_strip(strip + base - 1).x);
       float kS = bestS;
       int kStep = -1;
 
-      for (int g = 0; g < ngroups; ++g) {
-        uint32_t dw = 0;
-#pragma unroll 1
-        for (int k4 = 0; k4 < 16; k4 += 4) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int s = (g << 4) + k4 + k;
-            float nS = __shfl_up_sync(FULL, oS, 1);
-            float nU = __shfl_up_sync(FULL, oU, 1);
-            uint32_t nP = __shfl_up_sync(FULL, oPack, 1);
-            if (lane == 0) {
-              nS = pf.S;
-              nU = pf.U;
-              nP = (pf.pack & 0x00ffffffu) | (pfr << 24);
-              ++brel;
-              pf = ld_bnd(bin + min((unsigned)brel, plen));
-              pfr = __ldg(ref + base + s + 1);
-            }
-            const uint32_t r = nP >> 24;
-            const bool act = (unsigned)rel < rlen;
-            int upRun, leftRun;
-            if (RAW) {
-              const int upRaw = (int)(short)(nP & 0xffffu);
-              const uint32_t upDir = (nP >> 16) & 3u;
-              const bool rawHere = rel < t0rel;
-              upRun = (rawHere || upDir == DIR_I) ? upRaw : 0;
-              leftRun = (rawHere || lDir == DIR_D) ? lRun : 0;
-            } else {
-              upRun = (int)(nP & 0xffffu);
-              leftRun = lRun;
-            }
-            const float sub = (r == q) ? sc.mat : sc.mis;
-            const float dg = __fadd_rn(dS, sub);
-            dS = nS;
-            const float m = fmaxf(fmaxf(fmaxf(lL, 0.0f), dg), nU);
-            const bool eL = (m == lL), eU = (m == nU), eG = (m == dg);
-            // priority (:1232-1267): continue D, continue I, diagonal, open D, open I, STOP
-            const bool dc = eL && (leftRun > 0);
-            const bool ic = !dc && eU && (upRun > 0);
-            const bool gg = !dc && !ic && eG;
-            const bool resolved = dc || ic || gg;
-            const bool dn = !resolved && eL;
-            const bool in = !resolved && !eL && eU;
-            const bool isD = dc || dn, isI = ic || in;
-            int run = dc ? leftRun + 1 : (ic ? upRun + 1 : ((dn || in) ? 1 : 0));
-            if (RAW) run = (int)(short)run;  // MatrixElement::indelRun is a short
-            uint32_t code = gg ? DIR_DIAG : (isI ? DIR_I : (isD ? DIR_D : DIR_STOP));
-            float S = m;  // STOP implies m == 0
-            // what the neighbours will see: S + min(ext_min, gap_ext + run*decay), 0 if S == 0 (:666-676)
-            const float pen = fminf(sc.ext_min, __fadd_rn(sc.gap_ext, __fmul_rn((float)run, sc.decay)));
-            float e = __fadd_rn(S, pen);
-            if (S == 0.0f) e = 0.0f;
-            float U = isI ? e : __fadd_rn(S, sc.open_read);
-            float L = isD ? e : __fadd_rn(S, sc.open_ref);
-            if (!act) {  // outside the corridor / reference: reads as {0, 0, STOP}
-              S = 0.0f;
-              U = sc.open_read;
-              L = sc.open_ref;
-              run = 0;
-              code = DIR_STOP;
-            }
-            oS = S;
-            oU = U;
-            lL = L;
-            if (RAW) {
-              oPack = (r << 24) | (code << 16) | ((uint32_t)run & 0xffffu);
-              lRun = run;
-              lDir = code;
-            } else {
-              oPack = (r << 24) | (uint32_t)((act && isI) ? run : 0);
-              lRun = (act && isD) ? run : 0;
-            }
-            if (act && S > kS) {  // strict: first maximum in row-major order (:1165-1170)
-              kS = S;
-              kStep = s;
-            }
-            dw = __funnelshift_r(dw, code, 2);
-            if (lane == 31 && act) st_bnd(bout + rel, S, U, oPack & 0x00ffffffu);
-            ++rel;
-          }
+      // stage chunk 0: strip records + reference bytes for columns [base, base+64)
+      uint4 pa, pb;
+      uint32_t ra, rb;
+      {
+        const int x0 = base + lane;
+        pa = ld_strip(strip + x0);
+        pb = ld_strip(strip + x0 + 32);
+        ra = __ldg(ref + x0);
+        rb = __ldg(ref + x0 + 32);
+      }
+
+      for (int c = 0; c < nchunks; ++c) {
+        pa.z = (pa.z & 0x00ffffffu) | (ra << 24);
+        pb.z = (pb.z & 0x00ffffffu) | (rb << 24);
+        in_s[lane] = pa;
+        in_s[lane + 32] = pb;
+        __syncwarp();
+        if (c + 1 < nchunks) {  // fetch the next chunk while this one is computed
+          const int x0 = base + (c + 1) * CHUNK + lane;
+          pa = ld_strip(strip + x0);
+          pb = ld_strip(strip + x0 + 32);
+          ra = __ldg(ref + x0);
+          rb = __ldg(ref + x0 + 32);
         }
-        dwp[(size_t)g * 32] = dw;
+        const int g_end = min(ngroups, (c + 1) << 2);
+        for (int g = c << 2; g < g_end; ++g) {
+          const uint4* in_g = in_s + ((g & 3) << 4);
+          uint4* out_g = out_s + ((g & 3) << 4);
+          uint32_t dw = 0;
+#pragma unroll 1
+          for (int k4 = 0; k4 < 16; k4 += 4) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int s = (g << 4) + k4 + k;
+              uint4 v;
+              v.x = __float_as_uint(__shfl_up_sync(FULL, oS, 1));
+              v.y = __float_as_uint(__shfl_up_sync(FULL, oU, 1));
+              v.z = __shfl_up_sync(FULL, oPack, 1);
+              v.w = 0u;
+              if (is0) v = in_g[k4 + k];
+              const float nS = __uint_as_float(v.x), nU = __uint_as_float(v.y);
+              const uint32_t nP = v.z;
+              const uint32_t r = nP >> 24;
+              const bool act = (unsigned)rel < rlen;
+              int upRun, leftRun;
+              if (RAW) {
+                const int upRaw = (int)(short)(nP & 0xffffu);
+                const uint32_t upDir = (nP >> 16) & 3u;
+                const bool rawHere = rel < t0rel;
+                upRun = (rawHere || upDir == DIR_I) ? upRaw : 0;
+                leftRun = (rawHere || lDir == DIR_D) ? lRun : 0;
+              } else {
+                upRun = (int)(nP & 0xffffu);
+                leftRun = lRun;
+              }
+              const float sub = (r == q) ? sc.mat : sc.mis;
+              const float dg = __fadd_rn(dS, sub);
+              dS = nS;
+              const float m = fmaxf(fmaxf(fmaxf(lL, 0.0f), dg), nU);
+              // outside the corridor nothing matches: the cell degenerates to {0, 0, STOP}
+              const bool eL = act && (m == lL), eU = act && (m == nU), eG = act && (m == dg);
+              // priority (:1232-1267): continue D, continue I, diagonal, open D, open I, STOP
+              const bool dc = eL && (leftRun > 0);
+              const bool ic = !dc && eU && (upRun > 0);
+              const bool gg = !dc && !ic && eG;
+              const bool resolved = dc || ic || gg;
+              const bool isD = dc || (!resolved && eL);
+              const bool isI = ic || (!resolved && !eL && eU);
+              int run = dc ? leftRun : (ic ? upRun : 0);
+              run = (isD || isI) ? run + 1 : 0;
+              if (RAW) run = (int)(short)run;  // MatrixElement::indelRun is a short
+              const uint32_t code = gg ? DIR_DIAG : (isI ? DIR_I : (isD ? DIR_D : DIR_STOP));
+              const float S = act ? m : 0.0f;  // STOP implies m == 0
+              // what the neighbours will see: S + min(ext_min, gap_ext + run*decay), 0 if S == 0 (:666-676)
+              const float pen = fminf(sc.ext_min, __fadd_rn(sc.gap_ext, __fmul_rn((float)run, sc.decay)));
+              float e = __fadd_rn(S, pen);
+              if (S == 0.0f) e = 0.0f;
+              const float U = isI ? e : __fadd_rn(S, sc.open_read);
+              const float L = isD ? e : __fadd_rn(S, sc.open_ref);
+              oS = S;
+              oU = U;
+              lL = L;
+              if (RAW) {
+                oPack = (r << 24) | (code << 16) | ((uint32_t)run & 0xffffu);
+                lRun = run;
+                lDir = code;
+              } else {
+                oPack = (r << 24) | (uint32_t)(isI ? run : 0);
+                lRun = isD ? run : 0;
+              }
+              if (act && S > kS) {  // strict: first maximum in row-major order (:1165-1170)
+                kS = S;
+                kStep = s;
+              }
+              dw = __funnelshift_r(dw, code, 2);
+              if (is31) out_g[k4 + k] = make_uint4(__float_as_uint(S), __float_as_uint(U), oPack, 0u);
+              ++rel;
+            }
+          }
+          dwp[(size_t)g * 32] = dw;
+        }
+        __syncwarp();
+        // flush lane 31's records of this chunk: columns [base - 31 + 64c, ...)
+        {
+          const int done = (g_end - (c << 2)) << 4;  // steps executed in this chunk
+          const int xo = base - 31 + c * CHUNK;
+          if (lane < done) st_strip(strip + xo + lane, out_s[lane]);
+          if (lane + 32 < done) st_strip(strip + xo + lane + 32, out_s[lane + 32]);
+        }
+        __syncwarp();
       }
 
       if (kStep >= 0) {
@@ -241,10 +282,8 @@ convex_fill_kernel(const FillParams p) {
         bestY = y;
         bestX = base + kStep - lane;
       }
-      if (lane == 31) st_bnd(bout + rlen, 0.0f, sc.open_read, empty_pack);  // sentinel: EMPTY
-      pxlo = __shfl_sync(FULL, xlo, 31);
-      plen = __shfl_sync(FULL, rlen, 31);
-      cur ^= 1;
+      wlo = base - 31;
+      whi = base - 31 + (ngroups << 4);
       __syncwarp();
     }
 
@@ -263,7 +302,7 @@ convex_fill_kernel(const FillParams p) {
       }
       cells += c2;
     }
-    if (lane == 0) {
+    if (is0) {
       FillOut o;
       o.best_score = bestS;
       o.best_x = bestX;

@@ -47,7 +47,8 @@ struct alignas(16) BlockRec {
   int32_t nsteps;
 };
 
-// Boundary row handed from lane 31 of one block to lane 0 of the next (through L2).
+// Boundary row handed from lane 31 of one block to lane 0 of the next (through L2), one record
+// per reference column.
 struct alignas(16) BndEntry {
   float S;        // score of the cell
   float U;        // what the cell below receives as up_cell
@@ -83,7 +84,7 @@ struct FillParams {
   unsigned long long dir_capacity;      // words
   unsigned long long* dir_alloc;        // bump pointer
   int* work_counter;
-  BndEntry* bnd;                        // per-warp scratch: 2 * bnd_stride entries each
+  BndEntry* bnd;                        // per-warp boundary strip: bnd_stride 16-byte records each
   unsigned long long bnd_stride;
   FillOut* out;
   Scoring sc;
