@@ -50,7 +50,7 @@ __device__ __forceinline__ void st_strip(uint4* p, uint4 v) { __stcg(p, v); }
 template <bool RAW>
 __global__ void __launch_bounds__(FILL_WARPS_PER_CTA * 32, FILL_CTAS_PER_SM)
 convex_fill_kernel(const FillParams p) {
-  __shared__ uint4 s_in[FILL_WARPS_PER_CTA][CHUNK];
+  __shared__ uint4 s_in[FILL_WARPS_PER_CTA][CHUNK + 1];  // +1: lane 31 reads one record ahead
   __shared__ uint4 s_out[FILL_WARPS_PER_CTA][CHUNK];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
@@ -60,9 +60,10 @@ convex_fill_kernel(const FillParams p) {
   // strip[x + STRIP_PAD] = {S, U, pack, -} of column x of the last finished block's bottom row
   uint4* const strip = reinterpret_cast<uint4*>(p.bnd) + (size_t)warp_global * p.bnd_stride + STRIP_PAD;
   const Scoring sc = p.sc;
-  const uint32_t empty_pack = RAW ? (DIR_STOP << 16) : 0u;
+  const uint32_t empty_pack = RAW ? (DIR_STOP << 16) : 0u;  // scalar kernel: run 0.0f
   const uint4 EMPTY = make_uint4(0u, __float_as_uint(sc.open_read), empty_pack, 0u);
   const bool is0 = lane == 0, is31 = lane == 31;
+  const int src_lane = (lane + 31) & 31;  // rotate: lane 0 receives what lane 31 staged for it
 
   for (;;) {
     int w = 0;
@@ -78,8 +79,11 @@ convex_fill_kernel(const FillParams p) {
     const int H = d.height, ref_len = d.ref_len;
     const int nblk = (H + 31) >> 5;
 
-    float bestS = -1.0f;  // curr_max starts at -1 (:921)
+    // curr_max starts at -1 (:921), so the first visited cell is always recorded and only strictly
+    // larger scores replace it: track improvements over 0 here and remember the first visited cell.
+    float bestS = 0.0f;
     int bestX = 0, bestY = 0;
+    int firstX = 0, firstY = -1;
     unsigned long long cells = 0;
     int status = ST_OK;
 
@@ -124,6 +128,14 @@ convex_fill_kernel(const FillParams p) {
       const int ngroups = (nsteps + 15) >> 4;
       const int nchunks = (ngroups + 3) >> 2;
       cells += rlen;
+      if (firstY < 0) {
+        const unsigned any = __ballot_sync(FULL, rlen != 0);
+        if (any) {
+          const int l0 = __ffs(any) - 1;
+          firstY = (b << 5) + l0;
+          firstX = __shfl_sync(FULL, xlo, l0);
+        }
+      }
 
       unsigned long long word_off = 0;
       if (is0) {
@@ -155,11 +167,15 @@ convex_fill_kernel(const FillParams p) {
       int rel = base - lane - xlo;  // x - xlo at step 0; inside the corridor iff (unsigned)rel < rlen
       const int t0rel = (int)rlen > 12 ? (int)rlen - 12 : 0;  // tail start max(x0, xMax-12) - xlo (:1179)
 
-      float oS = 0.0f, oU = sc.open_read;  // what this lane hands down: EMPTY = {0,0,STOP}
-      uint32_t oPack = empty_pack;
-      float dS = 0.0f;                     // score of (x-1, y-1)
-      float lL = sc.open_ref;              // left_cell contribution of (x-1, y)
-      int lRun = 0;
+      // What this lane hands down / keeps for its right neighbour. EMPTY = {0, 0, STOP}.
+      // oP: scalar kernel = the I-run length as a float (0 unless the cell is an insertion);
+      //     RAW kernel    = indelRun (low 16 bits) | direction << 16.
+      float oS = 0.0f, oU = sc.open_read;
+      uint32_t oP = empty_pack, oC = 0u;
+      float dS = 0.0f;         // score of (x-1, y-1)
+      float lL = sc.open_ref;  // left_cell contribution of (x-1, y)
+      float lRunF = 0.0f;      // scalar kernel: D-run length of (x-1, y), 0 unless it is a deletion
+      int lRun = 0;            // RAW kernel: raw indelRun / direction of (x-1, y)
       uint32_t lDir = DIR_STOP;
       if (is0) dS = __uint_as_float(ld_strip(strip + base - 1).x);
       float kS = bestS;
@@ -177,11 +193,18 @@ convex_fill_kernel(const FillParams p) {
       }
 
       for (int c = 0; c < nchunks; ++c) {
-        pa.z = (pa.z & 0x00ffffffu) | (ra << 24);
-        pb.z = (pb.z & 0x00ffffffu) | (rb << 24);
+        pa.w = ra;  // the reference byte of the column rides in the record
+        pb.w = rb;
         in_s[lane] = pa;
         in_s[lane + 32] = pb;
         __syncwarp();
+        if (is31) {  // lane 31's shuffle sources carry the strip record lane 0 needs next
+          const uint4 t = in_s[0];
+          oS = __uint_as_float(t.x);
+          oU = __uint_as_float(t.y);
+          oP = t.z;
+          oC = t.w;
+        }
         if (c + 1 < nchunks) {  // fetch the next chunk while this one is computed
           const int x0 = base + (c + 1) * CHUNK + lane;
           pa = ld_strip(strip + x0);
@@ -200,67 +223,87 @@ convex_fill_kernel(const FillParams p) {
             for (int k = 0; k < 4; ++k) {
               const int s = (g << 4) + k4 + k;
               uint4 v;
-              v.x = __float_as_uint(__shfl_up_sync(FULL, oS, 1));
-              v.y = __float_as_uint(__shfl_up_sync(FULL, oU, 1));
-              v.z = __shfl_up_sync(FULL, oPack, 1);
-              v.w = 0u;
-              if (is0) v = in_g[k4 + k];
+              v.x = __float_as_uint(__shfl_sync(FULL, oS, src_lane));
+              v.y = __float_as_uint(__shfl_sync(FULL, oU, src_lane));
+              v.z = __shfl_sync(FULL, oP, src_lane);
+              v.w = __shfl_sync(FULL, oC, src_lane);
               const float nS = __uint_as_float(v.x), nU = __uint_as_float(v.y);
-              const uint32_t nP = v.z;
-              const uint32_t r = nP >> 24;
+              const uint32_t r = v.w;
               const bool act = (unsigned)rel < rlen;
-              int upRun, leftRun;
-              if (RAW) {
-                const int upRaw = (int)(short)(nP & 0xffffu);
-                const uint32_t upDir = (nP >> 16) & 3u;
-                const bool rawHere = rel < t0rel;
-                upRun = (rawHere || upDir == DIR_I) ? upRaw : 0;
-                leftRun = (rawHere || lDir == DIR_D) ? lRun : 0;
-              } else {
-                upRun = (int)(nP & 0xffffu);
-                leftRun = lRun;
-              }
               const float sub = (r == q) ? sc.mat : sc.mis;
               const float dg = __fadd_rn(dS, sub);
               dS = nS;
-              const float m = fmaxf(fmaxf(fmaxf(lL, 0.0f), dg), nU);
-              // outside the corridor nothing matches: the cell degenerates to {0, 0, STOP}
-              const bool eL = act && (m == lL), eU = act && (m == nU), eG = act && (m == dg);
-              // priority (:1232-1267): continue D, continue I, diagonal, open D, open I, STOP
-              const bool dc = eL && (leftRun > 0);
-              const bool ic = !dc && eU && (upRun > 0);
-              const bool gg = !dc && !ic && eG;
-              const bool resolved = dc || ic || gg;
-              const bool isD = dc || (!resolved && eL);
-              const bool isI = ic || (!resolved && !eL && eU);
-              int run = dc ? leftRun : (ic ? upRun : 0);
-              run = (isD || isI) ? run + 1 : 0;
-              if (RAW) run = (int)(short)run;  // MatrixElement::indelRun is a short
-              const uint32_t code = gg ? DIR_DIAG : (isI ? DIR_I : (isD ? DIR_D : DIR_STOP));
-              const float S = act ? m : 0.0f;  // STOP implies m == 0
-              // what the neighbours will see: S + min(ext_min, gap_ext + run*decay), 0 if S == 0 (:666-676)
-              const float pen = fminf(sc.ext_min, __fadd_rn(sc.gap_ext, __fmul_rn((float)run, sc.decay)));
-              float e = __fadd_rn(S, pen);
-              if (S == 0.0f) e = 0.0f;
-              const float U = isI ? e : __fadd_rn(S, sc.open_read);
-              const float L = isD ? e : __fadd_rn(S, sc.open_ref);
-              oS = S;
-              oU = U;
-              lL = L;
+              // Outside the corridor the cell must degenerate to {0, 0, STOP}: a NaN maximum makes every
+              // equality below false, and fmaxf(NaN, 0) = 0 gives the score.
+              const float m = act ? fmaxf(fmaxf(fmaxf(lL, 0.0f), dg), nU) : __int_as_float(0x7fffffff);
+              const bool eL = (m == lL), eU = (m == nU), eG = (m == dg);
+              const float S = fmaxf(m, 0.0f);  // STOP implies m == 0
+              uint32_t code;
+              float U, L;
               if (RAW) {
-                oPack = (r << 24) | (code << 16) | ((uint32_t)run & 0xffffu);
+                const uint32_t nP = v.z;
+                const int upRaw = (int)(short)(nP & 0xffffu);
+                const uint32_t upDir = (nP >> 16) & 3u;
+                const bool rawHere = rel < t0rel;
+                const int upRun = (rawHere || upDir == DIR_I) ? upRaw : 0;
+                const int leftRun = (rawHere || lDir == DIR_D) ? lRun : 0;
+                // priority (:1232-1267): continue D, continue I, diagonal, open D, open I, STOP
+                const bool dc = eL && (leftRun > 0);
+                const bool ic = !dc && eU && (upRun > 0);
+                const bool gg = !dc && !ic && eG;
+                const bool resolved = dc || ic || gg;
+                const bool isD = dc || (!resolved && eL);
+                const bool isI = ic || (!resolved && !eL && eU);
+                int run = dc ? leftRun : (ic ? upRun : 0);
+                run = (isD || isI) ? run + 1 : 0;
+                run = (int)(short)run;  // MatrixElement::indelRun is a short
+                code = gg ? DIR_DIAG : (isI ? DIR_I : (isD ? DIR_D : DIR_STOP));
+                // what the neighbours will see: S + min(ext_min, gap_ext + run*decay), 0 if S == 0 (:666-676)
+                const float pen = fminf(sc.ext_min, __fadd_rn(sc.gap_ext, __fmul_rn((float)run, sc.decay)));
+                float e = __fadd_rn(S, pen);
+                if (S == 0.0f) e = 0.0f;
+                U = isI ? e : __fadd_rn(S, sc.open_read);
+                L = isD ? e : __fadd_rn(S, sc.open_ref);
+                oP = (code << 16) | ((uint32_t)run & 0xffffu);
                 lRun = run;
                 lDir = code;
               } else {
-                oPack = (r << 24) | (uint32_t)(isI ? run : 0);
-                lRun = isD ? run : 0;
+                // Same priority chain as a 3-input predicate network (verified exhaustively):
+                //   D  <=>  eL && (lr || !((eU && ur) || eG))
+                //   I  <=>  !D && eU && (ur || !eG)
+                // with run lengths kept as floats (exact below 2^24; rows are < 32768 wide here).
+                const float upRunF = __uint_as_float(v.z);
+                const bool lr = lRunF > 0.0f, ur = upRunF > 0.0f;
+                const bool X = (eU && ur) || eG;
+                const bool pD = eL && (lr || !X);
+                const bool pI = !pD && eU && (ur || !eG);
+                code = pD ? DIR_D : (pI ? DIR_I : (eG ? DIR_DIAG : DIR_STOP));
+                const float runF = pD ? __fadd_rn(lRunF, 1.0f) : (pI ? __fadd_rn(upRunF, 1.0f) : 0.0f);
+                const float pen = fminf(sc.ext_min, __fadd_rn(sc.gap_ext, __fmul_rn(runF, sc.decay)));
+                float e = __fadd_rn(S, pen);
+                if (S == 0.0f) e = 0.0f;
+                U = pI ? e : __fadd_rn(S, sc.open_read);
+                L = pD ? e : __fadd_rn(S, sc.open_ref);
+                oP = __float_as_uint(pI ? runF : 0.0f);
+                lRunF = pD ? runF : 0.0f;
               }
-              if (act && S > kS) {  // strict: first maximum in row-major order (:1165-1170)
+              oS = S;
+              oU = U;
+              oC = r;
+              lL = L;
+              if (S > kS) {  // strict: first maximum in row-major order (:1165-1170)
                 kS = S;
                 kStep = s;
               }
               dw = __funnelshift_r(dw, code, 2);
-              if (is31) out_g[k4 + k] = make_uint4(__float_as_uint(S), __float_as_uint(U), oPack, 0u);
+              if (is31) {
+                out_g[k4 + k] = make_uint4(__float_as_uint(S), __float_as_uint(U), oP, 0u);
+                const uint4 t = in_g[k4 + k + 1];
+                oS = __uint_as_float(t.x);
+                oU = __uint_as_float(t.y);
+                oP = t.z;
+                oC = t.w;
+              }
               ++rel;
             }
           }
@@ -301,6 +344,11 @@ convex_fill_kernel(const FillParams p) {
         bestX = x2;
       }
       cells += c2;
+    }
+    if (bestS == 0.0f) {  // no positive score anywhere: the first visited cell stands (or nothing was visited)
+      bestS = firstY >= 0 ? 0.0f : -1.0f;
+      bestX = firstY >= 0 ? firstX : 0;
+      bestY = firstY >= 0 ? firstY : 0;
     }
     if (is0) {
       FillOut o;
