@@ -1,13 +1,18 @@
-// ngmlr_b200/csrc/convex_traceback.cu -- traceback + binary-CIGAR compaction for sm_100a.
+// ngmlr_b200/csrc/convex_traceback.cu -- traceback + binary-CIGAR emission for sm_100a.
 //
 // Replaces Convex::ConvexAlignFast::revBacktrack (src/ConvexAlignFast.cpp:335-432) with
 // AlignmentMatrixFast::getDirection / validPath (src/AlignmentMatrixFast.cpp:185-195, 213-220).
 //
 // The walk is a pointer chase (each step depends on the previous direction), at most H + W steps
-// against H x W cells of fill, so it is latency- not bandwidth-bound: one thread per problem, many
-// problems in flight. Runs are emitted back-to-front into a per-problem scratch strip exactly like
-// the reference's binaryCigar (element = len << 4 | op, EQ and X separate ops), then a second
-// kernel copies each strip, warp-coalesced, into a compact arena so the host needs one D2H copy.
+// against H x W cells of fill, so it is latency- not bandwidth-bound. One WARP per problem: for
+// every 32-row block the lanes load, in a few coalesced requests, everything the path can touch
+// there -- lane t keeps row 32b+t's corridor line, read byte and a 64-step window of its direction
+// words around the expected diagonal; a 128-column window of reference bytes is kept likewise --
+// and the walk itself then runs on registers + warp shuffles (uniform control flow, ~100 cycles
+// per step instead of several dependent L2/HBM round trips). A path that drifts out of a window
+// falls back to a direct load. Runs are emitted back-to-front into a per-problem strip exactly
+// like the reference's binaryCigar (element = len << 4 | op, EQ and X separate ops); the same
+// warp then copies them, coalesced, into a compact arena so the host needs a single D2H copy.
 #include <cuda_runtime.h>
 
 #include "device_types.h"
@@ -17,8 +22,20 @@ namespace nb {
 
 namespace {
 
-__global__ void __launch_bounds__(128) convex_traceback_kernel(const TraceParams p) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int TB_WARPS_PER_CTA = 4;
+constexpr int NW = 4;  // direction words (16 steps each) a lane keeps per block
+
+struct RowWindow {
+  int off, len;        // corridor line of row 32*blk + lane
+  uint32_t q;          // read byte of that row
+  int g0;              // first 16-step group held in w[]
+  uint32_t w[NW];
+};
+
+__global__ void __launch_bounds__(TB_WARPS_PER_CTA * 32) convex_traceback_kernel(const TraceParams p) {
+  const int i = blockIdx.x * TB_WARPS_PER_CTA + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (i >= p.n) return;
   const AlnDesc d = p.desc[i];
   const FillOut f = p.fill[i];
@@ -32,7 +49,7 @@ __global__ void __launch_bounds__(128) convex_traceback_kernel(const TraceParams
   o.run_off = 0;
   if (f.status != ST_OK) {
     o.status = f.status;
-    p.out[i] = o;
+    if (lane == 0) p.out[i] = o;
     return;
   }
   const int H = d.height;
@@ -49,7 +66,7 @@ __global__ void __launch_bounds__(128) convex_traceback_kernel(const TraceParams
   const int qend = H - y - 1;  // (:1281)
   o.qend = qend;
   if (y <= 0) {  // (:338)
-    p.out[i] = o;
+    if (lane == 0) p.out[i] = o;
     return;
   }
   int idx = cap - 1;       // next free slot, filled downwards
@@ -58,34 +75,62 @@ __global__ void __launch_bounds__(128) convex_traceback_kernel(const TraceParams
   int op_len = qend;
   int read_len = qend;
   int steps = 0;
-  int cached_blk = -1;
-  BlockRec br;
-  br.word_off = 0; br.base = 0; br.nsteps = 0;
   bool ok = true, threw = false;
 
+  int cur_blk = -1;
+  BlockRec br;
+  br.word_off = 0; br.base = 0; br.nsteps = 0;
+  int ngroups = 0;
+  RowWindow rw;
+  rw.off = 0; rw.len = 0; rw.q = 0; rw.g0 = 0;
+#pragma unroll
+  for (int j = 0; j < NW; ++j) rw.w[j] = 0;
+  int xw0 = 1 << 30;       // reference byte window [xw0, xw0 + 128), 4 bytes per lane
+  uint32_t refw = 0;
+
   for (;;) {
-    // getDirection(x, y)
-    int dir = OP_STOP;
-    int off = 0, len = 0;
-    if (y >= 0 && y <= H - 1 && x >= 0) {
-      off = coff[y];
-      len = clen[y];
-      if (x >= off && (long long)x < (long long)off + (long long)len) {
-        const int blk = y >> 5, t = y & 31;
-        if (blk != cached_blk) {
-          br = blocks[blk];
-          cached_blk = blk;
-        }
-        const int s = x - br.base + t;
-        const uint32_t wd = p.dir[br.word_off + (unsigned long long)(s >> 4) * 32ull + (unsigned)t];
-        const uint32_t code = (wd >> ((s & 15) * 2)) & 3u;
-        if (code == DIR_DIAG) dir = (qry[y] == ref[x]) ? OP_EQ : OP_X;
-        else if (code == DIR_I) dir = OP_I;
-        else if (code == DIR_D) dir = OP_D;
+    // ---- getDirection(x, y) ----
+    if (y < 0 || x < 0) break;  // STOP (y > H-1 cannot happen: y only decreases from best_y)
+    const int blk = y >> 5, t = y & 31;
+    if (blk != cur_blk) {
+      cur_blk = blk;
+      br = blocks[blk];
+      ngroups = (br.nsteps + 15) >> 4;
+      const int yy = (blk << 5) + lane;
+      rw.off = 0; rw.len = 0; rw.q = 0;
+      if (yy < H) {
+        rw.off = coff[yy];
+        rw.len = clen[yy];
+        rw.q = qry[yy];
+      }
+      // expected step index of the path in row `lane`: two steps per row along the diagonal
+      const int s_here = x - br.base + t;
+      const int s_exp = s_here - 2 * (t - lane);
+      int g0 = (s_exp >> 4) - (NW / 2 - 1) - 1;
+      g0 = max(0, min(g0, ngroups - NW));
+      rw.g0 = g0;
+#pragma unroll
+      for (int j = 0; j < NW; ++j) {
+        const int g = g0 + j;
+        rw.w[j] = (g < ngroups && lane <= t) ? p.dir[br.word_off + (unsigned long long)g * 32ull + (unsigned)lane] : 0u;
       }
     }
-    if (dir == OP_STOP) break;
-    // validPath(x, y): float math then truncation, as in the reference
+    const int off = __shfl_sync(FULL, rw.off, t);
+    const int len = __shfl_sync(FULL, rw.len, t);
+    if (x < off || (long long)x >= (long long)off + (long long)len) break;  // STOP: outside the corridor
+    const int s = x - br.base + t;
+    const int g = s >> 4;
+    const int j = g - __shfl_sync(FULL, rw.g0, t);
+    uint32_t wd;
+    if ((unsigned)j < (unsigned)NW) {
+      const uint32_t mine = j == 0 ? rw.w[0] : (j == 1 ? rw.w[1] : (j == 2 ? rw.w[2] : rw.w[3]));
+      wd = __shfl_sync(FULL, mine, t);
+    } else {
+      wd = p.dir[br.word_off + (unsigned long long)g * 32ull + (unsigned)t];  // drifted out of the window
+    }
+    const uint32_t code = (wd >> ((s & 15) * 2)) & 3u;
+    if (code == DIR_STOP) break;
+    // ---- validPath(x, y): float math then truncation, as in the reference ----
     {
       const float w = (float)len;
       const int min_c = (int)__fadd_rn((float)off, __fmul_rn(0.1f, w));
@@ -94,6 +139,20 @@ __global__ void __launch_bounds__(128) convex_traceback_kernel(const TraceParams
         ok = false;
         break;
       }
+    }
+    int dir;
+    if (code == DIR_DIAG) {
+      if (x < xw0 || x >= xw0 + 128) {
+        xw0 = max(0, x - 124) & ~3;
+        refw = *reinterpret_cast<const uint32_t*>(ref + xw0 + 4 * lane);  // arena is padded
+      }
+      const int rx = x - xw0;
+      const uint32_t rword = __shfl_sync(FULL, refw, rx >> 2);
+      const uint32_t rc = (rword >> ((rx & 3) * 8)) & 0xffu;
+      const uint32_t qc = __shfl_sync(FULL, rw.q, t);
+      dir = (qc == rc) ? OP_EQ : OP_X;
+    } else {
+      dir = (code == DIR_I) ? OP_I : OP_D;
     }
     ++steps;
     if (dir == OP_EQ || dir == OP_X) {
@@ -106,7 +165,7 @@ __global__ void __launch_bounds__(128) convex_traceback_kernel(const TraceParams
     if (dir == op) {
       ++op_len;
     } else {
-      if (idx >= 0) bc[idx] = (op_len << 4) | op;
+      if (lane == 0 && idx >= 0) bc[idx] = (op_len << 4) | op;
       --idx;
       ++used;
       op = dir;
@@ -120,63 +179,58 @@ __global__ void __launch_bounds__(128) convex_traceback_kernel(const TraceParams
   o.steps = steps;
   if (threw) {
     o.status = ST_THROW;
-    p.out[i] = o;
+    if (lane == 0) p.out[i] = o;
     return;
   }
   if (!ok) {
-    p.out[i] = o;
+    if (lane == 0) p.out[i] = o;
     return;
   }
   // last run + leading clip (:411-416); the reference writes both slots unchecked
   if (idx < 1 || used + 2 > ref_cap) {
     o.status = ST_THROW;
-    p.out[i] = o;
+    if (lane == 0) p.out[i] = o;
     return;
   }
-  bc[idx--] = (op_len << 4) | op;
-  bc[idx--] = ((y + 1) << 4) | OP_S;
+  if (lane == 0) {
+    bc[idx] = (op_len << 4) | op;
+    bc[idx - 1] = ((y + 1) << 4) | OP_S;
+  }
+  idx -= 2;
   read_len += y + 1;
   o.ref_position = x + 1;
   o.qstart = y + 1;
   const int n = cap - 1 - idx;
   o.n_runs = n;
   if (H != read_len) {  // (:424-428)
-    p.out[i] = o;
+    if (lane == 0) p.out[i] = o;
     return;
   }
-  const unsigned long long at = atomicAdd(p.runs_alloc, (unsigned long long)n);
+  unsigned long long at = 0;
+  if (lane == 0) at = atomicAdd(p.runs_alloc, (unsigned long long)n);
+  at = __shfl_sync(FULL, at, 0);
   o.run_off = at;
   o.status = (at + (unsigned long long)n <= p.runs_capacity) ? ST_OK : ST_DIR_OVERFLOW;
-  p.out[i] = o;
-}
-
-// One warp per problem: strip [cap-n, cap) -> compact arena [run_off, run_off+n), same order
-// (leading clip, runs..., trailing clip).
-__global__ void __launch_bounds__(256) convex_compact_kernel(const TraceParams p) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= p.n) return;
-  const TraceOut o = p.out[warp];
-  if (o.status != ST_OK) return;
-  const AlnDesc d = p.desc[warp];
-  const int32_t* __restrict__ src = p.scratch + d.tb_off + (d.tb_cap - o.n_runs);
-  int32_t* __restrict__ dst = p.runs + o.run_off;
-  for (int k = lane; k < o.n_runs; k += 32) dst[k] = src[k];
+  __syncwarp();
+  if (o.status == ST_OK) {
+    // strip [cap-n, cap) -> compact arena, same order (leading clip, runs..., trailing clip)
+    const int32_t* __restrict__ src = bc + (cap - n);
+    int32_t* __restrict__ dst = p.runs + at;
+    for (int k = lane; k < n; k += 32) dst[k] = src[k];
+  }
+  if (lane == 0) p.out[i] = o;
 }
 
 }  // namespace
 
 cudaError_t launch_convex_traceback(const TraceParams& p, cudaStream_t stream) {
   if (p.n <= 0) return cudaSuccess;
-  convex_traceback_kernel<<<(p.n + 127) / 128, 128, 0, stream>>>(p);
+  convex_traceback_kernel<<<(p.n + TB_WARPS_PER_CTA - 1) / TB_WARPS_PER_CTA, TB_WARPS_PER_CTA * 32, 0, stream>>>(p);
   return cudaGetLastError();
 }
 
-cudaError_t launch_convex_compact(const TraceParams& p, cudaStream_t stream) {
-  if (p.n <= 0) return cudaSuccess;
-  const int warps_per_cta = 8;
-  convex_compact_kernel<<<(p.n + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, stream>>>(p);
-  return cudaGetLastError();
+cudaError_t launch_convex_compact(const TraceParams&, cudaStream_t) {
+  return cudaSuccess;  // compaction is fused into the traceback kernel
 }
 
 }  // namespace nb
