@@ -132,7 +132,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--reads", type=int, default=2048, help="reads (alignment problems) per step per GPU")
+    ap.add_argument("--reads", type=int, default=8192, help="reads (alignment problems) per step per GPU")
     ap.add_argument("--genome-mb", type=float, default=50.0)
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     args = ap.parse_args()
@@ -235,7 +235,7 @@ def main():
     dev_ms = e0.elapsed_time(e1)
     res = al.fetch()
     st = al.stats()
-    assert all(r.ret == len(p.qry) for r, p in zip(res, pool)), "bench: invalid alignment in the timed batch"
+    assert all(res.ret(i) == len(p.qry) for i, p in enumerate(pool)), "bench: invalid alignment in the timed batch"
     cells = st["cells"]
 
     # ---- end to end from host buffers through the public call ----
@@ -300,7 +300,10 @@ def main():
             "kernel_ms_per_step": {"fill": float(np.mean(fill_ms)), "traceback": float(np.mean(tb_ms)),
                                    "compact": float(np.mean(cp_ms))},
             "e2e": {"value": e2e_val, "unit": "Gbp/s", "h2d_bytes_per_step": st_e2e["h2d_bytes"],
-                    "d2h_bytes_per_step": st_e2e["d2h_bytes"], "ms_per_step": e2e_ms / args.steps},
+                    "d2h_bytes_per_step": st_e2e["d2h_bytes"], "ms_per_step": e2e_ms / args.steps,
+                    "host_ms": {k: st_e2e[k] for k in ("host_pack_ms", "host_h2d_ms", "host_run_ms",
+                                                       "host_d2h_ms", "host_text_ms")},
+                    "host_threads": st_e2e["host_threads"]},
             "gpu_launches": 3 * args.steps,
             "clocks": clocks,
         }

@@ -74,6 +74,9 @@ typedef struct {
   float fill_ms, traceback_ms, compact_ms; /* CUDA-event durations on the context's stream */
   int32_t fill_launches, traceback_launches, compact_launches;
   int64_t h2d_bytes, d2h_bytes;
+  /* host wall-clock of the last upload / run / fetch phases (ms) */
+  float host_pack_ms, host_h2d_ms, host_run_ms, host_d2h_ms, host_text_ms;
+  int32_t host_threads;
 } ngmlr_b200_batch_stats;
 
 int ngmlr_b200_abi_version(void);

@@ -30,7 +30,9 @@ class BatchStats(C.Structure):
                 ("path_steps", C.c_int64), ("cigar_runs", C.c_int64), ("fill_ms", C.c_float),
                 ("traceback_ms", C.c_float), ("compact_ms", C.c_float),
                 ("fill_launches", C.c_int32), ("traceback_launches", C.c_int32),
-                ("compact_launches", C.c_int32), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+                ("compact_launches", C.c_int32), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+                ("host_pack_ms", C.c_float), ("host_h2d_ms", C.c_float), ("host_run_ms", C.c_float),
+                ("host_d2h_ms", C.c_float), ("host_text_ms", C.c_float), ("host_threads", C.c_int32)]
 
 
 # every symbol include/ngmlr_b200.h declares (tests/test_abi.py checks the list against the header)

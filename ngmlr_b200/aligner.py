@@ -142,6 +142,8 @@ class B200Aligner:
         return self.BatchAlign(b)[0]
 
     def BatchAlign(self, batch):
+        """Returns an AlignBatchResult: records are decoded on access and, like the C ABI's result
+        array, are valid until the next batch call on this aligner (`list(result)` copies them)."""
         res = (_lib.AlignResult * max(batch.n, 1))()
         self._check(self.lib.ngmlr_b200_convex_align_batch(self.h, *batch.c_args(), res))
         return self._collect(res, batch.n)
@@ -180,17 +182,45 @@ class B200Aligner:
 
     @staticmethod
     def _collect(res, n):
-        out = []
-        for i in range(n):
-            r = res[i]
-            nm = (np.ctypeslib.as_array(r.nm_positions, shape=(r.nm_count * 3,)).reshape(-1, 3).copy()
-                  if r.nm_count > 0 else np.zeros((0, 3), np.int32))
-            out.append(Align(ret=r.ret, threw=bool(r.threw), Score=float(r.score),
-                             Identity=float(r.identity), PositionOffset=r.position_offset,
-                             QStart=r.qstart, QEnd=r.qend, NM=r.nm,
-                             alignmentLength=r.alignment_length, cigarOpCount=r.cigar_op_count,
-                             svType=r.sv_type, firstPosition=(r.first_ref, r.first_read),
-                             lastPosition=(r.last_ref, r.last_read),
-                             pBuffer1=(r.cigar or b"").decode(), pBuffer2=(r.md or b"").decode(),
-                             nmPerPosition=nm, cells=r.cells))
-        return out
+        return AlignBatchResult(res, n)
+
+
+class AlignBatchResult:
+    """Sequence of `Align` records of one batch. Records are materialised on access from the
+    C result array (whose text/position buffers are owned by the aligner context and stay valid
+    until its next batch call) -- copy what must outlive that."""
+
+    def __init__(self, res, n):
+        self._res = res
+        self._n = n
+
+    def __len__(self):
+        return self._n
+
+    def __eq__(self, other):
+        return list(self) == other
+
+    def __iter__(self):
+        return (self[i] for i in range(self._n))
+
+    def ret(self, i):
+        return self._res[i].ret
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(self._n))]
+        if i < 0:
+            i += self._n
+        if not 0 <= i < self._n:
+            raise IndexError(i)
+        r = self._res[i]
+        nm = (np.ctypeslib.as_array(r.nm_positions, shape=(r.nm_count * 3,)).reshape(-1, 3).copy()
+              if r.nm_count > 0 else np.zeros((0, 3), np.int32))
+        return Align(ret=r.ret, threw=bool(r.threw), Score=float(r.score),
+                     Identity=float(r.identity), PositionOffset=r.position_offset,
+                     QStart=r.qstart, QEnd=r.qend, NM=r.nm,
+                     alignmentLength=r.alignment_length, cigarOpCount=r.cigar_op_count,
+                     svType=r.sv_type, firstPosition=(r.first_ref, r.first_read),
+                     lastPosition=(r.last_ref, r.last_read),
+                     pBuffer1=(r.cigar or b"").decode(), pBuffer2=(r.md or b"").decode(),
+                     nmPerPosition=nm, cells=r.cells)

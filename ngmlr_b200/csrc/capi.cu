@@ -10,7 +10,11 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <numeric>
+#include <stdlib.h>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -74,6 +78,45 @@ struct PinBuf {
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+inline double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// Host worker threads for packing and CIGAR/MD text (NGMLR_B200_HOST_THREADS overrides).
+int host_threads() {
+  static int n = [] {
+    const char* e = getenv("NGMLR_B200_HOST_THREADS");
+    int v = e ? atoi(e) : 0;
+    if (v <= 0) v = (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+    return v;
+  }();
+  return n;
+}
+
+// fn(i) for i in [0, n), dynamically scheduled in chunks over host_threads() threads.
+template <typename F>
+void parallel_for(int n, int chunk, F fn) {
+  const int threads = std::min(host_threads(), (n + chunk - 1) / chunk);
+  if (threads <= 1) {
+    for (int i = 0; i < n; ++i) fn(i);
+    return;
+  }
+  std::atomic<int> next(0);
+  auto work = [&]() {
+    for (;;) {
+      const int b = next.fetch_add(chunk);
+      if (b >= n) break;
+      const int e = std::min(n, b + chunk);
+      for (int i = b; i < e; ++i) fn(i);
+    }
+  };
+  std::vector<std::thread> pool;
+  pool.reserve(threads - 1);
+  for (int t = 1; t < threads; ++t) pool.emplace_back(work);
+  work();
+  for (auto& t : pool) t.join();
+}
 
 // bytes readable past the end of every staged sequence (the fill kernel stages whole 64-column
 // chunks, see convex_fill.cu) and slack of the per-warp boundary strip
@@ -300,21 +343,32 @@ int ngmlr_b200_convex_upload(ngmlr_b200_ctx* ctx, int n, const char* const* refs
   CU(ctx->h_order.reserve(n));
   ctx->ext_qs.assign(n, 0);
   ctx->ext_qe.assign(n, 0);
-  // ---- pack ----
+  // ---- pack (parallel over problems) ----
+  const double t_pack0 = now_ms();
   const int64_t r0 = row_start[0];
-  if (rows) {
-    memcpy(ctx->h_coff.p, corridor_offsets + r0, rows * sizeof(int32_t));
-    memcpy(ctx->h_clen.p, corridor_lengths + r0, rows * sizeof(int32_t));
+  std::vector<size_t> seq_at(n), blk_at(n), tb_at(n);
+  {
+    size_t so_ = 0, bo_ = 0, tb_ = 0;
+    for (int i = 0; i < n; ++i) {
+      const int rl = ref_lens[i], ql = qry_lens[i];
+      seq_at[i] = so_;
+      so_ += align_up((size_t)rl + SEQ_PAD, 16) + align_up((size_t)ql + SEQ_PAD, 16);
+      blk_at[i] = bo_;
+      bo_ += ((size_t)ql + 31) / 32;
+      tb_at[i] = tb_;
+      const long long ref_cap = ql > 200000 ? (long long)ql + 1 : 200000;  // maxBinaryCigarLength (:480-485)
+      tb_ += (size_t)std::min<long long>((long long)ql + rl + 4, ref_cap);
+    }
+    tb_ints = tb_;
   }
-  size_t so = 0, bo = 0;
-  ctx->max_ref_len = 0;
-  int max_len_all = 0;
-  size_t dir_words = 0;
   std::vector<unsigned long long> est(n);
-  for (int i = 0; i < n; ++i) {
+  std::vector<size_t> dirw(n);
+  std::vector<int> maxlen(n);
+  parallel_for(n, 16, [&](int i) {
     AlnDesc& d = ctx->h_desc.p[i];
     memset(&d, 0, sizeof(d));
     const int rl = ref_lens[i], ql = qry_lens[i];
+    size_t so = seq_at[i];
     d.ref_off = so;
     memcpy(ctx->h_seq.p + so, refs[i], rl);
     memset(ctx->h_seq.p + so + rl, 0, align_up((size_t)rl + SEQ_PAD, 16) - rl);
@@ -322,19 +376,19 @@ int ngmlr_b200_convex_upload(ngmlr_b200_ctx* ctx, int n, const char* const* refs
     d.qry_off = so;
     memcpy(ctx->h_seq.p + so, qrys[i], ql);
     memset(ctx->h_seq.p + so + ql, 0, align_up((size_t)ql + SEQ_PAD, 16) - ql);
-    so += align_up((size_t)ql + SEQ_PAD, 16);
     d.row_off = (uint64_t)(row_start[i] - r0);
-    d.blk_off = bo;
-    bo += ((size_t)ql + 31) / 32;
+    d.blk_off = blk_at[i];
     d.ref_len = rl;
     d.height = ql;
-    d.ref_cap = ql > 200000 ? ql + 1 : 200000;  // maxBinaryCigarLength (:480-485)
-    const long long worst = (long long)ql + rl + 4;
-    d.tb_cap = (int)std::min<long long>(worst, d.ref_cap);
-    d.tb_off = tb_ints;
-    tb_ints += (size_t)d.tb_cap;
-    const int32_t* lens = ctx->h_clen.p + d.row_off;
-    const int32_t* offs = ctx->h_coff.p + d.row_off;
+    d.ref_cap = ql > 200000 ? ql + 1 : 200000;
+    d.tb_cap = (int)std::min<long long>((long long)ql + rl + 4, d.ref_cap);
+    d.tb_off = tb_at[i];
+    int32_t* lens = ctx->h_clen.p + d.row_off;
+    int32_t* offs = ctx->h_coff.p + d.row_off;
+    if (ql) {
+      memcpy(offs, corridor_offsets + row_start[i], (size_t)ql * sizeof(int32_t));
+      memcpy(lens, corridor_lengths + row_start[i], (size_t)ql * sizeof(int32_t));
+    }
     int ml = 0;
     unsigned long long sum = 0;
     for (int y = 0; y < ql; ++y) {
@@ -342,22 +396,33 @@ int ngmlr_b200_convex_upload(ngmlr_b200_ctx* ctx, int n, const char* const* refs
       sum += (unsigned long long)std::max(lens[y], 0);
     }
     d.max_len = ml;
-    max_len_all = std::max(max_len_all, std::min(ml, rl));
-    ctx->max_ref_len = std::max(ctx->max_ref_len, rl);
+    maxlen[i] = std::min(ml, rl);
     est[i] = sum;
     // direction arena estimate: per 32-row block, steps = row width + 31 (stagger) + corridor
     // advance over the block; the exact figure is computed by the kernel (bump allocation) and an
     // overflow triggers a re-run with a larger arena.
+    dirw[i] = 0;
     if (ql > 0) {
       const long long adv_total = std::max<long long>(0, (long long)offs[ql - 1] - offs[0]);
       const long long adv = (adv_total * 32 + std::max(ql - 1, 1) - 1) / std::max(ql - 1, 1) + 2;
       const long long w = std::min<long long>(ml, (long long)rl);
       const long long steps = w + 31 + adv;
-      dir_words += (size_t)(((size_t)ql + 31) / 32) * (size_t)((steps + 15) / 16 + 1) * 32;
+      dirw[i] = (size_t)(((size_t)ql + 31) / 32) * (size_t)((steps + 15) / 16 + 1) * 32;
     }
+  });
+  size_t so = 0, bo = 0;
+  int max_len_all = 0;
+  size_t dir_words = 0;
+  ctx->max_ref_len = 0;
+  for (int i = 0; i < n; ++i) {
+    max_len_all = std::max(max_len_all, maxlen[i]);
+    ctx->max_ref_len = std::max(ctx->max_ref_len, ref_lens[i]);
+    dir_words += dirw[i];
     if (ext_qstart) ctx->ext_qs[i] = ext_qstart[i];
     if (ext_qend) ctx->ext_qe[i] = ext_qend[i];
   }
+  so = seq_bytes;
+  bo = nblocks;
   std::iota(ctx->h_order.p, ctx->h_order.p + n, 0);
   std::stable_sort(ctx->h_order.p, ctx->h_order.p + n,
                    [&](int a, int b) { return est[a] > est[b]; });
@@ -367,6 +432,7 @@ int ngmlr_b200_convex_upload(ngmlr_b200_ctx* ctx, int n, const char* const* refs
   ctx->tb_ints = tb_ints;
   ctx->max_len = max_len_all;
   ctx->dir_words_needed = dir_words + dir_words / 16 + 1024;
+  const double t_pack1 = now_ms();
   // ---- device arenas + H2D ----
   cudaStream_t st = ctx->stream;
   CU(ctx->d_seq.reserve(so + 64));
@@ -392,6 +458,9 @@ int ngmlr_b200_convex_upload(ngmlr_b200_ctx* ctx, int n, const char* const* refs
   CU(cudaMemcpyAsync(ctx->d_order.p, ctx->h_order.p, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   CU(cudaStreamSynchronize(st));
   ctx->stats = ngmlr_b200_batch_stats();
+  ctx->stats.host_pack_ms = (float)(t_pack1 - t_pack0);
+  ctx->stats.host_h2d_ms = (float)(now_ms() - t_pack1);
+  ctx->stats.host_threads = host_threads();
   ctx->stats.h2d_bytes = (int64_t)(so + rows * 8 + (size_t)n * (sizeof(AlnDesc) + 4));
   ctx->stats.seq_bytes = (int64_t)so;
   return 0;
@@ -406,6 +475,7 @@ int ngmlr_b200_convex_run(ngmlr_b200_ctx* ctx) {
   CU(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   const int n = ctx->n;
+  const double t_run0 = now_ms();
   const bool raw = ctx->force_raw < 0 ? (ctx->raw || ctx->max_len > 32767) : (ctx->force_raw != 0);
   static int ctas_per_sm[2] = {0, 0};
   if (!ctas_per_sm[raw]) ctas_per_sm[raw] = std::max(1, fill_max_ctas_per_sm(raw));
@@ -492,6 +562,7 @@ int ngmlr_b200_convex_run(ngmlr_b200_ctx* ctx) {
   ctx->stats.compact_ms = ms;
   ctx->stats.dir_bytes = (int64_t)ctx->dir_used * 4;
   ctx->stats.cigar_runs = (int64_t)ctx->runs_used;
+  ctx->stats.host_run_ms = (float)(now_ms() - t_run0);
   ctx->ran = true;
   return 0;
 }
@@ -503,6 +574,7 @@ int ngmlr_b200_convex_fetch(ngmlr_b200_ctx* ctx, ngmlr_b200_align_result* result
   if (n == 0) return 0;
   CU(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
+  const double t_f0 = now_ms();
   CU(ctx->h_runs.reserve((size_t)ctx->runs_used + 16));
   CU(cudaMemcpyAsync(ctx->h_fill.p, ctx->d_fill.p, (size_t)n * sizeof(FillOut), cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(ctx->h_trace.p, ctx->d_trace.p, (size_t)n * sizeof(TraceOut), cudaMemcpyDeviceToHost, st));
@@ -510,10 +582,13 @@ int ngmlr_b200_convex_fetch(ngmlr_b200_ctx* ctx, ngmlr_b200_align_result* result
     CU(cudaMemcpyAsync(ctx->h_runs.p, ctx->d_runs.p, (size_t)ctx->runs_used * sizeof(int32_t),
                        cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  const double t_f1 = now_ms();
   ctx->stats.d2h_bytes = (int64_t)((size_t)n * (sizeof(FillOut) + sizeof(TraceOut)) + ctx->runs_used * 4);
-  ctx->texts.assign(n, AlignText());
-  int64_t cells = 0, steps = 0;
-  for (int i = 0; i < n; ++i) {
+  if ((int)ctx->texts.size() < n) ctx->texts.resize(n);
+  for (int i = 0; i < n; ++i)
+    if (ctx->h_trace.p[i].status == ST_DIR_OVERFLOW)
+      return ctx->fail("convex_fetch: internal arena overflow survived run()");
+  parallel_for(n, 8, [&](int i) {
     const AlnDesc& d = ctx->h_desc.p[i];
     const FillOut& f = ctx->h_fill.p[i];
     const TraceOut& t = ctx->h_trace.p[i];
@@ -524,20 +599,17 @@ int ngmlr_b200_convex_fetch(ngmlr_b200_ctx* ctx, ngmlr_b200_align_result* result
     r.cigar = "";
     r.md = "";
     r.cells = (int64_t)f.cells;
-    cells += (int64_t)f.cells;
-    steps += t.steps;
     if (t.status == ST_THROW) {
       r.threw = 1;
-      continue;
+      return;
     }
-    if (t.status == ST_DIR_OVERFLOW) return ctx->fail("convex_fetch: internal arena overflow survived run()");
-    if (t.status != ST_OK) continue;
+    if (t.status != ST_OK) return;
     AlignText& tx = ctx->texts[i];
     const char* ref = reinterpret_cast<const char*>(ctx->h_seq.p + d.ref_off);
     if (!binary_cigar_to_text(ctx->h_runs.p + t.run_off, t.n_runs, ref, d.ref_len, t.ref_position,
                               ctx->ext_qs[i], ctx->ext_qe[i], tx)) {
       r.threw = 1;
-      continue;
+      return;
     }
     r.ret = tx.ret;
     r.score = f.best_score;
@@ -559,9 +631,16 @@ int ngmlr_b200_convex_fetch(ngmlr_b200_ctx* ctx, ngmlr_b200_align_result* result
     r.cigar = tx.cigar.c_str();
     r.md = tx.md.c_str();
     r.nm_positions = tx.nm_positions.data();
+  });
+  int64_t cells = 0, steps = 0;
+  for (int i = 0; i < n; ++i) {
+    cells += (int64_t)ctx->h_fill.p[i].cells;
+    steps += ctx->h_trace.p[i].steps;
   }
   ctx->stats.cells = cells;
   ctx->stats.path_steps = steps;
+  ctx->stats.host_d2h_ms = (float)(t_f1 - t_f0);
+  ctx->stats.host_text_ms = (float)(now_ms() - t_f1);
   return 0;
 }
 

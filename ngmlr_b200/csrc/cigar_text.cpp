@@ -52,7 +52,12 @@ struct ErrorWindow {
 
 bool binary_cigar_to_text(const int32_t* runs, int n_runs, const char* ref, int ref_len,
                           int ref_position, int ext_qstart, int ext_qend, AlignText& out) {
-  out = AlignText();
+  // reuse the caller's buffers (capacity survives across batches)
+  out.cigar.clear();
+  out.md.clear();
+  out.nm_positions.clear();
+  out.ret = -1;
+  out.sv_type = 0;
   if (n_runs < 2) return false;
   const char* aref = ref + ref_position;  // convertCigar receives refSeq + ref_position (:489)
   std::string& cg = out.cigar;

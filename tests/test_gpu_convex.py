@@ -106,7 +106,7 @@ def test_properties_at_scale(aligner):
     import re
     probs = synth.pacbio_problems(192, genome_len=2_000_000, seed=9, median=8000)
     batch = PackedBatch.from_problems(probs)
-    res = aligner.BatchAlign(batch)
+    res = list(aligner.BatchAlign(batch))  # materialise: the next batch call reuses the context's buffers
     for p, r in zip(probs, res):
         assert r.ret == len(p.qry), "valid alignment must cover the full read"
         ops = re.findall(r"(\d+)([MIDS])", r.pBuffer1)
