@@ -134,6 +134,29 @@ int ngmlr_b200_convex_debug_directions(ngmlr_b200_ctx* ctx, int i, uint8_t* dirs
 int ngmlr_b200_sw_score_batch(ngmlr_b200_ctx* ctx, int n, const char* const* refs,
                               const char* const* qrys, float* results);
 
+/* ---- k-mer candidate search: CS::RunRead's search --------------------------------------------
+ * ngmlr_b200_cs_set_index takes the reference's in-memory k-mer index of one table unit exactly as
+ * CompactPrefixTable holds it (src/PrefixTable.h:17-75): `packed_index` = Index records, 5 bytes
+ * each ({uint m_TabIndex; char m_RevCompIndex}, #pragma pack(1)), index_len = 4^k + 1 of them;
+ * `positions` = Location{uint} lists (cRefTableLen entries); unit_offset = TableUnit::Offset;
+ * k = CS::prefixBasecount (--kmer-length, <= 16), bin_shift = Config.getBinSize() (--bin-size).
+ * The arrays are copied to the device; host buffers may be released afterwards. */
+int ngmlr_b200_cs_set_index(ngmlr_b200_ctx* ctx, const void* packed_index, uint32_t index_len,
+                            const uint32_t* positions, uint32_t n_positions, uint64_t unit_offset,
+                            int k, int bin_shift);
+
+/* Candidate search for n (sub-)reads: replaces CS::PrefixIteration + PrefixSearch + AddLocationStd +
+ * CollectResultsStd (src/CSstatic.cpp:23-73, src/CS.cpp:57-149, 217-269) as driven by
+ * CS::RunRead (src/CS.cpp:324-398). sensitivity = Config.getSensitivity() (0.8),
+ * min_kmer_hits = Config.getMinKmerHits() (0). On return cand_start[i] .. cand_start[i+1] index the
+ * candidates of read i in the context-owned arrays *scores / *locs / *reverse
+ * (LocationScore::Score.f, Location.m_Location, isReverse()), in the reference's emission order;
+ * max_hits[i] = maxHitNumber (MappedRead::s). Arrays stay valid until the next cs call. */
+int ngmlr_b200_cs_search_batch(ngmlr_b200_ctx* ctx, int n, const char* const* seqs,
+                               const int32_t* lens, float sensitivity, float min_kmer_hits,
+                               int64_t* cand_start, const float** scores, const uint64_t** locs,
+                               const uint8_t** reverse, float* max_hits);
+
 #ifdef __cplusplus
 }
 #endif

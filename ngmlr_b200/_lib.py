@@ -41,7 +41,7 @@ C_API_SYMBOLS = (
     "ngmlr_b200_last_error", "ngmlr_b200_set_stream", "ngmlr_b200_get_stream",
     "ngmlr_b200_convex_align_batch", "ngmlr_b200_convex_upload", "ngmlr_b200_convex_run",
     "ngmlr_b200_convex_fetch", "ngmlr_b200_convex_stats", "ngmlr_b200_convex_debug_directions",
-    "ngmlr_b200_sw_score_batch",
+    "ngmlr_b200_sw_score_batch", "ngmlr_b200_cs_set_index", "ngmlr_b200_cs_search_batch",
 )
 PLUGIN_SYMBOLS = ("CreateAlignment", "DeleteAlignment", "SetAlignmentScoring")
 
@@ -77,6 +77,11 @@ def load():
     lib.ngmlr_b200_convex_debug_directions.argtypes = [vp, C.c_int, C.POINTER(C.c_uint8), C.c_size_t,
                                                        C.POINTER(C.c_float), i32p, i32p]
     lib.ngmlr_b200_sw_score_batch.argtypes = [vp, C.c_int, cpp, cpp, C.POINTER(C.c_float)]
+    lib.ngmlr_b200_cs_set_index.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint32, C.c_uint64, C.c_int, C.c_int]
+    lib.ngmlr_b200_cs_search_batch.argtypes = [vp, C.c_int, cpp, i32p, C.c_float, C.c_float, i64p,
+                                               C.POINTER(C.POINTER(C.c_float)),
+                                               C.POINTER(C.POINTER(C.c_uint64)),
+                                               C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_float)]
     lib.ngmlr_b200_sw_last_kernel_ms.argtypes = [vp]
     lib.ngmlr_b200_sw_last_kernel_ms.restype = C.c_float
     _lib = lib

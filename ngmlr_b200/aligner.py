@@ -148,6 +148,33 @@ class B200Aligner:
         self._check(self.lib.ngmlr_b200_convex_align_batch(self.h, *batch.c_args(), res))
         return self._collect(res, batch.n)
 
+    # ---- candidate search (CS::RunRead's search) --------------------------------------------
+    def set_index(self, index):
+        """index: ngmlr_b200.refindex.KmerIndex (the reference's CompactPrefixTable arrays)."""
+        packed = np.ascontiguousarray(index.packed_index())
+        pos = np.ascontiguousarray(index.pos, dtype=np.uint32)
+        self._check(self.lib.ngmlr_b200_cs_set_index(
+            self.h, packed.ctypes.data_as(C.c_void_p), index.tab.size, pos.ctypes.data_as(C.c_void_p),
+            pos.size, 0, index.k, index.bin_shift))
+
+    def cs_search(self, seqs, sensitivity=0.8, min_kmer_hits=0.0):
+        """Candidates of each (sub-)read, in the reference's emission order:
+        list of [(score, location, reverse)], plus maxHitNumber per read."""
+        n = len(seqs)
+        arr = (C.c_char_p * n)(*[bytes(s) for s in seqs])
+        lens = np.array([len(s) for s in seqs], dtype=np.int32)
+        start = np.zeros(n + 1, dtype=np.int64)
+        mx = np.zeros(max(n, 1), dtype=np.float32)
+        sc, lo, rv = C.POINTER(C.c_float)(), C.POINTER(C.c_uint64)(), C.POINTER(C.c_uint8)()
+        self._check(self.lib.ngmlr_b200_cs_search_batch(
+            self.h, n, arr, lens.ctypes.data_as(C.POINTER(C.c_int32)), sensitivity, min_kmer_hits,
+            start.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(sc), C.byref(lo), C.byref(rv),
+            mx.ctypes.data_as(C.POINTER(C.c_float))))
+        out = []
+        for i in range(n):
+            out.append([(sc[j], int(lo[j]), int(rv[j])) for j in range(start[i], start[i + 1])])
+        return out, mx[:n]
+
     # ---- phased interface (bench: inputs resident in HBM) ---------------------------------
     def upload(self, batch):
         self._n = batch.n

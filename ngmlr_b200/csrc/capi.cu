@@ -14,6 +14,7 @@
 #include <chrono>
 #include <numeric>
 #include <stdlib.h>
+#include <mutex>
 #include <thread>
 #include <string>
 #include <vector>
@@ -138,6 +139,8 @@ bool scoring_needs_raw(const Scoring& s) {
 }
 
 }  // namespace
+
+void nb_cs_release(ngmlr_b200_ctx* ctx);  // candidate-search state lives in a side table (below)
 
 struct ngmlr_b200_ctx {
   int device = 0;
@@ -274,6 +277,7 @@ void ngmlr_b200_destroy(ngmlr_b200_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  nb_cs_release(ctx);
   ctx->h_seq.release(); ctx->h_coff.release(); ctx->h_clen.release(); ctx->h_order.release();
   ctx->h_desc.release(); ctx->h_fill.release(); ctx->h_trace.release(); ctx->h_runs.release();
   ctx->h_counters.release();
@@ -777,6 +781,215 @@ float ngmlr_b200_sw_last_kernel_ms(ngmlr_b200_ctx* ctx) {
   float ms = 0;
   if (ctx) cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]);
   return ms;
+}
+
+}  // extern "C"
+
+// ============================================================================================
+// candidate search
+// ============================================================================================
+namespace {
+
+struct CsState {
+  DevBuf<uint8_t> d_packed;
+  DevBuf<uint32_t> d_tab, d_pos, d_order;
+  DevBuf<uint8_t> d_used, d_seq, d_tables;
+  DevBuf<uint64_t> d_off;     // seq_off | table_off | order_off | out_off
+  DevBuf<int32_t> d_len, d_count;
+  DevBuf<uint32_t> d_cap;
+  DevBuf<unsigned long long> d_hits;
+  DevBuf<float> d_max;
+  DevBuf<CsCandidate> d_out;
+  uint32_t index_len = 0, n_pos = 0;
+  uint64_t unit_offset = 0;
+  int k = 0, bin_shift = 0;
+  std::vector<float> scores;
+  std::vector<uint64_t> locs;
+  std::vector<uint8_t> reverse;
+  float last_ms = 0;
+};
+
+std::vector<std::pair<ngmlr_b200_ctx*, CsState*>> g_cs_states;
+std::mutex* g_cs_mutex = new std::mutex();
+
+CsState* cs_state(ngmlr_b200_ctx* ctx, bool create) {
+  std::lock_guard<std::mutex> lock(*g_cs_mutex);
+  for (auto& kv : g_cs_states)
+    if (kv.first == ctx) return kv.second;
+  if (!create) return nullptr;
+  g_cs_states.emplace_back(ctx, new CsState());
+  return g_cs_states.back().second;
+}
+
+}  // namespace
+
+void nb_cs_release(ngmlr_b200_ctx* ctx) {
+  std::lock_guard<std::mutex> lock(*g_cs_mutex);
+  for (size_t i = 0; i < g_cs_states.size(); ++i) {
+    if (g_cs_states[i].first != ctx) continue;
+    CsState* cs = g_cs_states[i].second;
+    cs->d_packed.release(); cs->d_tab.release(); cs->d_pos.release(); cs->d_order.release();
+    cs->d_used.release(); cs->d_seq.release(); cs->d_tables.release(); cs->d_off.release();
+    cs->d_len.release(); cs->d_count.release(); cs->d_cap.release(); cs->d_hits.release();
+    cs->d_max.release(); cs->d_out.release();
+    delete cs;
+    g_cs_states.erase(g_cs_states.begin() + i);
+    return;
+  }
+}
+
+extern "C" {
+
+int ngmlr_b200_cs_set_index(ngmlr_b200_ctx* ctx, const void* packed_index, uint32_t index_len,
+                            const uint32_t* positions, uint32_t n_positions, uint64_t unit_offset,
+                            int k, int bin_shift) {
+  if (!ctx) return -1;
+  if (k < 1 || k > 16) return ctx->fail("cs_set_index: k must be in 1..16");
+  if (index_len != (1u << (2 * k)) + 1u) return ctx->fail("cs_set_index: index_len must be 4^k + 1");
+  CU(cudaSetDevice(ctx->device));
+  CsState* cs = cs_state(ctx, true);
+  cudaStream_t st = ctx->stream;
+  CU(cs->d_packed.reserve((size_t)index_len * 5));
+  CU(cs->d_tab.reserve((size_t)index_len + 1));
+  CU(cs->d_used.reserve((size_t)index_len + 1));
+  CU(cs->d_pos.reserve((size_t)n_positions + 1));
+  CU(cudaMemcpyAsync(cs->d_packed.p, packed_index, (size_t)index_len * 5, cudaMemcpyHostToDevice, st));
+  if (n_positions)
+    CU(cudaMemcpyAsync(cs->d_pos.p, positions, (size_t)n_positions * 4, cudaMemcpyHostToDevice, st));
+  CU(launch_unpack_index(cs->d_packed.p, index_len, cs->d_tab.p, cs->d_used.p, st));
+  CU(cudaStreamSynchronize(st));
+  cs->d_packed.release();
+  cs->index_len = index_len;
+  cs->n_pos = n_positions;
+  cs->unit_offset = unit_offset;
+  cs->k = k;
+  cs->bin_shift = bin_shift;
+  return 0;
+}
+
+int ngmlr_b200_cs_search_batch(ngmlr_b200_ctx* ctx, int n, const char* const* seqs,
+                               const int32_t* lens, float sensitivity, float min_kmer_hits,
+                               int64_t* cand_start, const float** scores, const uint64_t** locs,
+                               const uint8_t** reverse, float* max_hits) {
+  if (!ctx) return -1;
+  CsState* cs = cs_state(ctx, false);
+  if (!cs || !cs->index_len) return ctx->fail("cs_search_batch: call cs_set_index first");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  cs->scores.clear();
+  cs->locs.clear();
+  cs->reverse.clear();
+  cand_start[0] = 0;
+  if (n <= 0) return 0;
+  // ---- reads -> device ----
+  std::vector<uint64_t> seq_off(n);
+  size_t bytes = 0;
+  for (int i = 0; i < n; ++i) {
+    seq_off[i] = bytes;
+    bytes += align_up((size_t)std::max(lens[i], 0) + 1, 16);
+  }
+  std::vector<uint8_t> hseq(bytes + 16, 0);
+  parallel_for(n, 256, [&](int i) { memcpy(hseq.data() + seq_off[i], seqs[i], (size_t)std::max(lens[i], 0)); });
+  CU(cs->d_seq.reserve(bytes + 16));
+  CU(cs->d_off.reserve((size_t)4 * n));
+  CU(cs->d_len.reserve(n));
+  CU(cs->d_hits.reserve(n));
+  CU(cs->d_cap.reserve(n));
+  CU(cs->d_count.reserve(n));
+  CU(cs->d_max.reserve(n));
+  CU(cudaMemcpyAsync(cs->d_seq.p, hseq.data(), bytes, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(cs->d_off.p, seq_off.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(cs->d_len.p, lens, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  CsParams p;
+  memset(&p, 0, sizeof(p));
+  p.tab = cs->d_tab.p;
+  p.used = cs->d_used.p;
+  p.pos = cs->d_pos.p;
+  p.unit_offset = cs->unit_offset;
+  p.k = cs->k;
+  p.bin_shift = cs->bin_shift;
+  p.sensitivity = sensitivity;
+  p.min_kmer_hits = min_kmer_hits;
+  p.seq = cs->d_seq.p;
+  p.seq_off = cs->d_off.p;
+  p.seq_len = cs->d_len.p;
+  p.n = n;
+  p.hits = cs->d_hits.p;
+  // ---- pass 1: hits per read ----
+  CU(cudaEventRecord(ctx->ev[4], st));
+  CU(launch_cs_search(p, true, st));
+  std::vector<unsigned long long> hits(n);
+  CU(cudaMemcpyAsync(hits.data(), cs->d_hits.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  // ---- pass 2 in chunks bounded by a device-memory budget ----
+  const size_t budget = (size_t)4 << 30;
+  std::vector<uint64_t> toff(n), ooff(n), roff(n);
+  std::vector<uint32_t> caps(n);
+  std::vector<int32_t> counts(n);
+  std::vector<CsCandidate> hout;
+  int first = 0;
+  while (first < n) {
+    size_t tent = 0, oent = 0, rent = 0;
+    int last = first;
+    while (last < n) {
+      uint32_t cap = 16;
+      while ((unsigned long long)cap < 2 * hits[last] + 2) cap <<= 1;
+      const size_t need = (size_t)cap * 16 + (size_t)hits[last] * 4 + (size_t)hits[last] * 2 * 16;
+      if (last > first && (tent * 16 + oent * 4 + rent * 16 + need) > budget) break;
+      caps[last] = cap;
+      toff[last] = tent;
+      ooff[last] = oent;
+      roff[last] = rent;
+      tent += cap;
+      oent += (size_t)hits[last];
+      rent += (size_t)hits[last] * 2;
+      ++last;
+    }
+    const int m = last - first;
+    CU(cs->d_tables.reserve(tent * 16 + 16));
+    CU(cs->d_order.reserve(oent + 4));
+    CU(cs->d_out.reserve(rent + 4));
+    CU(cudaMemsetAsync(cs->d_tables.p, 0, tent * 16, st));
+    CU(cudaMemcpyAsync(cs->d_off.p + (size_t)n, toff.data() + first, (size_t)m * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(cs->d_off.p + (size_t)2 * n, ooff.data() + first, (size_t)m * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(cs->d_off.p + (size_t)3 * n, roff.data() + first, (size_t)m * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(cs->d_cap.p, caps.data() + first, (size_t)m * 4, cudaMemcpyHostToDevice, st));
+    CsParams q = p;
+    q.seq_off = cs->d_off.p + first;
+    q.seq_len = cs->d_len.p + first;
+    q.n = m;
+    q.tables = cs->d_tables.p;
+    q.table_off = cs->d_off.p + (size_t)n;
+    q.table_cap = cs->d_cap.p;
+    q.order = cs->d_order.p;
+    q.order_off = cs->d_off.p + (size_t)2 * n;
+    q.out = cs->d_out.p;
+    q.out_off = cs->d_off.p + (size_t)3 * n;
+    q.out_count = cs->d_count.p;
+    q.max_hits = cs->d_max.p;
+    CU(launch_cs_search(q, false, st));
+    hout.resize(rent + 1);
+    CU(cudaMemcpyAsync(counts.data() + first, cs->d_count.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(max_hits + first, cs->d_max.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+    if (rent) CU(cudaMemcpyAsync(hout.data(), cs->d_out.p, rent * sizeof(CsCandidate), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int i = first; i < last; ++i) {
+      const CsCandidate* c = hout.data() + roff[i];
+      for (int j = 0; j < counts[i]; ++j) {
+        cs->scores.push_back(c[j].score);
+        cs->locs.push_back(c[j].loc);
+        cs->reverse.push_back((uint8_t)c[j].reverse);
+      }
+      cand_start[i + 1] = (int64_t)cs->scores.size();
+    }
+    first = last;
+  }
+  CU(cudaEventRecord(ctx->ev[5], st));
+  CU(cudaStreamSynchronize(st));
+  *scores = cs->scores.data();
+  *locs = cs->locs.data();
+  *reverse = cs->reverse.data();
+  return n;
 }
 
 }  // extern "C"

@@ -106,4 +106,38 @@ struct TraceParams {
   unsigned long long* runs_alloc;
 };
 
+// ---- candidate search -------------------------------------------------------------------
+struct alignas(16) CsCandidate {
+  unsigned long long loc;  // LocationScore::Location.m_Location = ResolveBin(bin)
+  float score;             // LocationScore::Score.f
+  uint32_t reverse;        // SequenceLocation::isReverse()
+};
+
+struct CsParams {
+  // index (one table unit)
+  const uint32_t* tab;     // Index::m_TabIndex, 4^k + 1 entries
+  const uint8_t* used;     // Index::used()
+  const uint32_t* pos;     // Location::m_Location lists
+  unsigned long long unit_offset;
+  int k, bin_shift;
+  float sensitivity, min_kmer_hits;
+  // reads
+  const uint8_t* seq;
+  const uint64_t* seq_off;
+  const int32_t* seq_len;
+  int n;
+  // pass 1
+  unsigned long long* hits;
+  // pass 2
+  void* tables;
+  const uint64_t* table_off;   // in entries
+  const uint32_t* table_cap;   // power of two
+  uint32_t* order;
+  const uint64_t* order_off;
+  CsCandidate* out;
+  const uint64_t* out_off;
+  int32_t* out_count;
+  float* max_hits;
+};
+
 }  // namespace nb

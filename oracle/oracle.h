@@ -64,6 +64,24 @@ float or_ssw_score(const char* ref, const char* qry);
 float or_ssw_score_striped(const char* ref, const char* qry);
 int or_ssw_batch_score(int n, const char* const* refs, const char* const* qrys, float* results);
 
+/* ---- candidate search (stage 0), reference layout, k-mer index: oracle/cs_oracle.c ---------- */
+struct or_cs;
+struct or_cs* or_cs_create(int ncontigs, const char* const* contigs, const int64_t* lens);
+void or_cs_destroy(struct or_cs* h);
+uint64_t or_cs_concat_len(const struct or_cs* h);
+int or_cs_ref_count(const struct or_cs* h);
+uint64_t or_cs_ref_start(const struct or_cs* h, int i);
+const uint8_t* or_cs_encoded(const struct or_cs* h, uint64_t* bytes);
+int or_cs_decode(const struct or_cs* h, uint64_t position, uint64_t buffer_len, char* out);
+int or_cs_build_index(struct or_cs* h, int k, int skip, int bin_shift, int max_freq);
+uint32_t or_cs_index_len(const struct or_cs* h);
+uint32_t or_cs_npos(const struct or_cs* h);
+const uint32_t* or_cs_tab(const struct or_cs* h);
+const int8_t* or_cs_rci(const struct or_cs* h);
+const uint32_t* or_cs_pos(const struct or_cs* h);
+int or_cs_search(const struct or_cs* h, const char* seq, int len, float sensitivity, float min_kmer_hits,
+                 float* scores, uint64_t* locs, int* reverse, int cap, float* max_hits);
+
 #ifdef __cplusplus
 }
 #endif

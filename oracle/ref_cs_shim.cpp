@@ -1,0 +1,174 @@
+// oracle/ref_cs_shim.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// extern "C" driver around the UNMODIFIED reference's candidate search, compiled together with all
+// of /root/reference/src (except main.cpp) into oracle/_ref/libngmlr_full.so by oracle/Makefile.
+// It runs the reference's own code for:
+//   reference encoding      _SequenceProvider::Init / DecodeRefSequence   src/SequenceProvider.cpp:292-473, 567-625
+//   k-mer index             CompactPrefixTable (build + GetRefEntry)        src/PrefixTable.cpp:233-532
+//   k-mer iteration         CS::PrefixIteration                            src/CSstatic.cpp:23-73
+//   vote + collect          CS::PrefixSearch / AddLocationStd / CollectResultsStd   src/CS.cpp:57-149, 217-269
+// through a CS subclass that repeats only the control flow of CS::RunRead (src/CS.cpp:324-398)
+// without handing the read to ScoreBuffer.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#define private public
+#define protected public
+#include "CS.h"
+#include "IConfig.h"
+#include "Log.h"
+#include "NGM.h"
+#include "PrefixTable.h"
+#include "SequenceProvider.h"
+#undef private
+#undef protected
+
+ILog const* _log = 0;
+IConfig* _config = 0;
+
+// main.cpp (not linked) also owns this helper (src/main.cpp:135-155); same contract, via stat().
+#include <sys/stat.h>
+uloc const FileSize(char const* const filename) {
+  struct stat st;
+  if (stat(filename, &st) != 0) return 0;
+  return (uloc)st.st_size;
+}
+
+namespace {
+
+CompactPrefixTable* g_table = 0;
+
+class CSProbe : public CS {
+ public:
+  CSProbe() : CS(false) {
+    int len = (int)pow(2, 24);  // x_SrchTableBitLen, src/CS.cpp:27, 422-432
+    rTable = new CSTableEntry[len];
+    rList = new int[len];
+    for (int i = 0; i < len; ++i) {
+      rTable[i].m_Location = (uint)9223372036854775808ull;
+      rTable[i].state = -1;
+      rList[i] = -1;
+    }
+    m_CsSensitivity = Config.getSensitivity();
+    m_RefProvider = g_table;
+    m_entryCount = m_RefProvider->GetRefEntryChainLength();
+    m_entry = new RefEntry[m_entryCount];
+  }
+
+  // CS::RunRead minus SendToBuffer. Returns candidate count or -1 if every table size overflowed.
+  int search(MappedRead* read, int table_bits) {
+    SetSearchTableBitLen(table_bits);
+    currentState++;
+    rListLength = 0;
+    maxHitNumber = 0.0f;
+    currentThresh = 0.0f;
+    extern int kCount;
+    m_CurrentReadLength = read->length;
+    bool fallback = false;
+    int n = -1;
+    try {
+      hpoc = c_SrchTableLen * 0.333f;
+      PrefixIteration(read->Seq, read->length, &CS::PrefixSearch, 0, 0, this, m_PrefixBaseSkip);
+      n = CollectResultsStd(read);
+    } catch (int) {
+      fallback = true;
+    }
+    if (fallback) {
+      int backup = c_SrchTableBitLen, x = 2;
+      while (fallback && (backup + x) <= 20) {
+        fallback = false;
+        try {
+          SetSearchTableBitLen(backup + x);
+          rListLength = 0;
+          currentState++;
+          maxHitNumber = 0.0f;
+          currentThresh = 0.0f;
+          hpoc = c_SrchTableLen * 0.777f;
+          PrefixIteration(read->Seq, read->length, &CS::PrefixSearch, 0, 0, this, m_PrefixBaseSkip);
+          n = CollectResultsStd(read);
+        } catch (int) {
+          fallback = true;
+          x += 1;
+        }
+      }
+      SetSearchTableBitLen(backup);
+      if (fallback) n = -1;
+    }
+    return n;
+  }
+};
+
+CSProbe* g_probe = 0;
+
+}  // namespace
+
+extern "C" {
+
+// Builds encoded reference + k-mer index from a FASTA file with the reference's own code.
+int ref_cs_init(const char* fasta) {
+  IConfig* c = new IConfig();
+  c->referenceFile = strdup(fasta);
+  c->queryFile = strdup(fasta);
+  c->outputFile = strdup("/dev/null");
+  c->skipSave = true;
+  c->progress = false;
+  _config = c;
+  _Log::Init(0, 0);
+  _log = &Log;
+  CS::Init();
+  SequenceProvider.Init();
+  g_table = new CompactPrefixTable();
+  g_probe = new CSProbe();
+  return 0;
+}
+
+unsigned long long ref_cs_concat_len() { return SequenceProvider.GetConcatRefLen(); }
+int ref_cs_ref_count() { return SequenceProvider.GetRefCount(); }
+unsigned long long ref_cs_ref_start(int n) { return SequenceProvider.GetRefStart(n); }
+unsigned long long ref_cs_ref_len(int n) { return SequenceProvider.GetRefLen(n); }
+
+// DecodeRefSequence(buffer, 0, offset, len): the call ScoreBuffer makes (src/ScoreBuffer.cpp:110)
+int ref_cs_decode(unsigned long long offset, unsigned long long len, char* buf) {
+  return SequenceProvider.DecodeRefSequence(buf, 0, offset, len) ? 1 : 0;
+}
+int ref_cs_decode_exact(unsigned long long offset, unsigned long long len, int corridor, char* buf) {
+  return SequenceProvider.DecodeRefSequenceExact(buf, offset, len, corridor) ? 1 : 0;
+}
+
+// Raw index of unit 0: packed 5-byte Index records and uint32 locations.
+const void* ref_cs_index(unsigned* index_len, const unsigned** ref_table, unsigned* ref_table_len,
+                         unsigned long long* unit_offset, unsigned* unit_count) {
+  *index_len = (unsigned)pow(4.0, (double)CS::prefixBasecount) + 1;
+  *ref_table = reinterpret_cast<const unsigned*>(g_table->m_Units[0].RefTable);
+  *ref_table_len = g_table->m_Units[0].cRefTableLen;
+  *unit_offset = g_table->m_Units[0].Offset;
+  *unit_count = g_table->m_UnitCount;
+  return g_table->m_Units[0].RefTableIndex;
+}
+
+// One (sub-)read through the reference's vote. Outputs in the reference's emission order.
+int ref_cs_search(const char* seq, int len, int table_bits, float* scores, unsigned long long* locs,
+                  int* reverse, int cap, float* max_hits) {
+  MappedRead* read = new MappedRead(0, len + 16);
+  read->Seq = new char[len + 16];
+  memcpy(read->Seq, seq, len);
+  read->Seq[len] = 0;
+  read->length = len;
+  int n = g_probe->search(read, table_bits);
+  *max_hits = g_probe->maxHitNumber;
+  int m = read->numScores();
+  if (n >= 0) {
+    for (int i = 0; i < m && i < cap; ++i) {
+      scores[i] = read->Scores[i].Score.f;
+      locs[i] = read->Scores[i].Location.m_Location;
+      reverse[i] = read->Scores[i].Location.isReverse() ? 1 : 0;
+    }
+  }
+  delete read;
+  return n < 0 ? -1 : m;
+}
+
+}  // extern "C"

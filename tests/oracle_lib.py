@@ -168,3 +168,123 @@ def same_alignment(a, b):
     if not bad and not np.array_equal(a["nm_positions"], b["nm_positions"]):
         bad.append("nm_positions")
     return bad
+
+
+# ---------------------------------------------------------------------------------------------
+# candidate search (stage 0)
+# ---------------------------------------------------------------------------------------------
+class CsOracle:
+    """C restatement of the reference layout, k-mer index and vote (oracle/cs_oracle.c)."""
+
+    def __init__(self, contigs, k=13, skip=2, bin_shift=4, max_freq=1000):
+        path = os.path.join(ORACLE_DIR, "liboracle.so")
+        if not os.path.exists(path):
+            build_oracle()
+        lib = C.CDLL(path)
+        lib.or_cs_create.restype = C.c_void_p
+        lib.or_cs_concat_len.restype = C.c_uint64
+        lib.or_cs_ref_start.restype = C.c_uint64
+        for f in ("or_cs_tab", "or_cs_rci", "or_cs_pos", "or_cs_encoded"):
+            getattr(lib, f).restype = C.c_void_p
+        lib.or_cs_index_len.restype = C.c_uint32
+        lib.or_cs_npos.restype = C.c_uint32
+        self.lib = lib
+        self.contigs = [bytes(c) for c in contigs]
+        arr = (C.c_char_p * len(contigs))(*self.contigs)
+        lens = (C.c_int64 * len(contigs))(*[len(c) for c in self.contigs])
+        self.h = C.c_void_p(lib.or_cs_create(len(contigs), arr, lens))
+        lib.or_cs_build_index(self.h, k, skip, bin_shift, max_freq)
+
+    def close(self):
+        if self.h:
+            self.lib.or_cs_destroy(self.h)
+            self.h = None
+
+    @property
+    def concat_len(self):
+        return int(self.lib.or_cs_concat_len(self.h))
+
+    def ref_starts(self):
+        return [int(self.lib.or_cs_ref_start(self.h, i)) for i in range(self.lib.or_cs_ref_count(self.h))]
+
+    def encoded(self):
+        n = C.c_uint64()
+        p = self.lib.or_cs_encoded(self.h, C.byref(n))
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n.value,)).copy()
+
+    def index(self):
+        n = int(self.lib.or_cs_index_len(self.h))
+        npos = int(self.lib.or_cs_npos(self.h))
+        tab = np.ctypeslib.as_array(C.cast(self.lib.or_cs_tab(self.h), C.POINTER(C.c_uint32)), shape=(n,)).copy()
+        rci = np.ctypeslib.as_array(C.cast(self.lib.or_cs_rci(self.h), C.POINTER(C.c_int8)), shape=(n,)).copy()
+        pos = np.ctypeslib.as_array(C.cast(self.lib.or_cs_pos(self.h), C.POINTER(C.c_uint32)), shape=(npos + 1,)).copy()
+        return tab, rci, pos[:npos]
+
+    def decode(self, position, buffer_len=308):
+        buf = C.create_string_buffer(buffer_len + 4)
+        ok = self.lib.or_cs_decode(self.h, C.c_uint64(position), C.c_uint64(buffer_len), buf)
+        return buf.value if ok else None
+
+    def search(self, seq, sensitivity=0.8, min_kmer_hits=0.0, cap=4096):
+        sc = (C.c_float * cap)()
+        lo = (C.c_uint64 * cap)()
+        rv = (C.c_int * cap)()
+        mh = C.c_float()
+        n = self.lib.or_cs_search(self.h, bytes(seq), len(seq), C.c_float(sensitivity),
+                                  C.c_float(min_kmer_hits), sc, lo, rv, cap, C.byref(mh))
+        return [(sc[i], int(lo[i]), rv[i]) for i in range(min(n, cap))], mh.value
+
+
+class CsReference:
+    """The unmodified reference's candidate search (oracle/_ref/libngmlr_full.so). One instance per
+    process: the reference keeps its state in singletons."""
+
+    PATH = os.path.join(ORACLE_DIR, "_ref", "libngmlr_full.so")
+    _inited = None
+
+    @classmethod
+    def available(cls):
+        return os.path.exists(cls.PATH)
+
+    def __init__(self, fasta_path):
+        assert CsReference._inited in (None, fasta_path), "reference singletons already initialised"
+        self.lib = C.CDLL(self.PATH)
+        lib = self.lib
+        lib.ref_cs_concat_len.restype = C.c_ulonglong
+        lib.ref_cs_ref_start.restype = C.c_ulonglong
+        lib.ref_cs_ref_len.restype = C.c_ulonglong
+        lib.ref_cs_index.restype = C.c_void_p
+        if CsReference._inited is None:
+            lib.ref_cs_init(fasta_path.encode())
+            CsReference._inited = fasta_path
+
+    @property
+    def concat_len(self):
+        return int(self.lib.ref_cs_concat_len())
+
+    def ref_starts(self):
+        return [int(self.lib.ref_cs_ref_start(i)) for i in range(0, self.lib.ref_cs_ref_count(), 2)]
+
+    def index(self):
+        il, rl, uo, uc = C.c_uint(), C.c_uint(), C.c_ulonglong(), C.c_uint()
+        rt = C.POINTER(C.c_uint)()
+        ip = self.lib.ref_cs_index(C.byref(il), C.byref(rt), C.byref(rl), C.byref(uo), C.byref(uc))
+        raw = np.ctypeslib.as_array(C.cast(ip, C.POINTER(C.c_uint8)), shape=(il.value * 5,)).reshape(-1, 5)
+        tab = raw[:, :4].copy().view(np.uint32).reshape(-1)
+        rci = raw[:, 4].copy().view(np.int8)
+        pos = np.ctypeslib.as_array(rt, shape=(rl.value + 1,))[:rl.value].copy()
+        assert uo.value == 0 and uc.value == 1
+        return tab, rci, pos
+
+    def decode(self, position, buffer_len=308):
+        buf = C.create_string_buffer(buffer_len + 4)
+        ok = self.lib.ref_cs_decode(C.c_ulonglong(position), C.c_ulonglong(buffer_len), buf)
+        return buf.value if ok else None
+
+    def search(self, seq, table_bits=16, cap=4096):
+        sc = (C.c_float * cap)()
+        lo = (C.c_ulonglong * cap)()
+        rv = (C.c_int * cap)()
+        mh = C.c_float()
+        n = self.lib.ref_cs_search(bytes(seq), len(seq), table_bits, sc, lo, rv, cap, C.byref(mh))
+        return [(sc[i], int(lo[i]), rv[i]) for i in range(max(0, min(n, cap)))], mh.value
