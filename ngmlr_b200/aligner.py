@@ -196,6 +196,10 @@ class B200Aligner:
     def force_raw(self, v):
         self.lib.ngmlr_b200_set_force_raw(self.h, int(v))
 
+    def force_team(self, v):
+        """-1 auto, 0 one warp per problem, 1 four-warp teams (fill kernel scheduling)."""
+        self.lib.ngmlr_b200_set_force_team(self.h, int(v))
+
     def debug_directions(self, i, total_cells):
         dirs = np.zeros(total_cells + 1, dtype=np.uint8)
         bs, bx, by = C.c_float(), C.c_int32(), C.c_int32()

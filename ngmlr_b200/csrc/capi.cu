@@ -158,6 +158,8 @@ struct ngmlr_b200_ctx {
   size_t seq_bytes = 0, rows = 0, nblocks = 0, tb_ints = 0;
   int max_len = 0;
   int max_ref_len = 0;
+  int wide_problems = 0;  // problems whose corridor is >= 352 columns wide
+  int force_team = -1;
   PinBuf<uint8_t> h_seq;
   PinBuf<int32_t> h_coff, h_clen, h_order;
   PinBuf<AlnDesc> h_desc;
@@ -269,6 +271,7 @@ int ngmlr_b200_create(int gpu_id, const ngmlr_b200_scoring* s, ngmlr_b200_ctx** 
   ctx->sc.ext_min = d.gap_extend_min;
   ctx->sc.decay = d.gap_decay;
   ctx->raw = scoring_needs_raw(ctx->sc);
+  if (const char* e = getenv("NGMLR_B200_FILL_TEAM")) ctx->force_team = atoi(e);
   *out = ctx;
   return 0;
 }
@@ -309,6 +312,13 @@ int ngmlr_b200_set_stream(ngmlr_b200_ctx* ctx, void* s) {
 }
 
 void* ngmlr_b200_get_stream(ngmlr_b200_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+// force_team: -1 auto, 0 one warp per problem, 1 four-warp teams. Test / tuning hook.
+int ngmlr_b200_set_force_team(ngmlr_b200_ctx* ctx, int v) {
+  if (!ctx) return -1;
+  ctx->force_team = v;
+  return 0;
+}
 
 // force_raw: -1 auto (by scoring), 0 scalar-rule kernel, 1 as-coded (RAW) kernel. Test hook.
 int ngmlr_b200_set_force_raw(ngmlr_b200_ctx* ctx, int v) {
@@ -418,7 +428,9 @@ int ngmlr_b200_convex_upload(ngmlr_b200_ctx* ctx, int n, const char* const* refs
   int max_len_all = 0;
   size_t dir_words = 0;
   ctx->max_ref_len = 0;
+  ctx->wide_problems = 0;
   for (int i = 0; i < n; ++i) {
+    if (maxlen[i] >= 352) ctx->wide_problems++;
     max_len_all = std::max(max_len_all, maxlen[i]);
     ctx->max_ref_len = std::max(ctx->max_ref_len, ref_lens[i]);
     dir_words += dirw[i];
@@ -481,10 +493,16 @@ int ngmlr_b200_convex_run(ngmlr_b200_ctx* ctx) {
   const int n = ctx->n;
   const double t_run0 = now_ms();
   const bool raw = ctx->force_raw < 0 ? (ctx->raw || ctx->max_len > 32767) : (ctx->force_raw != 0);
-  static int ctas_per_sm[2] = {0, 0};
-  if (!ctas_per_sm[raw]) ctas_per_sm[raw] = std::max(1, fill_max_ctas_per_sm(raw));
-  const int max_grid = ctx->num_sms * ctas_per_sm[raw];
-  const int want_grid = (n + FILL_WARPS_PER_CTA - 1) / FILL_WARPS_PER_CTA;
+  // Team mode (4 warps pipeline one problem) when the corridors are wide enough for the pipeline to
+  // stay full (a warp must still be busy with its block when the fourth warp behind it has produced
+  // the first chunk of the next one: ~4 x 100 columns); NGMLR_B200_FILL_TEAM=0/1 overrides.
+  bool team = ctx->wide_problems * 2 > n;
+  if (ctx->force_team >= 0) team = ctx->force_team != 0;
+  static int ctas_per_sm[4] = {0, 0, 0, 0};
+  const int variant = (raw ? 1 : 0) | (team ? 2 : 0);
+  if (!ctas_per_sm[variant]) ctas_per_sm[variant] = std::max(1, fill_max_ctas_per_sm(raw, team));
+  const int max_grid = ctx->num_sms * ctas_per_sm[variant];
+  const int want_grid = team ? n : (n + FILL_WARPS_PER_CTA - 1) / FILL_WARPS_PER_CTA;
   const int grid = std::max(1, std::min(max_grid, want_grid));
   ctx->fill_grid = grid;
   const size_t warps = (size_t)grid * FILL_WARPS_PER_CTA;
@@ -529,7 +547,7 @@ int ngmlr_b200_convex_run(ngmlr_b200_ctx* ctx) {
     tp.runs_alloc = ctx->d_counters.p + 1;
 
     CU(cudaEventRecord(ctx->ev[0], st));
-    CU(launch_convex_fill(fp, raw, grid, st));
+    CU(launch_convex_fill(fp, raw, team, grid, st));
     CU(cudaEventRecord(ctx->ev[1], st));
     CU(launch_convex_traceback(tp, st));
     CU(cudaEventRecord(ctx->ev[2], st));

@@ -19,6 +19,13 @@
 // chunks are flushed back coalesced. Because lane 31 always trails lane 0 by 31 columns the strip
 // is updated in place for any corridor shape.
 //
+// Team mode (NW = 4). One warp per problem leaves a long tail behind the largest matrices (the
+// reference sees 93 M-cell matrices). In team mode the 4 warps of a CTA share one problem: warp w
+// takes the 32-row blocks b = w, w+4, w+8, ... and block b+1 consumes the strip records of block b
+// as they are produced (16-step chunks, progress published through shared memory), so the four
+// warps run as a software pipeline about 100 columns apart and a problem finishes ~4x sooner at
+// the same total work.
+//
 // HBM traffic. The only per-cell output is the traceback direction: 2 bits per cell (EQ/X are
 // re-derived by the traceback), 16 steps per 32-bit word, written as one fully coalesced 128-byte
 // warp store every 16 steps (word index = group*32 + lane). The reference spends 1 byte per cell
@@ -41,24 +48,69 @@ namespace nb {
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int CHUNK = 64;        // steps staged through shared memory at a time
 constexpr int STRIP_PAD = 32;    // strip index = column + STRIP_PAD (lane 31 trails lane 0 by 31)
+constexpr unsigned X_BIAS = 1u << 20;
 
 __device__ __forceinline__ uint4 ld_strip(const uint4* p) { return __ldcg(p); }
 __device__ __forceinline__ void st_strip(uint4* p, uint4 v) { __stcg(p, v); }
 
-template <bool RAW>
+__device__ __forceinline__ unsigned long long prog_key(int blk, int x) {
+  return ((unsigned long long)(unsigned)(blk + 1) << 32) | (unsigned long long)((unsigned)x + X_BIAS);
+}
+
+// Geometry of one 32-row block, identical for the warp that fills it and the warp that consumes it.
+struct BlockGeom {
+  int base, ngroups;
+};
+
+__device__ __forceinline__ void row_span(int off, int len, int ref_len, int& xlo, int& xhi, unsigned& rlen) {
+  // columns of a row: [max(0,off), min(off+len, refLen))   (:943-950)
+  xlo = off > 0 ? off : 0;
+  const long long hi64 = (long long)off + (long long)len;
+  xhi = hi64 < (long long)ref_len ? (int)hi64 : ref_len;
+  rlen = xhi > xlo ? (unsigned)(xhi - xlo) : 0u;
+}
+
+__device__ __forceinline__ BlockGeom block_geom(int xlo, int xhi, unsigned rlen, int lane, int& nsteps) {
+  // base = leftmost column of the block: lane t first becomes active at step >= t, i.e. after the
+  // reference byte for its column has travelled down the shuffle chain from lane 0
+  const int lo_key = rlen ? xlo : INT_MAX;
+  const int hi_key = rlen ? xhi + lane : INT_MIN;
+  int base = __reduce_min_sync(FULL, lo_key);
+  const int send = __reduce_max_sync(FULL, hi_key);
+  nsteps = 0;
+  if (base != INT_MAX) nsteps = send - base; else base = 0;
+  BlockGeom g;
+  g.base = base;
+  g.ngroups = (nsteps + 15) >> 4;
+  return g;
+}
+
+struct TeamBest {
+  float S;
+  int x, y, firstX, firstY, status;
+  unsigned long long cells;
+};
+
+template <bool RAW, int NW>
 __global__ void __launch_bounds__(FILL_WARPS_PER_CTA * 32, FILL_CTAS_PER_SM)
 convex_fill_kernel(const FillParams p) {
+  constexpr int CHUNK = NW == 1 ? 64 : 16;  // steps staged through shared memory at a time
+  constexpr int GPC = CHUNK / 16;           // 16-step groups per chunk
+  static_assert(NW == 1 || NW == FILL_WARPS_PER_CTA, "a team is one warp or the whole CTA");
   __shared__ uint4 s_in[FILL_WARPS_PER_CTA][CHUNK + 1];  // +1: lane 31 reads one record ahead
   __shared__ uint4 s_out[FILL_WARPS_PER_CTA][CHUNK];
+  __shared__ volatile unsigned long long s_prog[FILL_WARPS_PER_CTA];
+  __shared__ int s_work;
+  __shared__ TeamBest s_best[FILL_WARPS_PER_CTA];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
-  const int warp_global = blockIdx.x * FILL_WARPS_PER_CTA + wib;
+  const int tw = NW == 1 ? 0 : wib;  // warp index within the team
+  const int team_global = NW == 1 ? blockIdx.x * FILL_WARPS_PER_CTA + wib : blockIdx.x;
   uint4* const in_s = s_in[wib];
   uint4* const out_s = s_out[wib];
-  // strip[x + STRIP_PAD] = {S, U, pack, -} of column x of the last finished block's bottom row
-  uint4* const strip = reinterpret_cast<uint4*>(p.bnd) + (size_t)warp_global * p.bnd_stride + STRIP_PAD;
+  // strip[x + STRIP_PAD] = {S, U, run, ref byte} of column x of the most recently finished bottom row
+  uint4* const strip = reinterpret_cast<uint4*>(p.bnd) + (size_t)team_global * p.bnd_stride + STRIP_PAD;
   const Scoring sc = p.sc;
   const uint32_t empty_pack = RAW ? (DIR_STOP << 16) : 0u;  // scalar kernel: run 0.0f
   const uint4 EMPTY = make_uint4(0u, __float_as_uint(sc.open_read), empty_pack, 0u);
@@ -67,8 +119,16 @@ convex_fill_kernel(const FillParams p) {
 
   for (;;) {
     int w = 0;
-    if (is0) w = atomicAdd(p.work_counter, 1);
-    w = __shfl_sync(FULL, w, 0);
+    if (NW == 1) {
+      if (is0) w = atomicAdd(p.work_counter, 1);
+      w = __shfl_sync(FULL, w, 0);
+    } else {
+      __syncthreads();  // previous problem fully retired (strip, progress words, s_work)
+      if (threadIdx.x == 0) s_work = atomicAdd(p.work_counter, 1);
+      if (threadIdx.x < NW) s_prog[threadIdx.x] = 0ull;
+      __syncthreads();
+      w = s_work;
+    }
     if (w >= p.n) break;
     const int ai = p.order[w];
     const AlnDesc d = p.desc[ai];
@@ -87,24 +147,25 @@ convex_fill_kernel(const FillParams p) {
     unsigned long long cells = 0;
     int status = ST_OK;
 
-    // columns of the strip that hold valid records of the row above the current block
-    int wlo = 0, whi = 0;  // nothing written yet: the row above block 0 does not exist
+    // strip columns [wlo, whi) hold records of the row above the current block; everything else
+    // reads as EMPTY. Nothing is written before block 0.
+    int wlo = 0, whi = 0;
 
-    // rows of the next block are fetched one block ahead
+    // rows of this warp's next block are fetched one block ahead
     int n_off = 0, n_len = 0;
     uint32_t n_q = 0x100u;  // never equals a byte
-    if (lane < H) {
-      n_off = coff[lane];
-      n_len = clen[lane];
-      n_q = qry[lane];
+    if ((tw << 5) + lane < H) {
+      n_off = coff[(tw << 5) + lane];
+      n_len = clen[(tw << 5) + lane];
+      n_q = qry[(tw << 5) + lane];
     }
 
-    for (int b = 0; b < nblk; ++b) {
+    for (int b = tw; b < nblk; b += NW) {
       const int y = (b << 5) + lane;
       const int off = n_off, len = n_len;
       const uint32_t q = n_q;
       {
-        const int yn = y + 32;
+        const int yn = y + 32 * NW;
         n_off = 0; n_len = 0; n_q = 0x100u;
         if (yn < H) {
           n_off = coff[yn];
@@ -112,21 +173,12 @@ convex_fill_kernel(const FillParams p) {
           n_q = qry[yn];
         }
       }
-      // columns of this row: [max(0,off), min(off+len, refLen))   (:943-950)
-      const int xlo = off > 0 ? off : 0;
-      const long long hi64 = (long long)off + (long long)len;
-      const int xhi = hi64 < (long long)ref_len ? (int)hi64 : ref_len;
-      const unsigned rlen = xhi > xlo ? (unsigned)(xhi - xlo) : 0u;
-      // base = leftmost column of the block: lane t first becomes active at step >= t, i.e. after the
-      // reference byte for its column has travelled down the shuffle chain from lane 0
-      const int lo_key = rlen ? xlo : INT_MAX;
-      const int hi_key = rlen ? xhi + lane : INT_MIN;
-      int base = __reduce_min_sync(FULL, lo_key);
-      const int send = __reduce_max_sync(FULL, hi_key);
-      int nsteps = 0;
-      if (base != INT_MAX) nsteps = send - base; else base = 0;
-      const int ngroups = (nsteps + 15) >> 4;
-      const int nchunks = (ngroups + 3) >> 2;
+      int xlo, xhi, nsteps;
+      unsigned rlen;
+      row_span(off, len, ref_len, xlo, xhi, rlen);
+      const BlockGeom geo = block_geom(xlo, xhi, rlen, lane, nsteps);
+      const int base = geo.base, ngroups = geo.ngroups;
+      const int nchunks = (ngroups + GPC - 1) / GPC;
       cells += rlen;
       if (firstY < 0) {
         const unsigned any = __ballot_sync(FULL, rlen != 0);
@@ -136,6 +188,35 @@ convex_fill_kernel(const FillParams p) {
           firstX = __shfl_sync(FULL, xlo, l0);
         }
       }
+      if (NW > 1) {
+        // what the warp filling block b-1 writes: recompute its geometry from its rows
+        wlo = 0; whi = 0;
+        if (b > 0) {
+          const int yp = y - 32;  // always < H
+          int pxlo, pxhi, pn;
+          unsigned prl;
+          row_span(coff[yp], clen[yp], ref_len, pxlo, pxhi, prl);
+          const BlockGeom pg = block_geom(pxlo, pxhi, prl, lane, pn);
+          wlo = pg.base - 31;
+          whi = wlo + (pg.ngroups << 4);
+        }
+      }
+      const int prev_tw = (tw + NW - 1) % NW;
+      // team mode: block until the producer of block b-1 has flushed strip columns < x_end
+      auto wait_for = [&](int x_end) {
+        if (NW > 1 && b > 0) {
+          const int need = x_end < whi ? x_end : whi;
+          if (need > wlo) {
+            const unsigned long long key = prog_key(b - 1, need);
+            if (is0) {
+              while (s_prog[prev_tw] < key) __nanosleep(64);
+            }
+            __syncwarp();
+            __threadfence_block();
+          }
+        }
+      };
+      auto strip_rec = [&](int x) -> uint4 { return (x >= wlo && x < whi) ? ld_strip(strip + x) : EMPTY; };
 
       unsigned long long word_off = 0;
       if (is0) {
@@ -153,17 +234,6 @@ convex_fill_kernel(const FillParams p) {
       }
       uint32_t* __restrict__ dwp = p.dir + word_off + lane;
 
-      // The strip must hold a record of the row above for every column lane 0 will visit,
-      // [base-1, base + nchunks*64): what the previous block did not write is EMPTY.
-      {
-        const int need_lo = base - 1, need_hi = base + nchunks * CHUNK;
-        const int l_hi = wlo < need_hi ? wlo : need_hi;
-        for (int x = need_lo + lane; x < l_hi; x += 32) st_strip(strip + x, EMPTY);
-        const int r_lo = whi > need_lo ? whi : need_lo;
-        for (int x = r_lo + lane; x < need_hi; x += 32) st_strip(strip + x, EMPTY);
-      }
-      __syncwarp();
-
       int rel = base - lane - xlo;  // x - xlo at step 0; inside the corridor iff (unsigned)rel < rlen
       const int t0rel = (int)rlen > 12 ? (int)rlen - 12 : 0;  // tail start max(x0, xMax-12) - xlo (:1179)
 
@@ -177,26 +247,31 @@ convex_fill_kernel(const FillParams p) {
       float lRunF = 0.0f;      // scalar kernel: D-run length of (x-1, y), 0 unless it is a deletion
       int lRun = 0;            // RAW kernel: raw indelRun / direction of (x-1, y)
       uint32_t lDir = DIR_STOP;
-      if (is0) dS = __uint_as_float(ld_strip(strip + base - 1).x);
       float kS = bestS;
       int kStep = -1;
 
-      // stage chunk 0: strip records + reference bytes for columns [base, base+64)
-      uint4 pa, pb;
-      uint32_t ra, rb;
+      // stage chunk 0 (+ the diagonal neighbour of lane 0's first cell)
+      wait_for(base + CHUNK);
+      if (is0) dS = __uint_as_float(strip_rec(base - 1).x);
+      uint4 pa = EMPTY, pb = EMPTY;
+      uint32_t ra = 0, rb = 0;
       {
         const int x0 = base + lane;
-        pa = ld_strip(strip + x0);
-        pb = ld_strip(strip + x0 + 32);
-        ra = __ldg(ref + x0);
-        rb = __ldg(ref + x0 + 32);
+        if (lane < CHUNK) {
+          pa = strip_rec(x0);
+          ra = __ldg(ref + x0);
+        }
+        if (CHUNK > 32) {
+          pb = strip_rec(x0 + 32);
+          rb = __ldg(ref + x0 + 32);
+        }
       }
 
       for (int c = 0; c < nchunks; ++c) {
         pa.w = ra;  // the reference byte of the column rides in the record
         pb.w = rb;
-        in_s[lane] = pa;
-        in_s[lane + 32] = pb;
+        if (lane < CHUNK) in_s[lane] = pa;
+        if (CHUNK > 32) in_s[lane + 32] = pb;
         __syncwarp();
         if (is31) {  // lane 31's shuffle sources carry the strip record lane 0 needs next
           const uint4 t = in_s[0];
@@ -207,15 +282,20 @@ convex_fill_kernel(const FillParams p) {
         }
         if (c + 1 < nchunks) {  // fetch the next chunk while this one is computed
           const int x0 = base + (c + 1) * CHUNK + lane;
-          pa = ld_strip(strip + x0);
-          pb = ld_strip(strip + x0 + 32);
-          ra = __ldg(ref + x0);
-          rb = __ldg(ref + x0 + 32);
+          wait_for(base + (c + 2) * CHUNK);
+          if (lane < CHUNK) {
+            pa = strip_rec(x0);
+            ra = __ldg(ref + x0);
+          }
+          if (CHUNK > 32) {
+            pb = strip_rec(x0 + 32);
+            rb = __ldg(ref + x0 + 32);
+          }
         }
-        const int g_end = min(ngroups, (c + 1) << 2);
-        for (int g = c << 2; g < g_end; ++g) {
-          const uint4* in_g = in_s + ((g & 3) << 4);
-          uint4* out_g = out_s + ((g & 3) << 4);
+        const int g_end = min(ngroups, (c + 1) * GPC);
+        for (int g = c * GPC; g < g_end; ++g) {
+          const uint4* in_g = in_s + ((g % GPC) << 4);
+          uint4* out_g = out_s + ((g % GPC) << 4);
           uint32_t dw = 0;
 #pragma unroll 1
           for (int k4 = 0; k4 < 16; k4 += 4) {
@@ -310,12 +390,17 @@ convex_fill_kernel(const FillParams p) {
           dwp[(size_t)g * 32] = dw;
         }
         __syncwarp();
-        // flush lane 31's records of this chunk: columns [base - 31 + 64c, ...)
+        // flush lane 31's records of this chunk: columns [base - 31 + CHUNK*c, ...)
         {
-          const int done = (g_end - (c << 2)) << 4;  // steps executed in this chunk
+          const int done = (g_end - c * GPC) << 4;  // steps executed in this chunk
           const int xo = base - 31 + c * CHUNK;
           if (lane < done) st_strip(strip + xo + lane, out_s[lane]);
-          if (lane + 32 < done) st_strip(strip + xo + lane + 32, out_s[lane + 32]);
+          if (CHUNK > 32 && lane + 32 < done) st_strip(strip + xo + lane + 32, out_s[lane + 32]);
+          if (NW > 1) {
+            __threadfence_block();
+            __syncwarp();
+            if (is0) s_prog[tw] = prog_key(b, xo + done);
+          }
         }
         __syncwarp();
       }
@@ -325,9 +410,16 @@ convex_fill_kernel(const FillParams p) {
         bestY = y;
         bestX = base + kStep - lane;
       }
-      wlo = base - 31;
-      whi = base - 31 + (ngroups << 4);
+      if (NW == 1) {
+        wlo = base - 31;
+        whi = base - 31 + (ngroups << 4);
+      } else if (is0) {
+        s_prog[tw] = prog_key(b, (1 << 30));  // block complete
+      }
       __syncwarp();
+    }
+    if (NW > 1) {
+      if (is0) s_prog[tw] = ~0ull;  // also after an arena overflow: never leave a consumer waiting
     }
 
     // first maximum in row-major order across lanes: larger score, then smaller y, then smaller x
@@ -345,12 +437,31 @@ convex_fill_kernel(const FillParams p) {
       }
       cells += c2;
     }
+    if (NW > 1) {
+      if (is0) {
+        TeamBest tb;
+        tb.S = bestS; tb.x = bestX; tb.y = bestY; tb.firstX = firstX; tb.firstY = firstY;
+        tb.status = status; tb.cells = cells;
+        s_best[tw] = tb;
+      }
+      __syncthreads();
+      if (wib == 0) {
+        for (int t = 1; t < NW; ++t) {
+          const TeamBest tb = s_best[t];
+          const bool take = (tb.S > bestS) || (tb.S == bestS && (tb.y < bestY || (tb.y == bestY && tb.x < bestX)));
+          if (take) { bestS = tb.S; bestY = tb.y; bestX = tb.x; }
+          cells += tb.cells;
+          if (tb.status != ST_OK) status = tb.status;
+          if (tb.firstY >= 0 && (firstY < 0 || tb.firstY < firstY)) { firstY = tb.firstY; firstX = tb.firstX; }
+        }
+      }
+    }
     if (bestS == 0.0f) {  // no positive score anywhere: the first visited cell stands (or nothing was visited)
       bestS = firstY >= 0 ? 0.0f : -1.0f;
       bestX = firstY >= 0 ? firstX : 0;
       bestY = firstY >= 0 ? firstY : 0;
     }
-    if (is0) {
+    if (is0 && (NW == 1 || wib == 0)) {
       FillOut o;
       o.best_score = bestS;
       o.best_x = bestX;
@@ -364,20 +475,28 @@ convex_fill_kernel(const FillParams p) {
 
 }  // namespace
 
-cudaError_t launch_convex_fill(const FillParams& p, bool raw, int grid, cudaStream_t stream) {
-  if (raw)
-    convex_fill_kernel<true><<<grid, FILL_WARPS_PER_CTA * 32, 0, stream>>>(p);
-  else
-    convex_fill_kernel<false><<<grid, FILL_WARPS_PER_CTA * 32, 0, stream>>>(p);
+cudaError_t launch_convex_fill(const FillParams& p, bool raw, bool team, int grid, cudaStream_t stream) {
+  const int threads = FILL_WARPS_PER_CTA * 32;
+  if (raw) {
+    if (team) convex_fill_kernel<true, FILL_WARPS_PER_CTA><<<grid, threads, 0, stream>>>(p);
+    else convex_fill_kernel<true, 1><<<grid, threads, 0, stream>>>(p);
+  } else {
+    if (team) convex_fill_kernel<false, FILL_WARPS_PER_CTA><<<grid, threads, 0, stream>>>(p);
+    else convex_fill_kernel<false, 1><<<grid, threads, 0, stream>>>(p);
+  }
   return cudaGetLastError();
 }
 
-int fill_max_ctas_per_sm(bool raw) {
+int fill_max_ctas_per_sm(bool raw, bool team) {
   int n = 0;
-  if (raw)
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, convex_fill_kernel<true>, FILL_WARPS_PER_CTA * 32, 0);
-  else
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, convex_fill_kernel<false>, FILL_WARPS_PER_CTA * 32, 0);
+  const int threads = FILL_WARPS_PER_CTA * 32;
+  if (raw) {
+    if (team) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, convex_fill_kernel<true, FILL_WARPS_PER_CTA>, threads, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, convex_fill_kernel<true, 1>, threads, 0);
+  } else {
+    if (team) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, convex_fill_kernel<false, FILL_WARPS_PER_CTA>, threads, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, convex_fill_kernel<false, 1>, threads, 0);
+  }
   return n;
 }
 

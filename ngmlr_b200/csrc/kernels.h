@@ -9,8 +9,9 @@ namespace nb {
 constexpr int FILL_WARPS_PER_CTA = 4;
 constexpr int FILL_CTAS_PER_SM = 4;
 
-cudaError_t launch_convex_fill(const FillParams& p, bool raw, int grid, cudaStream_t stream);
-int fill_max_ctas_per_sm(bool raw);
+// team = all FILL_WARPS_PER_CTA warps of a CTA pipeline one problem; otherwise one warp per problem
+cudaError_t launch_convex_fill(const FillParams& p, bool raw, bool team, int grid, cudaStream_t stream);
+int fill_max_ctas_per_sm(bool raw, bool team);
 
 cudaError_t launch_convex_traceback(const TraceParams& p, cudaStream_t stream);
 cudaError_t launch_convex_compact(const TraceParams& p, cudaStream_t stream);

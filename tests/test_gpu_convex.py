@@ -132,3 +132,17 @@ def test_properties_at_scale(aligner):
 
 def test_empty_batch(aligner):
     assert aligner.BatchAlign(PackedBatch([], [], [], [])) == []
+
+
+@pytest.mark.parametrize("team", [0, 1])
+def test_both_fill_schedules_are_bit_exact(aligner, oracle, team):
+    """One warp per problem and the 4-warp team pipeline must give identical matrices, including
+    on ragged / non-monotone / tiny corridors where team members wait on each other's strip."""
+    aligner.force_team(team)
+    try:
+        _compare_batch(aligner, oracle, cases.edge_problems(), check_dirs=True)
+        _compare_batch(aligner, oracle, cases.random_problems(40, 606, max_len=1500), check_dirs=True)
+        probs = synth.pacbio_problems(4, genome_len=300_000, seed=12, median=5000)
+        _compare_batch(aligner, oracle, probs)
+    finally:
+        aligner.force_team(-1)
