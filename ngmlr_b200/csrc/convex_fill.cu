@@ -40,6 +40,8 @@
 #include <cuda_runtime.h>
 #include <limits.h>
 
+#include <type_traits>
+
 #include "device_types.h"
 #include "kernels.h"
 
@@ -293,7 +295,10 @@ convex_fill_kernel(const FillParams p) {
           }
         }
         const int g_end = min(ngroups, (c + 1) * GPC);
-        for (int g = c * GPC; g < g_end; ++g) {
+        // A 16-step group in which every lane stays inside its corridor row needs no masking at all
+        // (the common case away from the block's leading and trailing wavefront).
+        auto do_group = [&](auto all_active_tag, int g) {
+          constexpr bool ALL_ACTIVE = decltype(all_active_tag)::value;
           const uint4* in_g = in_s + ((g % GPC) << 4);
           uint4* out_g = out_s + ((g % GPC) << 4);
           uint32_t dw = 0;
@@ -309,15 +314,16 @@ convex_fill_kernel(const FillParams p) {
               v.w = __shfl_sync(FULL, oC, src_lane);
               const float nS = __uint_as_float(v.x), nU = __uint_as_float(v.y);
               const uint32_t r = v.w;
-              const bool act = (unsigned)rel < rlen;
+              const bool act = ALL_ACTIVE ? true : ((unsigned)rel < rlen);
               const float sub = (r == q) ? sc.mat : sc.mis;
               const float dg = __fadd_rn(dS, sub);
               dS = nS;
               // Outside the corridor the cell must degenerate to {0, 0, STOP}: a NaN maximum makes every
               // equality below false, and fmaxf(NaN, 0) = 0 gives the score.
-              const float m = act ? fmaxf(fmaxf(fmaxf(lL, 0.0f), dg), nU) : __int_as_float(0x7fffffff);
+              const float m0 = fmaxf(fmaxf(fmaxf(lL, 0.0f), dg), nU);
+              const float m = (ALL_ACTIVE || act) ? m0 : __int_as_float(0x7fffffff);
               const bool eL = (m == lL), eU = (m == nU), eG = (m == dg);
-              const float S = fmaxf(m, 0.0f);  // STOP implies m == 0
+              const float S = ALL_ACTIVE ? m : fmaxf(m, 0.0f);  // STOP implies m == 0
               uint32_t code;
               float U, L;
               if (RAW) {
@@ -384,10 +390,16 @@ convex_fill_kernel(const FillParams p) {
                 oP = t.z;
                 oC = t.w;
               }
-              ++rel;
+              if (!ALL_ACTIVE || RAW) ++rel;  // the RAW kernel needs the column for its tail rule
             }
           }
+          if (ALL_ACTIVE && !RAW) rel += 16;
           dwp[(size_t)g * 32] = dw;
+        };
+        for (int g = c * GPC; g < g_end; ++g) {
+          const bool all_active = __all_sync(FULL, rel >= 0 && rel + 15 < (int)rlen);
+          if (all_active) do_group(std::true_type{}, g);
+          else do_group(std::false_type{}, g);
         }
         __syncwarp();
         // flush lane 31's records of this chunk: columns [base - 31 + CHUNK*c, ...)
