@@ -145,6 +145,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cores = os.cpu_count() or 1
 
+    # host worker threads of the library (packing / CIGAR text): share the cores among ranks x contexts
+    os.environ.setdefault("NGMLR_B200_HOST_THREADS",
+                          str(max(4, min(32, cores // max(1, world * max(1, args.contexts))))))
+
     from ngmlr_b200 import synth
 
     # ------------------------------------------------------------------ reference arm (CPU)
@@ -317,7 +321,14 @@ def main():
         algo_bytes = cells * 0.25 + seq_b + rows * 8
         fill_s = float(np.mean(fill_ms)) * 1e-3
         achieved = algo_bytes / fill_s / 1e9
-        issue_bound_cells = 148 * 128 * float(clocks.get("sm_mhz") or 1965.0) * 1e6 / 93.0
+        issue_bound_cells = 148 * 4 * 32 * float(clocks.get("sm_mhz") or 1965.0) * 1e6 / (38.0 * 2.0)
+        traffic = None
+        try:  # DRAM bytes of one fill launch from the committed ncu capture (same reads/step only)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "fill_traffic.json")))
+            if tr.get("reads_per_step") == args.reads:
+                traffic = tr["dram_bytes_per_launch"]
+        except Exception:
+            pass
         line = {
             "metric": "aligned_gbp_per_s", "value": value, "unit": "Gbp/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
@@ -333,12 +344,14 @@ def main():
             "reads_per_s": args.reads * world * args.steps / (dev_ms * 1e-3),
             "gcells_per_s": tot_cells * args.steps / (dev_ms * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel": "convex_fill_kernel", "launch_ms": fill_s * 1e3,
                          "algorithmic_bytes_per_launch": algo_bytes,
                          "gcells_per_s_kernel": cells / fill_s / 1e9,
-                         "note": "issue-bound kernel (~93 SASS instr/cell): cells/s vs issue bound "
-                                 f"{cells / fill_s / issue_bound_cells:.2f}"},
+                         "alu_pipe_bound_gcells_per_s": issue_bound_cells / 1e9,
+                         "frac_of_alu_pipe_bound": cells / fill_s / issue_bound_cells,
+                         "note": "ALU-pipe-bound kernel (~38 ALU-pipe SASS instr per 32-cell step, 2 cycles each "
+                                 "per SMSP, DESIGN.md 4.1); HBM frac is structurally ~0.015"},
             "kernel_ms_per_step": {"fill": float(np.mean(fill_ms)), "traceback": float(np.mean(tb_ms)),
                                    "compact": float(np.mean(cp_ms))},
             "e2e": {"value": e2e_val, "unit": "Gbp/s", "h2d_bytes_per_step": st_e2e["h2d_bytes"],
