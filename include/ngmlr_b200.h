@@ -157,6 +157,26 @@ int ngmlr_b200_cs_search_batch(ngmlr_b200_ctx* ctx, int n, const char* const* se
                                int64_t* cand_start, const float** scores, const uint64_t** locs,
                                const uint8_t** reverse, float* max_hits);
 
+/* The 4-bit encoded, spacer-padded concatenated genome exactly as _SequenceProvider holds it
+ * (`binRef`, src/SequenceProvider.cpp:76-105, 292-400): 2 bases per byte, A0 T1 G2 C3 N4;
+ * concat_len = GetConcatRefLen(). Needed by ngmlr_b200_cs_score_batch. Copied to the device. */
+int ngmlr_b200_cs_set_reference(ngmlr_b200_ctx* ctx, const uint8_t* bin_ref, uint64_t n_bytes,
+                                uint64_t concat_len);
+
+/* Candidate search + candidate scoring in one call: what CS::RunRead followed by
+ * ScoreBuffer::DoRun computes for (sub-)reads (src/ScoreBuffer.cpp:87-168): every candidate of
+ * ngmlr_b200_cs_search_batch is scored with the StrippedSW kernel against the window
+ * DecodeRefSequence(buf, 0, loc - (corridor >> 1), ((read_part_length + 10 + corridor) | 1) + 1)
+ * decoded on the device (src/SequenceProvider.cpp:567-625), using the read or, for reverse
+ * candidates, MappedRead::computeReverseSeq (src/MappedRead.cpp:35-73). *sw_scores[j] is the float
+ * ScoreBuffer writes to Scores[j].Score.f. corridor = Config.getReadPartCorridor() (40),
+ * read_part_length = Config.getReadPartLength() (256). Other outputs as in cs_search_batch. */
+int ngmlr_b200_cs_score_batch(ngmlr_b200_ctx* ctx, int n, const char* const* seqs,
+                              const int32_t* lens, float sensitivity, float min_kmer_hits,
+                              int corridor, int read_part_length, int64_t* cand_start,
+                              const float** cs_scores, const uint64_t** locs, const uint8_t** reverse,
+                              const float** sw_scores, float* max_hits);
+
 #ifdef __cplusplus
 }
 #endif

@@ -175,6 +175,29 @@ class B200Aligner:
             out.append([(sc[j], int(lo[j]), int(rv[j])) for j in range(start[i], start[i + 1])])
         return out, mx[:n]
 
+    def set_reference(self, ref):
+        """ref: ngmlr_b200.refindex.EncodedReference (the reference's 4-bit `binRef`)."""
+        enc = np.ascontiguousarray(ref.enc, dtype=np.uint8)
+        self._check(self.lib.ngmlr_b200_cs_set_reference(self.h, enc.ctypes.data_as(C.c_void_p), enc.size,
+                                                         ref.concat_len))
+
+    def cs_score(self, seqs, sensitivity=0.8, min_kmer_hits=0.0, corridor=40, read_part_length=256):
+        """CS::RunRead + ScoreBuffer::DoRun for sub-reads: per read [(cs_score, location, reverse,
+        sw_score)] in the reference's emission order."""
+        n = len(seqs)
+        arr = (C.c_char_p * n)(*[bytes(s) for s in seqs])
+        lens = np.array([len(s) for s in seqs], dtype=np.int32)
+        start = np.zeros(n + 1, dtype=np.int64)
+        mx = np.zeros(max(n, 1), dtype=np.float32)
+        sc, lo, rv, sw = (C.POINTER(C.c_float)(), C.POINTER(C.c_uint64)(), C.POINTER(C.c_uint8)(),
+                          C.POINTER(C.c_float)())
+        self._check(self.lib.ngmlr_b200_cs_score_batch(
+            self.h, n, arr, lens.ctypes.data_as(C.POINTER(C.c_int32)), sensitivity, min_kmer_hits, corridor,
+            read_part_length, start.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(sc), C.byref(lo),
+            C.byref(rv), C.byref(sw), mx.ctypes.data_as(C.POINTER(C.c_float))))
+        return [[(sc[j], int(lo[j]), int(rv[j]), sw[j]) for j in range(start[i], start[i + 1])]
+                for i in range(n)], mx[:n]
+
     # ---- phased interface (bench: inputs resident in HBM) ---------------------------------
     def upload(self, batch):
         self._n = batch.n

@@ -824,7 +824,17 @@ struct CsState {
   std::vector<float> scores;
   std::vector<uint64_t> locs;
   std::vector<uint8_t> reverse;
+  std::vector<float> sw_scores;
   float last_ms = 0;
+  // candidate scoring
+  DevBuf<uint8_t> d_enc, d_rev;
+  uint64_t enc_bytes = 0, concat_len = 0;
+  DevBuf<unsigned long long> d_winpos;
+  DevBuf<uint64_t> d_qoff;
+  DevBuf<int32_t> d_qlen;
+  DevBuf<float> d_sw;
+  DevBuf<int32_t> d_swscratch;
+  std::vector<uint64_t> last_seq_off;  // arena offsets of the reads of the last search
 };
 
 std::vector<std::pair<ngmlr_b200_ctx*, CsState*>> g_cs_states;
@@ -849,7 +859,9 @@ void nb_cs_release(ngmlr_b200_ctx* ctx) {
     cs->d_packed.release(); cs->d_tab.release(); cs->d_pos.release(); cs->d_order.release();
     cs->d_used.release(); cs->d_seq.release(); cs->d_tables.release(); cs->d_off.release();
     cs->d_len.release(); cs->d_count.release(); cs->d_cap.release(); cs->d_hits.release();
-    cs->d_max.release(); cs->d_out.release();
+    cs->d_max.release(); cs->d_out.release(); cs->d_enc.release(); cs->d_rev.release();
+    cs->d_winpos.release(); cs->d_qoff.release(); cs->d_qlen.release(); cs->d_sw.release();
+    cs->d_swscratch.release();
     delete cs;
     g_cs_states.erase(g_cs_states.begin() + i);
     return;
@@ -906,6 +918,7 @@ int ngmlr_b200_cs_search_batch(ngmlr_b200_ctx* ctx, int n, const char* const* se
     seq_off[i] = bytes;
     bytes += align_up((size_t)std::max(lens[i], 0) + 1, 16);
   }
+  cs->last_seq_off = seq_off;
   std::vector<uint8_t> hseq(bytes + 16, 0);
   parallel_for(n, 256, [&](int i) { memcpy(hseq.data() + seq_off[i], seqs[i], (size_t)std::max(lens[i], 0)); });
   CU(cs->d_seq.reserve(bytes + 16));
@@ -1008,6 +1021,93 @@ int ngmlr_b200_cs_search_batch(ngmlr_b200_ctx* ctx, int n, const char* const* se
   *locs = cs->locs.data();
   *reverse = cs->reverse.data();
   return n;
+}
+
+}  // extern "C"
+
+extern "C" {
+
+int ngmlr_b200_cs_set_reference(ngmlr_b200_ctx* ctx, const uint8_t* bin_ref, uint64_t n_bytes,
+                                uint64_t concat_len) {
+  if (!ctx) return -1;
+  if (concat_len > 2 * n_bytes) return ctx->fail("cs_set_reference: concat_len exceeds 2 * n_bytes");
+  CU(cudaSetDevice(ctx->device));
+  CsState* cs = cs_state(ctx, true);
+  CU(cs->d_enc.reserve(n_bytes + 64));
+  CU(cudaMemsetAsync(cs->d_enc.p, 0x44, n_bytes + 64, ctx->stream));  // 'N','N' past the end
+  CU(cudaMemcpyAsync(cs->d_enc.p, bin_ref, n_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  cs->enc_bytes = n_bytes;
+  cs->concat_len = concat_len;
+  return 0;
+}
+
+int ngmlr_b200_cs_score_batch(ngmlr_b200_ctx* ctx, int n, const char* const* seqs,
+                              const int32_t* lens, float sensitivity, float min_kmer_hits,
+                              int corridor, int read_part_length, int64_t* cand_start,
+                              const float** cs_scores, const uint64_t** locs, const uint8_t** reverse,
+                              const float** sw_scores, float* max_hits) {
+  if (!ctx) return -1;
+  CsState* cs = cs_state(ctx, false);
+  if (!cs || !cs->enc_bytes) return ctx->fail("cs_score_batch: call cs_set_reference first");
+  int rc = ngmlr_b200_cs_search_batch(ctx, n, seqs, lens, sensitivity, min_kmer_hits, cand_start,
+                                      cs_scores, locs, reverse, max_hits);
+  if (rc < 0) return rc;
+  cs->sw_scores.clear();
+  *sw_scores = cs->sw_scores.data();
+  if (n <= 0) return rc;
+  const size_t m = (size_t)cand_start[n];
+  cs->sw_scores.assign(m, -1.0f);
+  *sw_scores = cs->sw_scores.data();
+  if (!m) return rc;
+  cudaStream_t st = ctx->stream;
+  // per candidate: window position, strand, and the arena location of its read (already on device)
+  std::vector<unsigned long long> win(m);
+  std::vector<uint64_t> qoff(m);
+  std::vector<int32_t> qlen(m);
+  int max_q = 0;
+  for (int i = 0; i < n; ++i) {
+    for (int64_t j = cand_start[i]; j < cand_start[i + 1]; ++j) {
+      win[j] = (unsigned long long)cs->locs[j] - (unsigned long long)(corridor >> 1);  // uloc arithmetic (:110)
+      qoff[j] = cs->last_seq_off[i];
+      qlen[j] = lens[i] + 1;  // strlen + 1
+    }
+    max_q = std::max(max_q, lens[i] + 1);
+  }
+  const int win_len = ((read_part_length + 10 + corridor) | 1) + 1;  // refMaxLen, src/ScoreBuffer.h:71-72
+  CU(cs->d_winpos.reserve(m));
+  CU(cs->d_qoff.reserve(m));
+  CU(cs->d_qlen.reserve(m));
+  CU(cs->d_rev.reserve(m));
+  CU(cs->d_sw.reserve(m));
+  CU(cudaMemcpyAsync(cs->d_winpos.p, win.data(), m * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(cs->d_qoff.p, qoff.data(), m * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(cs->d_qlen.p, qlen.data(), m * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(cs->d_rev.p, cs->reverse.data(), m, cudaMemcpyHostToDevice, st));
+  const int warps_per_cta = 4;
+  const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->num_sms * 8, (m + warps_per_cta - 1) / warps_per_cta));
+  const size_t stride = max_q > 288 ? align_up((size_t)win_len + 4, 4) : 4;
+  CU(cs->d_swscratch.reserve((size_t)grid * warps_per_cta * stride * 2));
+  SwParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.seq = cs->d_seq.p;
+  sp.ref_off = cs->d_qoff.p;  // unused in gather mode
+  sp.qry_off = cs->d_qoff.p;
+  sp.ref_len = cs->d_qlen.p;  // unused in gather mode
+  sp.qry_len = cs->d_qlen.p;
+  sp.out = cs->d_sw.p;
+  sp.n = (int)m;
+  sp.scratch = cs->d_swscratch.p;
+  sp.scratch_stride = stride;
+  sp.enc = cs->d_enc.p;
+  sp.concat_len = cs->concat_len;
+  sp.win_pos = cs->d_winpos.p;
+  sp.rev = cs->d_rev.p;
+  sp.win_len = win_len;
+  CU(launch_sw_score_gather(sp, grid, st));
+  CU(cudaMemcpyAsync(cs->sw_scores.data(), cs->d_sw.p, m * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return rc;
 }
 
 }  // extern "C"

@@ -27,8 +27,17 @@ struct SwParams {
   int n;
   int32_t* scratch;            // per-warp H/E rows for queries longer than the register tile
   unsigned long long scratch_stride;
+  // gather mode (candidate scoring straight from the 4-bit genome, ScoreBuffer::DoRun semantics):
+  // pair i scores sub-read qry (reverse-complemented with MappedRead::computeReverseSeq's cpl()
+  // when rev[i]) against DecodeRefSequence(buf, 0, win_pos[i], win_len)
+  const uint8_t* enc;          // binRef, 2 bases per byte (A0 T1 G2 C3 N4)
+  unsigned long long concat_len;
+  const unsigned long long* win_pos;
+  const uint8_t* rev;
+  int win_len;                 // refMaxLen (308)
 };
 cudaError_t launch_sw_score(const SwParams& p, int grid, cudaStream_t stream);
+cudaError_t launch_sw_score_gather(const SwParams& p, int grid, cudaStream_t stream);
 
 cudaError_t launch_cs_search(const CsParams& p, bool count_only, cudaStream_t stream);
 cudaError_t launch_unpack_index(const uint8_t* packed, uint32_t n, uint32_t* tab, uint8_t* used,

@@ -36,6 +36,44 @@ __device__ __forceinline__ int nt_code(uint32_t c) {
   return c == 'A' ? 0 : (c == 'C' ? 1 : (c == 'G' ? 2 : (c == 'T' ? 3 : 4)));
 }
 
+// DecodeRefSequence(sequence, 0, position, bufferLength) as a random-access function
+// (src/SequenceProvider.cpp:567-625): character i of the window, as an nt_table code.
+struct GenomeWindow {
+  const uint8_t* enc;
+  unsigned long long pos, concat_len;
+  int odd;        // position & 1: one extra leading base
+  int pairs2;     // 2 * ceil(len / 2) characters decoded pairwise
+  int x_at;       // index (after the odd base) that is overwritten by 'x' when len is odd, else -1
+  int str_len;    // strlen of the decoded window
+  bool invalid;   // position >= concat_len: the caller fills the buffer with 'N'
+  __device__ void init(const uint8_t* e, unsigned long long p, unsigned long long cl, int buffer_len) {
+    enc = e; pos = p; concat_len = cl;
+    invalid = p >= cl;
+    unsigned long long len = (unsigned long long)(buffer_len - 2), end = 0;
+    if (!invalid && p + len > cl) { end = p + len - cl; len -= end; }
+    odd = (int)(p & 1ull);
+    pairs2 = (int)(((len + 1) / 2) * 2);
+    x_at = (len & 1ull) ? pairs2 - 1 : -1;
+    str_len = invalid ? buffer_len : odd + pairs2 + (int)end;
+  }
+  __device__ __forceinline__ int code(int i) const {
+    if (invalid) return 4;                   // memset(buf, 'N', refMaxLen), src/ScoreBuffer.cpp:114
+    if (i >= str_len) return 4;              // the terminating NUL (scored as N)
+    const int k = i - odd;
+    if (k >= pairs2 || k == x_at) return 4;  // 'x' padding
+    const unsigned long long b = pos + (unsigned long long)i;  // base index in the concatenated genome
+    const uint32_t byte = enc[b >> 1];
+    const uint32_t c4 = (b & 1ull) ? (byte & 0xFu) : (byte >> 4);
+    // enc4 A0 T1 G2 C3 N4 -> nt_table A0 C1 G2 T3 N4
+    return c4 == 0 ? 0 : (c4 == 1 ? 3 : (c4 == 2 ? 2 : (c4 == 3 ? 1 : 4)));
+  }
+};
+
+__device__ __forceinline__ uint32_t cpl(uint32_t c) {  // src/MappedRead.cpp:35-46
+  return c == 'A' ? 'T' : (c == 'T' ? 'A' : (c == 'C' ? 'G' : (c == 'G' ? 'C' : c)));
+}
+
+template <bool GATHER>
 __global__ void __launch_bounds__(SW_WARPS_PER_CTA * 32) sw_score_kernel(const SwParams p) {
   const int lane = threadIdx.x & 31;
   const int warp_global = blockIdx.x * SW_WARPS_PER_CTA + (threadIdx.x >> 5);
@@ -43,12 +81,19 @@ __global__ void __launch_bounds__(SW_WARPS_PER_CTA * 32) sw_score_kernel(const S
   int2* strip = reinterpret_cast<int2*>(p.scratch) + (size_t)warp_global * p.scratch_stride;
 
   for (int pair = warp_global; pair < p.n; pair += nwarps) {
-    const int qlen = p.qry_len[pair], rlen = p.ref_len[pair];
+    GenomeWindow gw;
+    int rlen_g = 0;
+    if (GATHER) {
+      gw.init(p.enc, p.win_pos[pair], p.concat_len, p.win_len);
+      rlen_g = gw.str_len + 1;  // strlen + 1: the NUL is scored
+    }
+    const bool q_rev = GATHER && p.rev[pair];
+    const int qlen = p.qry_len[pair], rlen = GATHER ? rlen_g : p.ref_len[pair];
     if (qlen >= 100000 || rlen >= 100000) {  // maxSeqLen, src/StrippedSW.h:88
       if (lane == 0) p.out[pair] = -1.0f;
       continue;
     }
-    const uint8_t* __restrict__ ref = p.seq + p.ref_off[pair];
+    const uint8_t* __restrict__ ref = GATHER ? p.seq : p.seq + p.ref_off[pair];
     const uint8_t* __restrict__ qry = p.seq + p.qry_off[pair];
     int best = 0;
     const int rows_per_pass = 32 * SW_ROWS;
@@ -61,7 +106,12 @@ __global__ void __launch_bounds__(SW_WARPS_PER_CTA * 32) sw_score_kernel(const S
       for (int r = 0; r < SW_ROWS; ++r) {
         const int row = row0 + r;
         // the NUL at qlen-1 is part of the query and maps to 4; rows >= qlen do not exist (-1)
-        qc[r] = row < qlen ? nt_code(qry[row]) : -1;
+        if (q_rev) {  // RevSeq[j] = cpl(Seq[len - 1 - j]), then the NUL
+          const int L = qlen - 1;
+          qc[r] = row < L ? nt_code(cpl(qry[L - 1 - row])) : (row < qlen ? 4 : -1);
+        } else {
+          qc[r] = row < qlen ? nt_code(qry[row]) : -1;
+        }
         H[r] = 0;
         E[r] = 0;
       }
@@ -82,7 +132,7 @@ __global__ void __launch_bounds__(SW_WARPS_PER_CTA * 32) sw_score_kernel(const S
           }
         }
         if (in) {
-          const int rc = nt_code(ref[c]);
+          const int rc = GATHER ? gw.code(c) : nt_code(ref[c]);
           int diag = diagTop;
           diagTop = upH;
           int F = upF;
@@ -118,7 +168,13 @@ __global__ void __launch_bounds__(SW_WARPS_PER_CTA * 32) sw_score_kernel(const S
 
 cudaError_t launch_sw_score(const SwParams& p, int grid, cudaStream_t stream) {
   if (p.n <= 0) return cudaSuccess;
-  sw_score_kernel<<<grid, SW_WARPS_PER_CTA * 32, 0, stream>>>(p);
+  sw_score_kernel<false><<<grid, SW_WARPS_PER_CTA * 32, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sw_score_gather(const SwParams& p, int grid, cudaStream_t stream) {
+  if (p.n <= 0) return cudaSuccess;
+  sw_score_kernel<true><<<grid, SW_WARPS_PER_CTA * 32, 0, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -25,3 +25,43 @@ def test_cs_search_matches_oracle(aligner):
     for i in range(50):
         assert got2[i] == orc.search(subs[i], sensitivity=0.5)[0]
     orc.close()
+
+
+def _cpl(b):
+    t = {ord("A"): ord("T"), ord("T"): ord("A"), ord("C"): ord("G"), ord("G"): ord("C")}
+    return bytes(t.get(c, c) for c in b)
+
+
+def test_fused_search_and_candidate_scoring_matches_oracle(aligner, oracle):
+    """CS candidates + device-side DecodeRefSequence + StrippedSW score == oracle composition of
+    or_cs_search -> or_cs_decode(loc - 20, 308) -> or_ssw_score (what ScoreBuffer::DoRun computes)."""
+    from ngmlr_b200 import refindex
+    contigs = cs_cases.genome_contigs()
+    orc = CsOracle([c.tobytes() for c in contigs])
+    ref = refindex.encode_reference(contigs)
+    aligner.set_index(refindex.build_index(ref))
+    aligner.set_reference(ref)
+    subs = [s for s in cs_cases.subreads(300, 29, contigs)]
+    got, _ = aligner.cs_score(subs)
+    n_scored = 0
+    for i, s in enumerate(subs):
+        want, _ = orc.search(s)
+        assert [g[:3] for g in got[i]] == want
+        for (cs_sc, loc, rev, sw) in got[i]:
+            pos = (loc - 20) % (1 << 64)
+            window = orc.decode(pos, 308)
+            if window is None:
+                window = b"N" * 308
+            q = _cpl(s)[::-1] if rev else s
+            assert sw == oracle.ssw_score(window, q), (i, loc, rev)
+            n_scored += 1
+    assert n_scored > 250
+    # windows at the very end of the genome ('x' padding) and odd/even positions
+    tail = contigs[4].tobytes()[-13 - 40:]
+    got, _ = aligner.cs_score([tail, contigs[0][1001:1257].tobytes(), contigs[0][1002:1258].tobytes()])
+    for i, s in enumerate([tail, contigs[0][1001:1257].tobytes(), contigs[0][1002:1258].tobytes()]):
+        for (cs_sc, loc, rev, sw) in got[i]:
+            window = orc.decode((loc - 20) % (1 << 64), 308) or b"N" * 308
+            q = _cpl(s)[::-1] if rev else s
+            assert sw == oracle.ssw_score(window, q)
+    orc.close()
