@@ -117,6 +117,37 @@ __global__ void __launch_bounds__(SW_WARPS_PER_CTA * 32) sw_score_kernel(const S
       }
       int outH = 0, outF = 0, diagTop = 0;
       const int nsteps = rlen + 31;
+      // A gap costs 255 per base, so a gapped path beats its best ungapped piece only if it gains
+      // more than 255 before AND after the gap: impossible with fewer than 512 query characters.
+      // Then E and F never influence the maximum and the recurrence is H = max(0, diag + s)
+      // (the hot case: 256-bp sub-reads, one pass of 288 rows). Longer queries take the full affine
+      // recurrence below.
+      if (qlen <= rows_per_pass) {  // single pass, and < 512 characters
+        for (int s = 0; s < nsteps; ++s) {
+          const int c = s - lane;
+          int upH = __shfl_up_sync(FULL, outH, 1);
+          if (lane == 0) upH = 0;
+          if (c >= 0 && c < rlen) {
+            const int rc = GATHER ? gw.code(c) : nt_code(ref[c]);
+#pragma unroll
+            for (int r = SW_ROWS - 1; r > 0; --r) {
+              const int sub = ((rc | qc[r]) & 4) ? 0 : (rc == qc[r] ? 1 : -1);
+              const int h = qc[r] < 0 ? 0 : max(H[r - 1] + sub, 0);
+              H[r] = h;
+              best = max(best, h);
+            }
+            {
+              const int sub = ((rc | qc[0]) & 4) ? 0 : (rc == qc[0] ? 1 : -1);
+              const int h = qc[0] < 0 ? 0 : max(diagTop + sub, 0);
+              H[0] = h;
+              best = max(best, h);
+            }
+            diagTop = upH;
+            outH = H[SW_ROWS - 1];
+          }
+        }
+        continue;
+      }
       for (int s = 0; s < nsteps; ++s) {
         const int c = s - lane;
         int upH = __shfl_up_sync(FULL, outH, 1);
