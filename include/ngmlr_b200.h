@@ -177,6 +177,19 @@ int ngmlr_b200_cs_score_batch(ngmlr_b200_ctx* ctx, int n, const char* const* seq
                               const float** cs_scores, const uint64_t** locs, const uint8_t** reverse,
                               const float** sw_scores, float* max_hits);
 
+/* The same stage-0/2 work in phases, so that benchmarks can time it with the reads resident in HBM:
+ *   cs_upload : (sub-)reads -> device (no kernels)
+ *   cs_run    : count -> size (device prefix sums) -> vote -> compact -> decode + score; results stay
+ *               on the device; *n_candidates and the CUDA-event kernel time are returned. Needs
+ *               cs_set_index and cs_set_reference. May be called repeatedly on one upload.
+ *   cs_fetch  : D2H of the candidate arrays (same meaning as ngmlr_b200_cs_score_batch). */
+int ngmlr_b200_cs_upload(ngmlr_b200_ctx* ctx, int n, const char* const* seqs, const int32_t* lens);
+int ngmlr_b200_cs_run(ngmlr_b200_ctx* ctx, float sensitivity, float min_kmer_hits, int corridor,
+                      int read_part_length, int64_t* n_candidates, float* kernel_ms);
+int ngmlr_b200_cs_fetch(ngmlr_b200_ctx* ctx, int64_t* cand_start, const float** cs_scores,
+                        const uint64_t** locs, const uint8_t** reverse, const float** sw_scores,
+                        float* max_hits);
+
 #ifdef __cplusplus
 }
 #endif

@@ -198,6 +198,33 @@ class B200Aligner:
         return [[(sc[j], int(lo[j]), int(rv[j]), sw[j]) for j in range(start[i], start[i + 1])]
                 for i in range(n)], mx[:n]
 
+    def cs_upload(self, seqs):
+        n = len(seqs)
+        self._cs_n = n
+        arr = (C.c_char_p * n)(*[bytes(s) for s in seqs])
+        lens = np.array([len(s) for s in seqs], dtype=np.int32)
+        self._check(self.lib.ngmlr_b200_cs_upload(self.h, n, arr, lens.ctypes.data_as(C.POINTER(C.c_int32))))
+
+    def cs_run(self, sensitivity=0.8, min_kmer_hits=0.0, corridor=40, read_part_length=256):
+        """Resident stage 0/2 pass; returns (number of candidates, kernel milliseconds)."""
+        m, ms = C.c_int64(0), C.c_float(0)
+        self._check(self.lib.ngmlr_b200_cs_run(self.h, sensitivity, min_kmer_hits, corridor, read_part_length,
+                                               C.byref(m), C.byref(ms)))
+        return m.value, ms.value
+
+    def cs_fetch(self):
+        n = self._cs_n
+        start = np.zeros(n + 1, dtype=np.int64)
+        mx = np.zeros(max(n, 1), dtype=np.float32)
+        sc, lo, rv, sw = (C.POINTER(C.c_float)(), C.POINTER(C.c_uint64)(), C.POINTER(C.c_uint8)(),
+                          C.POINTER(C.c_float)())
+        self._check(self.lib.ngmlr_b200_cs_fetch(self.h, start.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(sc),
+                                                 C.byref(lo), C.byref(rv), C.byref(sw),
+                                                 mx.ctypes.data_as(C.POINTER(C.c_float))))
+        m = int(start[-1])
+        as_np = lambda p, dt: (np.ctypeslib.as_array(p, shape=(m,)).copy() if m else np.zeros(0, dt))
+        return start, as_np(sc, np.float32), as_np(lo, np.uint64), as_np(rv, np.uint8), as_np(sw, np.float32), mx[:n]
+
     # ---- phased interface (bench: inputs resident in HBM) ---------------------------------
     def upload(self, batch):
         self._n = batch.n

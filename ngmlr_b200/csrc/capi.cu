@@ -835,6 +835,15 @@ struct CsState {
   DevBuf<float> d_sw;
   DevBuf<int32_t> d_swscratch;
   std::vector<uint64_t> last_seq_off;  // arena offsets of the reads of the last search
+  // resident pipeline
+  int rn = 0;                       // reads uploaded
+  size_t rbytes = 0;
+  DevBuf<unsigned long long> d_a, d_b, d_c, d_sa, d_sb, d_sc, d_cnt64, d_cstart, d_cloc;
+  DevBuf<uint8_t> d_scan_tmp;
+  DevBuf<float> d_cscore;
+  long long n_cand = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<int64_t> h_cstart;
 };
 
 std::vector<std::pair<ngmlr_b200_ctx*, CsState*>> g_cs_states;
@@ -861,7 +870,11 @@ void nb_cs_release(ngmlr_b200_ctx* ctx) {
     cs->d_len.release(); cs->d_count.release(); cs->d_cap.release(); cs->d_hits.release();
     cs->d_max.release(); cs->d_out.release(); cs->d_enc.release(); cs->d_rev.release();
     cs->d_winpos.release(); cs->d_qoff.release(); cs->d_qlen.release(); cs->d_sw.release();
-    cs->d_swscratch.release();
+    cs->d_swscratch.release(); cs->d_a.release(); cs->d_b.release(); cs->d_c.release();
+    cs->d_sa.release(); cs->d_sb.release(); cs->d_sc.release(); cs->d_cnt64.release();
+    cs->d_cstart.release(); cs->d_cloc.release(); cs->d_scan_tmp.release(); cs->d_cscore.release();
+    if (cs->ev0) cudaEventDestroy(cs->ev0);
+    if (cs->ev1) cudaEventDestroy(cs->ev1);
     delete cs;
     g_cs_states.erase(g_cs_states.begin() + i);
     return;
@@ -1108,6 +1121,193 @@ int ngmlr_b200_cs_score_batch(ngmlr_b200_ctx* ctx, int n, const char* const* seq
   CU(cudaMemcpyAsync(cs->sw_scores.data(), cs->d_sw.p, m * 4, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   return rc;
+}
+
+}  // extern "C"
+
+extern "C" {
+
+int ngmlr_b200_cs_upload(ngmlr_b200_ctx* ctx, int n, const char* const* seqs, const int32_t* lens) {
+  if (!ctx) return -1;
+  if (n < 0) return ctx->fail("cs_upload: n < 0");
+  CU(cudaSetDevice(ctx->device));
+  CsState* cs = cs_state(ctx, true);
+  cudaStream_t st = ctx->stream;
+  std::vector<uint64_t> seq_off((size_t)n + 1);
+  size_t bytes = 0;
+  for (int i = 0; i < n; ++i) {
+    seq_off[i] = bytes;
+    bytes += align_up((size_t)std::max(lens[i], 0) + 1, 16);
+  }
+  std::vector<uint8_t> hseq(bytes + 16, 0);
+  parallel_for(n, 256, [&](int i) { memcpy(hseq.data() + seq_off[i], seqs[i], (size_t)std::max(lens[i], 0)); });
+  CU(cs->d_seq.reserve(bytes + 16));
+  CU(cs->d_off.reserve((size_t)n + 1));
+  CU(cs->d_len.reserve((size_t)n + 1));
+  CU(cudaMemcpyAsync(cs->d_seq.p, hseq.data(), bytes, cudaMemcpyHostToDevice, st));
+  if (n) {
+    CU(cudaMemcpyAsync(cs->d_off.p, seq_off.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(cs->d_len.p, lens, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  }
+  CU(cudaStreamSynchronize(st));
+  cs->rn = n;
+  cs->rbytes = bytes;
+  cs->n_cand = 0;
+  return 0;
+}
+
+int ngmlr_b200_cs_run(ngmlr_b200_ctx* ctx, float sensitivity, float min_kmer_hits, int corridor,
+                      int read_part_length, int64_t* n_candidates, float* kernel_ms) {
+  if (!ctx) return -1;
+  CsState* cs = cs_state(ctx, false);
+  if (!cs || !cs->index_len) return ctx->fail("cs_run: call cs_set_index first");
+  if (!cs->enc_bytes) return ctx->fail("cs_run: call cs_set_reference first");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int n = cs->rn;
+  if (n_candidates) *n_candidates = 0;
+  if (kernel_ms) *kernel_ms = 0.0f;
+  if (n <= 0) return 0;
+  if (!cs->ev0) {
+    CU(cudaEventCreate(&cs->ev0));
+    CU(cudaEventCreate(&cs->ev1));
+  }
+  const size_t n1 = (size_t)n + 1;
+  CU(cs->d_hits.reserve(n1));
+  CU(cs->d_cap.reserve(n1));
+  CU(cs->d_count.reserve(n1));
+  CU(cs->d_max.reserve(n1));
+  CU(cs->d_a.reserve(n1)); CU(cs->d_b.reserve(n1)); CU(cs->d_c.reserve(n1));
+  CU(cs->d_sa.reserve(n1)); CU(cs->d_sb.reserve(n1)); CU(cs->d_sc.reserve(n1));
+  CU(cs->d_cnt64.reserve(n1)); CU(cs->d_cstart.reserve(n1));
+  size_t tmp_bytes = 0;
+  CU(cs_exclusive_scan(nullptr, tmp_bytes, cs->d_a.p, cs->d_sa.p, (int)n1, st));
+  CU(cs->d_scan_tmp.reserve(tmp_bytes + 256));
+  CsParams p;
+  memset(&p, 0, sizeof(p));
+  p.tab = cs->d_tab.p;
+  p.used = cs->d_used.p;
+  p.pos = cs->d_pos.p;
+  p.unit_offset = cs->unit_offset;
+  p.k = cs->k;
+  p.bin_shift = cs->bin_shift;
+  p.sensitivity = sensitivity;
+  p.min_kmer_hits = min_kmer_hits;
+  p.seq = cs->d_seq.p;
+  p.seq_off = cs->d_off.p;
+  p.seq_len = cs->d_len.p;
+  p.n = n;
+  p.hits = cs->d_hits.p;
+  CU(cudaEventRecord(cs->ev0, st));
+  CU(launch_cs_search(p, true, st));
+  CU(launch_cs_sizes(cs->d_hits.p, n, cs->d_cap.p, cs->d_a.p, cs->d_b.p, cs->d_c.p, st));
+  size_t tb = cs->d_scan_tmp.cap;
+  CU(cs_exclusive_scan(cs->d_scan_tmp.p, tb, cs->d_a.p, cs->d_sa.p, (int)n1, st));
+  tb = cs->d_scan_tmp.cap;
+  CU(cs_exclusive_scan(cs->d_scan_tmp.p, tb, cs->d_b.p, cs->d_sb.p, (int)n1, st));
+  tb = cs->d_scan_tmp.cap;
+  CU(cs_exclusive_scan(cs->d_scan_tmp.p, tb, cs->d_c.p, cs->d_sc.p, (int)n1, st));
+  unsigned long long totals[3] = {0, 0, 0};
+  CU(cudaMemcpyAsync(&totals[0], cs->d_sa.p + n, 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(&totals[1], cs->d_sb.p + n, 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(&totals[2], cs->d_sc.p + n, 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  const size_t need = (size_t)totals[0] * 16 + (size_t)totals[1] * 4 + (size_t)totals[2] * 16;
+  if (need > ((size_t)48 << 30))
+    return ctx->fail("cs_run: %zu bytes of vote tables needed; use cs_score_batch (chunked) for this batch", need);
+  CU(cs->d_tables.reserve((size_t)totals[0] * 16 + 16));
+  CU(cs->d_order.reserve((size_t)totals[1] + 4));
+  CU(cs->d_out.reserve((size_t)totals[2] + 4));
+  CU(cudaMemsetAsync(cs->d_tables.p, 0, (size_t)totals[0] * 16, st));
+  p.tables = cs->d_tables.p;
+  p.table_off = reinterpret_cast<const uint64_t*>(cs->d_sa.p);
+  p.table_cap = cs->d_cap.p;
+  p.order = cs->d_order.p;
+  p.order_off = reinterpret_cast<const uint64_t*>(cs->d_sb.p);
+  p.out = cs->d_out.p;
+  p.out_off = reinterpret_cast<const uint64_t*>(cs->d_sc.p);
+  p.out_count = cs->d_count.p;
+  p.max_hits = cs->d_max.p;
+  CU(launch_cs_search(p, false, st));
+  CU(launch_cs_count_to_u64(cs->d_count.p, n, cs->d_cnt64.p, st));
+  tb = cs->d_scan_tmp.cap;
+  CU(cs_exclusive_scan(cs->d_scan_tmp.p, tb, cs->d_cnt64.p, cs->d_cstart.p, (int)n1, st));
+  unsigned long long m64 = 0;
+  CU(cudaMemcpyAsync(&m64, cs->d_cstart.p + n, 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  const size_t m = (size_t)m64;
+  cs->n_cand = (long long)m;
+  CU(cs->d_cloc.reserve(m + 1));
+  CU(cs->d_cscore.reserve(m + 1));
+  CU(cs->d_rev.reserve(m + 1));
+  CU(cs->d_winpos.reserve(m + 1));
+  CU(cs->d_qoff.reserve(m + 1));
+  CU(cs->d_qlen.reserve(m + 1));
+  CU(cs->d_sw.reserve(m + 1));
+  CU(launch_cs_compact(cs->d_out.p, reinterpret_cast<const uint64_t*>(cs->d_sc.p), cs->d_count.p, cs->d_cstart.p,
+                       cs->d_off.p, cs->d_len.p, n, corridor >> 1, cs->d_cloc.p, cs->d_cscore.p, cs->d_rev.p,
+                       cs->d_winpos.p, cs->d_qoff.p, cs->d_qlen.p, st));
+  if (m) {
+    const int win_len = ((read_part_length + 10 + corridor) | 1) + 1;  // refMaxLen, src/ScoreBuffer.h:71-72
+    const int warps_per_cta = 4;
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->num_sms * 8, (m + warps_per_cta - 1) / warps_per_cta));
+    const size_t stride = align_up((size_t)win_len + 4, 4);
+    CU(cs->d_swscratch.reserve((size_t)grid * warps_per_cta * stride * 2));
+    SwParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.seq = cs->d_seq.p;
+    sp.ref_off = cs->d_qoff.p;
+    sp.qry_off = cs->d_qoff.p;
+    sp.ref_len = cs->d_qlen.p;
+    sp.qry_len = cs->d_qlen.p;
+    sp.out = cs->d_sw.p;
+    sp.n = (int)m;
+    sp.scratch = cs->d_swscratch.p;
+    sp.scratch_stride = stride;
+    sp.enc = cs->d_enc.p;
+    sp.concat_len = cs->concat_len;
+    sp.win_pos = cs->d_winpos.p;
+    sp.rev = cs->d_rev.p;
+    sp.win_len = win_len;
+    CU(launch_sw_score_gather(sp, grid, st));
+  }
+  CU(cudaEventRecord(cs->ev1, st));
+  CU(cudaStreamSynchronize(st));
+  if (n_candidates) *n_candidates = (int64_t)m;
+  if (kernel_ms) cudaEventElapsedTime(kernel_ms, cs->ev0, cs->ev1);
+  return 0;
+}
+
+int ngmlr_b200_cs_fetch(ngmlr_b200_ctx* ctx, int64_t* cand_start, const float** cs_scores,
+                        const uint64_t** locs, const uint8_t** reverse, const float** sw_scores,
+                        float* max_hits) {
+  if (!ctx) return -1;
+  CsState* cs = cs_state(ctx, false);
+  if (!cs) return ctx->fail("cs_fetch: nothing to fetch");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int n = cs->rn;
+  const size_t m = (size_t)cs->n_cand;
+  cs->scores.assign(m, 0.0f);
+  cs->locs.assign(m, 0);
+  cs->reverse.assign(m, 0);
+  cs->sw_scores.assign(m, -1.0f);
+  static_assert(sizeof(unsigned long long) == sizeof(int64_t), "");
+  if (n) CU(cudaMemcpyAsync(cand_start, cs->d_cstart.p, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, st));
+  else cand_start[0] = 0;
+  if (n && max_hits) CU(cudaMemcpyAsync(max_hits, cs->d_max.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  if (m) {
+    CU(cudaMemcpyAsync(cs->scores.data(), cs->d_cscore.p, m * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(cs->locs.data(), cs->d_cloc.p, m * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(cs->reverse.data(), cs->d_rev.p, m, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(cs->sw_scores.data(), cs->d_sw.p, m * 4, cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaStreamSynchronize(st));
+  *cs_scores = cs->scores.data();
+  *locs = cs->locs.data();
+  *reverse = cs->reverse.data();
+  *sw_scores = cs->sw_scores.data();
+  return n;
 }
 
 }  // extern "C"

@@ -43,4 +43,15 @@ cudaError_t launch_cs_search(const CsParams& p, bool count_only, cudaStream_t st
 cudaError_t launch_unpack_index(const uint8_t* packed, uint32_t n, uint32_t* tab, uint8_t* used,
                                 cudaStream_t stream);
 
+// device-resident candidate pipeline glue (cs_pipeline.cu)
+cudaError_t cs_exclusive_scan(void* temp, size_t& temp_bytes, const unsigned long long* in,
+                              unsigned long long* out, int n, cudaStream_t stream);
+cudaError_t launch_cs_sizes(const unsigned long long* hits, int n, uint32_t* cap, unsigned long long* a,
+                            unsigned long long* b, unsigned long long* c, cudaStream_t stream);
+cudaError_t launch_cs_count_to_u64(const int32_t* cnt, int n, unsigned long long* out, cudaStream_t stream);
+cudaError_t launch_cs_compact(const CsCandidate* out, const uint64_t* out_off, const int32_t* out_count,
+                              const unsigned long long* cstart, const uint64_t* seq_off, const int32_t* seq_len,
+                              int n, int half_corridor, unsigned long long* loc, float* score, uint8_t* rev,
+                              unsigned long long* win_pos, uint64_t* qoff, int32_t* qlen, cudaStream_t stream);
+
 }  // namespace nb

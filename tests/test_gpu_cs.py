@@ -65,3 +65,24 @@ def test_fused_search_and_candidate_scoring_matches_oracle(aligner, oracle):
             q = _cpl(s)[::-1] if rev else s
             assert sw == oracle.ssw_score(window, q)
     orc.close()
+
+
+def test_resident_pipeline_equals_one_shot_call(aligner):
+    """cs_upload / cs_run / cs_fetch (device-resident: prefix sums, compaction and scoring without
+    host round trips) must return exactly what cs_score_batch returns."""
+    from ngmlr_b200 import refindex
+    contigs = cs_cases.genome_contigs()
+    ref = refindex.encode_reference(contigs)
+    aligner.set_index(refindex.build_index(ref))
+    aligner.set_reference(ref)
+    subs = cs_cases.subreads(500, 31, contigs)
+    want, wmx = aligner.cs_score(subs)
+    aligner.cs_upload(subs)
+    for _ in range(2):   # repeatable on one upload
+        m, ms = aligner.cs_run()
+        start, sc, lo, rv, sw, mx = aligner.cs_fetch()
+        assert m == start[-1] == sum(len(w) for w in want) and ms > 0
+        for i, w in enumerate(want):
+            got = [(sc[j], int(lo[j]), int(rv[j]), sw[j]) for j in range(start[i], start[i + 1])]
+            assert got == w, i
+        assert np.array_equal(mx, wmx)
