@@ -1,8 +1,10 @@
 #!/usr/bin/env python
 """bench.py -- aligned Gbp/s of the convex-gap banded alignment hot path on B200.
 
-One "step" = one pass of the hot path (fill -> traceback -> binary CIGAR -> CIGAR/MD text) over
-one batch of synthetic PacBio-shaped alignment problems: BASELINE.json configs[1] (synthetic 50 Mb
+One "step" = one pass of the hot path over one batch of synthetic PacBio-shaped reads: stage 0/2
+(k-mer candidate search of every 256-bp sub-read, device-side window decode and StrippedSW scoring
+of every candidate) followed by stage 4 (convex fill -> traceback -> binary CIGAR -> CIGAR/MD text of
+the read's interval alignment): BASELINE.json configs[1] (synthetic 50 Mb
 reference, ~8 kb reads, 15 % errors ins:del:sub 9:4:2, anchored corridor) sharded by read across
 ranks (weak scaling: every rank aligns its own `--reads` reads per step; no per-step collective;
 one NCCL broadcast of the reference at start-up).
@@ -83,34 +85,109 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_run(problems, threads, impl):
+class CpuStage02:
+    """Stage 0/2 on the CPU with the reference's own code (oracle/_ref/libngmlr_full.so: CS vote,
+    DecodeRefSequence, StrippedSW), or with the oracle port when that library is absent."""
+
+    def __init__(self, genome, n_contigs=5):
+        import ctypes as C
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib
+        self.C = C
+        step_c = genome.size // n_contigs
+        contigs = [genome[i * step_c:(i + 1) * step_c] for i in range(n_contigs)]
+        self.kind = "port"
+        if oracle_lib.CsReference.available():
+            try:
+                fasta = f"/tmp/ngmlr_b200_bench_{os.getpid()}.fa"
+                with open(fasta, "w") as f:
+                    for i, c in enumerate(contigs):
+                        f.write(f">c{i}\n{c.tobytes().decode()}\n")
+                lib = C.CDLL(oracle_lib.CsReference.PATH)
+                lib.ref_cs_init(fasta.encode())
+                lib.ref_cs_probe_create.restype = C.c_void_p
+                lib.ref_full_ssw_create.restype = C.c_void_p
+                lib.ref_full_ssw_score.restype = C.c_float
+                lib.ref_full_ssw_score.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+                self.lib = lib
+                self.kind = "reference"
+                os.unlink(fasta)
+            except OSError:
+                self.kind = "port"
+        if self.kind == "port":
+            self.orc = oracle_lib.CsOracle([c.tobytes() for c in contigs])
+            self.ssw = oracle_lib.Oracle()
+
+    def worker_state(self):
+        if self.kind == "reference":
+            return (self.C.c_void_p(self.lib.ref_cs_probe_create()), self.C.c_void_p(self.lib.ref_full_ssw_create()))
+        return None
+
+    _CPL = bytes.maketrans(b"ACGT", b"TGCA")
+
+    def read(self, st, qry):
+        """All sub-reads of one read: vote, then score every candidate. Returns #candidates."""
+        C = self.C
+        n_c = 0
+        for k in range(len(qry) // 256):
+            sub = qry[k * 256:(k + 1) * 256]
+            if self.kind == "reference":
+                sc = (C.c_float * 512)()
+                lo = (C.c_ulonglong * 512)()
+                rv = (C.c_int * 512)()
+                mh = C.c_float()
+                n = self.lib.ref_cs_search_p(st[0], sub, len(sub), 16, sc, lo, rv, 512, C.byref(mh))
+                buf = C.create_string_buffer(312)
+                for j in range(max(0, min(n, 512))):
+                    if not self.lib.ref_cs_decode(C.c_ulonglong(lo[j] - 20), C.c_ulonglong(308), buf):
+                        buf.value = b"N" * 308
+                    q = sub.translate(self._CPL)[::-1] if rv[j] else sub
+                    self.lib.ref_full_ssw_score(st[1], buf.value, q)
+                    n_c += 1
+            else:
+                cands, _ = self.orc.search(sub)
+                for (_s, loc, rev) in cands:
+                    w = self.orc.decode((loc - 20) % (1 << 64), 308) or b"N" * 308
+                    self.ssw.ssw_score(w, sub.translate(self._CPL)[::-1] if rev else sub)
+                    n_c += 1
+        return n_c
+
+
+def cpu_reference_run(problems, threads, impl, stage02=None):
     """Run problems through the CPU implementation on `threads` host threads (ctypes releases the
-    GIL). impl: 'reference' = oracle/_ref (unmodified ConvexAlignFast), 'port' = oracle C port."""
+    GIL). impl: 'reference' = oracle/_ref (unmodified ConvexAlignFast), 'port' = oracle C port.
+    stage02: CpuStage02 or None (stage 4 only)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
     work = list(range(len(problems)))
     lock = threading.Lock()
+    engines = [(oracle_lib.Reference() if impl == "reference" else oracle_lib.Oracle(),
+                stage02.worker_state() if stage02 else None) for _ in range(threads)]
 
-    def worker():
-        eng = oracle_lib.Reference() if impl == "reference" else oracle_lib.Oracle()
+    def worker(t):
+        eng, st = engines[t]
         while True:
             with lock:
                 if not work:
                     break
                 i = work.pop()
             p = problems[i]
+            if stage02:
+                stage02.read(st, p.qry)
             r = eng.single_align(p.ref, p.qry, p.offsets, p.lengths)
             assert r["ret"] == len(p.qry)
-        if impl == "reference":
-            eng.close()
 
-    ts = [threading.Thread(target=worker) for _ in range(threads)]
+    ts = [threading.Thread(target=worker, args=(t,)) for t in range(threads)]
     t0 = time.perf_counter()
     for t in ts:
         t.start()
     for t in ts:
         t.join()
-    return time.perf_counter() - t0
+    dt = time.perf_counter() - t0
+    if impl == "reference":
+        for eng, _ in engines:
+            eng.close()
+    return dt
 
 
 def cpu_impl_kind():
@@ -134,6 +211,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--reads", type=int, default=8192, help="reads (alignment problems) per step per GPU")
     ap.add_argument("--genome-mb", type=float, default=50.0)
+    ap.add_argument("--dp-only", action="store_true", help="time stage 4 (convex alignment) alone")
     ap.add_argument("--contexts", type=int, default=2, help="aligner contexts (host threads/streams) per GPU")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     args = ap.parse_args()
@@ -163,9 +241,10 @@ def main():
         pool = make_pool(genome, n, seed=2)
         bases = sum(len(p.qry) for p in pool)
         cells = sum(p.cells for p in pool)
+        st02 = None if args.dp_only else CpuStage02(genome)
         for _ in range(min(args.warmup, 1)):
-            cpu_reference_run(pool[:threads], threads, kind)
-        times = [cpu_reference_run(pool, threads, kind) for _ in range(args.steps)]
+            cpu_reference_run(pool[:threads], threads, kind, st02)
+        times = [cpu_reference_run(pool, threads, kind, st02) for _ in range(args.steps)]
         t = float(np.sum(times))
         val = bases * args.steps / t / 1e9
         line = {"metric": "aligned_gbp_per_s", "value": val, "unit": "Gbp/s", "impl": "reference",
@@ -176,7 +255,8 @@ def main():
                            "dp_cells_per_step": cells},
                 "cpu_baseline": {"value": val, "unit": "Gbp/s", "cores": threads, "kind": kind,
                                  "sample": f"{n} reads ({bases} bases, {cells} DP cells) per step, {threads} threads, "
-                                           "ConvexAlignFast::SingleAlign only (fill+backtrack+CIGAR/MD)",
+                                           + ("ConvexAlignFast::SingleAlign only" if args.dp_only else
+                                              f"CS vote + DecodeRefSequence + StrippedSW ({st02.kind}) then ConvexAlignFast::SingleAlign"),
                                  "mcells_per_s_per_core": cells * args.steps / t / threads / 1e6},
                 "e2e": {"value": val, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -193,22 +273,47 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    # reference genome: generated on rank 0, ONE NCCL broadcast at start-up, none per step
+    # reference: genome + 4-bit encoding + k-mer index built on rank 0, then ONE NCCL broadcast of
+    # the packed reference at start-up; no collective per step
+    from ngmlr_b200 import refindex
     n_genome = int(args.genome_mb * 1e6)
-    if world > 1:
-        g = torch.empty(n_genome, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            g.copy_(torch.from_numpy(synth.random_genome(n_genome, 1)))
-        dist.broadcast(g, src=0)
-        genome = g.cpu().numpy()
-        del g
-    else:
+    n_contigs = 5
+    t_ref0 = time.perf_counter()
+    if rank == 0:
         genome = synth.random_genome(n_genome, 1)
+        step_c = n_genome // n_contigs
+        enc_ref = refindex.encode_reference([genome[i * step_c:(i + 1) * step_c] for i in range(n_contigs)])
+        kidx = refindex.build_index(enc_ref)
+        meta = [enc_ref.enc.size, enc_ref.concat_len, kidx.tab.size, kidx.pos.size] + enc_ref.ref_start + enc_ref.ref_len
+    if world > 1:
+        mt = torch.zeros(4 + 2 * n_contigs, dtype=torch.int64, device=dev)
+        if rank == 0:
+            mt.copy_(torch.tensor(meta, dtype=torch.int64))
+        dist.broadcast(mt, src=0)
+        m = [int(x) for x in mt.cpu()]
+        bufs = {"genome": (n_genome, torch.uint8), "enc": (m[0], torch.uint8), "tab": (m[2], torch.int32),
+                "rci": (m[2], torch.int8), "pos": (m[3], torch.int32)}
+        got = {}
+        for name, (sz, dt) in bufs.items():
+            t = torch.empty(sz, dtype=dt, device=dev)
+            if rank == 0:
+                src = {"genome": genome, "enc": enc_ref.enc, "tab": kidx.tab.view(np.int32),
+                       "rci": kidx.rci, "pos": kidx.pos.view(np.int32)}[name]
+                t.copy_(torch.from_numpy(np.ascontiguousarray(src)))
+            dist.broadcast(t, src=0)
+            got[name] = t.cpu().numpy()
+            del t
+        if rank != 0:
+            genome = got["genome"]
+            enc_ref = refindex.EncodedReference(got["enc"], m[1], m[4:4 + n_contigs], m[4 + n_contigs:4 + 2 * n_contigs])
+            kidx = refindex.KmerIndex(13, 4, got["tab"].view(np.uint32), got["rci"], got["pos"].view(np.uint32))
+    t_ref = time.perf_counter() - t_ref0
 
-    from ngmlr_b200 import B200Aligner, PackedBatch
+    from ngmlr_b200 import B200Aligner, PackedBatch, PackedReads, split_read
     pool = make_pool(genome, args.reads, seed=2 + rank)   # reads sharded by rank: own reads per rank
     batch = PackedBatch.from_problems(pool)
     bases = batch.read_bases
+    subreads = PackedReads([s for p in pool for s in split_read(p.qry)])   # ReadProvider::splitRead
     # S independent aligner contexts (own stream, own device arenas), driven by S host threads --
     # the reference's model of one aligner object per worker thread. Batches of different contexts
     # overlap on the GPU, which hides the tail of each fill launch and the traceback behind the
@@ -217,6 +322,9 @@ def main():
     streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
     als = [B200Aligner(local_rank, stream=st_.cuda_stream) for st_ in streams]
     al = als[0]
+    for a_ in als:
+        a_.set_index(kidx)
+        a_.set_reference(enc_ref)
 
     def barrier():
         if world > 1:
@@ -236,14 +344,20 @@ def main():
     # ---- device-resident: upload once per context, then time K x run() ----
     for a_ in als:
         a_.upload(batch)
+        a_.cs_upload(subreads)
         for _ in range(args.warmup):
+            if not args.dp_only:
+                a_.cs_run()
             a_.run()
     # (a) one context alone: per-kernel durations for the roofline (kernel timed in isolation)
     barrier()
-    fill_ms, tb_ms, cp_ms = [], [], []
+    fill_ms, tb_ms, cp_ms, cs_ms = [], [], [], []
+    n_cand = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(streams[0])
     for _ in range(args.steps):
+        n_cand, ms_ = (0, 0.0) if args.dp_only else al.cs_run()
+        cs_ms.append(ms_)
         al.run()
         st = al.stats()
         fill_ms.append(st["fill_ms"])
@@ -265,6 +379,8 @@ def main():
 
     def dev_worker(j, k):
         for _ in range(k):
+            if not args.dp_only:
+                als[j].cs_run()
             als[j].run()
         ends[j].record(streams[j])
 
@@ -283,8 +399,17 @@ def main():
     cells = st["cells"]
 
     # ---- end to end from host buffers through the public call ----
+    cs_bytes = {}
+
     def e2e_worker(j, k):
         for _ in range(k):
+            if not args.dp_only:
+                als[j].cs_upload(subreads)       # host buffers -> device
+                m_, _ms = als[j].cs_run()
+                cstart, _sc, _lo, _rv, sw_, _mx = als[j].cs_fetch()   # candidates + scores -> host
+                assert m_ == cstart[-1] and sw_.size == m_
+                cs_bytes["h2d"] = subreads.bases + 12 * subreads.n
+                cs_bytes["d2h"] = 17 * int(m_) + 12 * subreads.n
             out = als[j].BatchAlign(batch)
             assert len(out) == batch.n and out.ret(0) == len(pool[0].qry)
 
@@ -353,15 +478,20 @@ def main():
                          "note": "ALU-pipe-bound kernel (~38 ALU-pipe SASS instr per 32-cell step, 2 cycles each "
                                  "per SMSP, DESIGN.md 4.1); HBM frac is structurally ~0.015"},
             "kernel_ms_per_step": {"fill": float(np.mean(fill_ms)), "traceback": float(np.mean(tb_ms)),
-                                   "compact": float(np.mean(cp_ms))},
-            "e2e": {"value": e2e_val, "unit": "Gbp/s", "h2d_bytes_per_step": st_e2e["h2d_bytes"],
-                    "d2h_bytes_per_step": st_e2e["d2h_bytes"], "ms_per_step": e2e_ms / args.steps,
+                                   "compact": float(np.mean(cp_ms)),
+                                   "stage02_cs_vote_decode_score": float(np.mean(cs_ms))},
+            "stage02": {"subreads_per_step_per_gpu": subreads.n, "candidates_per_step_per_gpu": int(n_cand),
+                        "sw_cell_updates_per_step_per_gpu": int(n_cand) * 257 * 307,
+                        "reference_setup_s": t_ref,
+                        "note": "k-mer vote of every 256-bp sub-read + device decode + StrippedSW score of every candidate"},
+            "e2e": {"value": e2e_val, "unit": "Gbp/s", "h2d_bytes_per_step": st_e2e["h2d_bytes"] + cs_bytes.get("h2d", 0),
+                    "d2h_bytes_per_step": st_e2e["d2h_bytes"] + cs_bytes.get("d2h", 0), "ms_per_step": e2e_ms / args.steps,
                     "host_ms": {k: st_e2e[k] for k in ("host_pack_ms", "host_h2d_ms", "host_run_ms",
                                                        "host_d2h_ms", "host_text_ms")},
                     "host_threads": st_e2e["host_threads"]},
             "solo": {"gbp_per_s": bases * args.steps / (solo_ms * 1e-3) / 1e9, "ms_per_step": solo_ms / args.steps,
                      "note": "one context alone, same K steps (kernels not overlapped)"},
-            "gpu_launches": 2 * args.steps,
+            "gpu_launches": 14 * args.steps,
             "clocks": clocks,
         }
         # CPU baseline on this box's host cores, bounded sample of the same workload
@@ -370,12 +500,14 @@ def main():
             threads = cores
             n = args.cpu_sample or max(threads, min(len(pool), 2 * threads))
             sample = pool[:n]
-            t = cpu_reference_run(sample, threads, kind)
+            st02 = None if args.dp_only else CpuStage02(genome)
+            t = cpu_reference_run(sample, threads, kind, st02)
             sb = sum(len(p.qry) for p in sample)
             sc = sum(p.cells for p in sample)
             line["cpu_baseline"] = {"value": sb / t / 1e9, "unit": "Gbp/s", "cores": threads, "kind": kind,
                                     "sample": f"first {n} reads of the batch ({sb} bases, {sc} DP cells), "
-                                              f"{threads} threads, {t:.1f} s",
+                                              f"{threads} threads, {t:.1f} s, stages: "
+                                              + ("4 only" if st02 is None else f"0/2 ({st02.kind}) + 4"),
                                     "mcells_per_s_per_core": sc / t / threads / 1e6}
         except Exception as ex:  # the baseline is reported, never required for the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "Gbp/s", "cores": 0, "kind": "unavailable",

@@ -93,6 +93,24 @@ class PackedBatch:
                 self.ext_qstart.ctypes.data_as(i32p), self.ext_qend.ctypes.data_as(i32p))
 
 
+class PackedReads:
+    """(Sub-)reads laid out for the C ABI once, reusable across calls."""
+
+    def __init__(self, seqs):
+        self.seqs = [bytes(s) for s in seqs]
+        self.n = len(self.seqs)
+        self.arr = (C.c_char_p * max(self.n, 1))(*self.seqs)
+        self.lens = np.array([len(s) for s in self.seqs], dtype=np.int32)
+        self.bases = int(self.lens.sum())
+
+
+def split_read(seq, part_length=256):
+    """ReadProvider::splitRead's sub-reads (src/ReadProvider.cpp:57-134): floor(len / part_length)
+    consecutive pieces of part_length bases."""
+    n = len(seq) // part_length
+    return [seq[i * part_length:(i + 1) * part_length] for i in range(n)]
+
+
 class B200Aligner:
     def __init__(self, gpu_id=0, scoring=DEFAULT_SCORING, stream=None):
         self.lib = _lib.load()
@@ -199,11 +217,11 @@ class B200Aligner:
                 for i in range(n)], mx[:n]
 
     def cs_upload(self, seqs):
-        n = len(seqs)
-        self._cs_n = n
-        arr = (C.c_char_p * n)(*[bytes(s) for s in seqs])
-        lens = np.array([len(s) for s in seqs], dtype=np.int32)
-        self._check(self.lib.ngmlr_b200_cs_upload(self.h, n, arr, lens.ctypes.data_as(C.POINTER(C.c_int32))))
+        """seqs: list of bytes, or a PackedReads (pre-built C arrays, no per-call Python work)."""
+        reads = seqs if isinstance(seqs, PackedReads) else PackedReads(seqs)
+        self._cs_n = reads.n
+        self._check(self.lib.ngmlr_b200_cs_upload(self.h, reads.n, reads.arr,
+                                                  reads.lens.ctypes.data_as(C.POINTER(C.c_int32))))
 
     def cs_run(self, sensitivity=0.8, min_kmer_hits=0.0, corridor=40, read_part_length=256):
         """Resident stage 0/2 pass; returns (number of candidates, kernel milliseconds)."""

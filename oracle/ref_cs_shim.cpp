@@ -23,6 +23,7 @@
 #include "NGM.h"
 #include "PrefixTable.h"
 #include "SequenceProvider.h"
+#include "StrippedSW.h"
 #undef private
 #undef protected
 
@@ -43,8 +44,8 @@ CompactPrefixTable* g_table = 0;
 
 class CSProbe : public CS {
  public:
-  CSProbe() : CS(false) {
-    int len = (int)pow(2, 24);  // x_SrchTableBitLen, src/CS.cpp:27, 422-432
+  explicit CSProbe(int bits = 24) : CS(false) {
+    int len = (int)pow(2, bits);  // x_SrchTableBitLen = 24 in the reference, src/CS.cpp:27, 422-432
     rTable = new CSTableEntry[len];
     rList = new int[len];
     for (int i = 0; i < len; ++i) {
@@ -149,16 +150,38 @@ const void* ref_cs_index(unsigned* index_len, const unsigned** ref_table, unsign
   return g_table->m_Units[0].RefTableIndex;
 }
 
+// Extra probes for multi-threaded timing (one per thread, like one CS task per worker thread in
+// the reference). table 2^21 entries: RunRead never asks for more than 2^20.
+void* ref_cs_probe_create() { return new CSProbe(21); }
+void ref_cs_probe_destroy(void* p) { delete static_cast<CSProbe*>(p); }
+
+// StrippedSW::SingleScore through the full library (src/StrippedSW.cpp:162-202)
+void* ref_full_ssw_create() { return new StrippedSW(); }
+float ref_full_ssw_score(void* h, const char* ref, const char* qry) {
+  float r = -1.0f;
+  static_cast<StrippedSW*>(h)->SingleScore(0, 0, ref, qry, r, 0);
+  return r;
+}
+
+int ref_cs_search_p(void* probe, const char* seq, int len, int table_bits, float* scores,
+                    unsigned long long* locs, int* reverse, int cap, float* max_hits);
+
 // One (sub-)read through the reference's vote. Outputs in the reference's emission order.
 int ref_cs_search(const char* seq, int len, int table_bits, float* scores, unsigned long long* locs,
                   int* reverse, int cap, float* max_hits) {
+  return ref_cs_search_p(g_probe, seq, len, table_bits, scores, locs, reverse, cap, max_hits);
+}
+
+int ref_cs_search_p(void* probe_, const char* seq, int len, int table_bits, float* scores,
+                    unsigned long long* locs, int* reverse, int cap, float* max_hits) {
+  CSProbe* probe = static_cast<CSProbe*>(probe_);
   MappedRead* read = new MappedRead(0, len + 16);
   read->Seq = new char[len + 16];
   memcpy(read->Seq, seq, len);
   read->Seq[len] = 0;
   read->length = len;
-  int n = g_probe->search(read, table_bits);
-  *max_hits = g_probe->maxHitNumber;
+  int n = probe->search(read, table_bits);
+  *max_hits = probe->maxHitNumber;
   int m = read->numScores();
   if (n >= 0) {
     for (int i = 0; i < m && i < cap; ++i) {
