@@ -28,6 +28,7 @@ namespace {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int SW_ROWS = 9;  // 32 * 9 = 288 >= 257 = 256-bp sub-read + NUL: one pass for the hot case
 constexpr int SW_GAP = 255;
+constexpr int SW_PAIRS = 5;  // packed path: 5 registers x 2 rows per lane = 320 rows
 constexpr int SW_WARPS_PER_CTA = 4;
 
 __device__ __forceinline__ int nt_code(uint32_t c) {
@@ -96,6 +97,62 @@ __global__ void __launch_bounds__(SW_WARPS_PER_CTA * 32) sw_score_kernel(const S
     const uint8_t* __restrict__ ref = GATHER ? p.seq : p.seq + p.ref_off[pair];
     const uint8_t* __restrict__ qry = p.seq + p.qry_off[pair];
     int best = 0;
+    // ---- hot case: at most 320 query characters (256-bp sub-read + NUL) ----
+    // A gap costs 255 per base, so a gapped path beats its best ungapped piece only if it gains
+    // more than 255 before AND after the gap: impossible with fewer than 512 query characters.
+    // Then E and F never influence the maximum and the recurrence is H = max(0, diag + s).
+    // Two rows per register (16-bit halves) with Blackwell's packed integer ops:
+    // VIMNMX.U16x2 (character mismatch), VIADDMNMX.S16x2.RELU (max(diag + s, 0)), VIMNMX.S16x2.
+    if (qlen <= 32 * 2 * SW_PAIRS) {
+      const int row0 = lane * 2 * SW_PAIRS;
+      uint32_t qc2[SW_PAIRS], vq2[SW_PAIRS], H2[SW_PAIRS];
+#pragma unroll
+      for (int pq = 0; pq < SW_PAIRS; ++pq) {
+        uint32_t codes[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int row = row0 + 2 * pq + h;
+          int cq = 4;  // NUL / beyond the query: scores 0 against everything
+          if (row < qlen - 1) cq = q_rev ? nt_code(cpl(qry[qlen - 2 - row])) : nt_code(qry[row]);
+          codes[h] = (uint32_t)cq;
+        }
+        qc2[pq] = codes[0] | (codes[1] << 16);
+        vq2[pq] = (codes[0] == 4u ? 0u : 0xffffu) | (codes[1] == 4u ? 0u : 0xffff0000u);
+        H2[pq] = 0u;
+      }
+      uint32_t best2 = 0u, diag_top = 0u;
+      const int nsteps = rlen + 31;
+      for (int s = 0; s < nsteps; ++s) {
+        const int c = s - lane;
+        uint32_t up2 = __shfl_up_sync(FULL, H2[SW_PAIRS - 1], 1);
+        if (lane == 0) up2 = 0u;
+        if (c >= 0 && c < rlen) {
+          const uint32_t rc = (uint32_t)(GATHER ? gw.code(c) : nt_code(ref[c]));
+          const uint32_t rc2 = rc * 0x00010001u;
+          const bool col_n = rc == 4u;
+          uint32_t prev = diag_top;  // H of the row above pair 0 at column c-1 sits in its high half
+#pragma unroll
+          for (int pq = 0; pq < SW_PAIRS; ++pq) {
+            const uint32_t old = H2[pq];
+            const uint32_t diag = __byte_perm(prev, old, 0x5432);     // (H[2p-1], H[2p]) of column c-1
+            const uint32_t ne = __vminu2(qc2[pq] ^ rc2, 0x00010001u);  // 1 per half where the bases differ
+            const uint32_t mism = ne * 0xffffu;                        // 0xffff per differing half
+            const uint32_t valid = col_n ? 0u : vq2[pq];
+            const uint32_t sub = (mism | 0x00010001u) & valid;         // +1 / -1, 0 against N
+            const uint32_t h = __viaddmax_s16x2_relu(diag, sub, 0u);
+            H2[pq] = h;
+            best2 = __vmaxs2(best2, h);
+            prev = old;
+          }
+          diag_top = up2;
+        }
+      }
+      best = max((int)(best2 & 0xffffu), (int)(best2 >> 16));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(FULL, best, o));
+      if (lane == 0) p.out[pair] = (float)(best & 0xffff);
+      continue;
+    }
     const int rows_per_pass = 32 * SW_ROWS;
     for (int row_base = 0; row_base < qlen; row_base += rows_per_pass) {
       const bool first_pass = row_base == 0;
@@ -117,37 +174,6 @@ __global__ void __launch_bounds__(SW_WARPS_PER_CTA * 32) sw_score_kernel(const S
       }
       int outH = 0, outF = 0, diagTop = 0;
       const int nsteps = rlen + 31;
-      // A gap costs 255 per base, so a gapped path beats its best ungapped piece only if it gains
-      // more than 255 before AND after the gap: impossible with fewer than 512 query characters.
-      // Then E and F never influence the maximum and the recurrence is H = max(0, diag + s)
-      // (the hot case: 256-bp sub-reads, one pass of 288 rows). Longer queries take the full affine
-      // recurrence below.
-      if (qlen <= rows_per_pass) {  // single pass, and < 512 characters
-        for (int s = 0; s < nsteps; ++s) {
-          const int c = s - lane;
-          int upH = __shfl_up_sync(FULL, outH, 1);
-          if (lane == 0) upH = 0;
-          if (c >= 0 && c < rlen) {
-            const int rc = GATHER ? gw.code(c) : nt_code(ref[c]);
-#pragma unroll
-            for (int r = SW_ROWS - 1; r > 0; --r) {
-              const int sub = ((rc | qc[r]) & 4) ? 0 : (rc == qc[r] ? 1 : -1);
-              const int h = qc[r] < 0 ? 0 : max(H[r - 1] + sub, 0);
-              H[r] = h;
-              best = max(best, h);
-            }
-            {
-              const int sub = ((rc | qc[0]) & 4) ? 0 : (rc == qc[0] ? 1 : -1);
-              const int h = qc[0] < 0 ? 0 : max(diagTop + sub, 0);
-              H[0] = h;
-              best = max(best, h);
-            }
-            diagTop = upH;
-            outH = H[SW_ROWS - 1];
-          }
-        }
-        continue;
-      }
       for (int s = 0; s < nsteps; ++s) {
         const int c = s - lane;
         int upH = __shfl_up_sync(FULL, outH, 1);
