@@ -247,6 +247,7 @@ convex_fill_kernel(const FillParams p) {
       float dS = 0.0f;         // score of (x-1, y-1)
       float lL = sc.open_ref;  // left_cell contribution of (x-1, y)
       float lRunF = 0.0f;      // scalar kernel: D-run length of (x-1, y), 0 unless it is a deletion
+      bool lIsD = false;
       int lRun = 0;            // RAW kernel: raw indelRun / direction of (x-1, y)
       uint32_t lDir = DIR_STOP;
       float kS = bestS;
@@ -359,19 +360,25 @@ convex_fill_kernel(const FillParams p) {
                 //   I  <=>  !D && eU && (ur || !eG)
                 // with run lengths kept as floats (exact below 2^24; rows are < 32768 wide here).
                 const float upRunF = __uint_as_float(v.z);
-                const bool lr = lRunF > 0.0f, ur = upRunF > 0.0f;
+                const bool lr = lIsD, ur = upRunF > 0.0f;  // the left cell's run is > 0 iff it is a deletion
                 const bool X = (eU && ur) || eG;
                 const bool pD = eL && (lr || !X);
                 const bool pI = !pD && eU && (ur || !eG);
                 code = pD ? DIR_D : (pI ? DIR_I : (eG ? DIR_DIAG : DIR_STOP));
-                const float runF = pD ? __fadd_rn(lRunF, 1.0f) : (pI ? __fadd_rn(upRunF, 1.0f) : 0.0f);
+                // at most one of the two run counters is alive after this cell
+                const float newD = pD ? __fadd_rn(lRunF, 1.0f) : 0.0f;
+                const float newI = pI ? __fadd_rn(upRunF, 1.0f) : 0.0f;
+                const float runF = __fadd_rn(newD, newI);
                 const float pen = fminf(sc.ext_min, __fadd_rn(sc.gap_ext, __fmul_rn(runF, sc.decay)));
-                float e = __fadd_rn(S, pen);
-                if (S == 0.0f) e = 0.0f;
+                // e = (S == 0) ? 0 : S + pen  as one exact fused op: S + pen * [S != 0]
+                float nz;
+                asm("set.ne.f32.f32 %0, %1, 0f00000000;" : "=f"(nz) : "f"(S));
+                const float e = __fmaf_rn(pen, nz, S);
                 U = pI ? e : __fadd_rn(S, sc.open_read);
                 L = pD ? e : __fadd_rn(S, sc.open_ref);
-                oP = __float_as_uint(pI ? runF : 0.0f);
-                lRunF = pD ? runF : 0.0f;
+                oP = __float_as_uint(newI);
+                lRunF = newD;
+                lIsD = pD;
               }
               oS = S;
               oU = U;

@@ -7,7 +7,7 @@
 namespace nb {
 
 constexpr int FILL_WARPS_PER_CTA = 4;
-constexpr int FILL_CTAS_PER_SM = 4;
+constexpr int FILL_CTAS_PER_SM = 5;
 
 // team = all FILL_WARPS_PER_CTA warps of a CTA pipeline one problem; otherwise one warp per problem
 cudaError_t launch_convex_fill(const FillParams& p, bool raw, bool team, int grid, cudaStream_t stream);
