@@ -305,7 +305,7 @@ convex_fill_kernel(const FillParams p) {
           uint32_t dw = 0;
 #pragma unroll 1
           for (int k4 = 0; k4 < 16; k4 += 4) {
-#pragma unroll
+#pragma unroll 2  // 2 keeps the per-step predicates in registers; 4 makes ptxas spill them to a bit mask
             for (int k = 0; k < 4; ++k) {
               const int s = (g << 4) + k4 + k;
               uint4 v;
