@@ -844,6 +844,10 @@ struct CsState {
   long long n_cand = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<int64_t> h_cstart;
+  // pinned staging for the resident pipeline's upload / fetch
+  PinBuf<uint8_t> p_seq, p_rev;
+  PinBuf<float> p_score, p_sw;
+  PinBuf<uint64_t> p_loc;
 };
 
 std::vector<std::pair<ngmlr_b200_ctx*, CsState*>> g_cs_states;
@@ -875,6 +879,7 @@ void nb_cs_release(ngmlr_b200_ctx* ctx) {
     cs->d_cstart.release(); cs->d_cloc.release(); cs->d_scan_tmp.release(); cs->d_cscore.release();
     if (cs->ev0) cudaEventDestroy(cs->ev0);
     if (cs->ev1) cudaEventDestroy(cs->ev1);
+    cs->p_seq.release(); cs->p_rev.release(); cs->p_score.release(); cs->p_sw.release(); cs->p_loc.release();
     delete cs;
     g_cs_states.erase(g_cs_states.begin() + i);
     return;
@@ -1139,12 +1144,17 @@ int ngmlr_b200_cs_upload(ngmlr_b200_ctx* ctx, int n, const char* const* seqs, co
     seq_off[i] = bytes;
     bytes += align_up((size_t)std::max(lens[i], 0) + 1, 16);
   }
-  std::vector<uint8_t> hseq(bytes + 16, 0);
-  parallel_for(n, 256, [&](int i) { memcpy(hseq.data() + seq_off[i], seqs[i], (size_t)std::max(lens[i], 0)); });
+  CU(cs->p_seq.reserve(bytes + 16));
+  uint8_t* hseq = cs->p_seq.p;
+  parallel_for(n, 256, [&](int i) {
+    const size_t L = (size_t)std::max(lens[i], 0);
+    memcpy(hseq + seq_off[i], seqs[i], L);
+    memset(hseq + seq_off[i] + L, 0, align_up(L + 1, 16) - L);
+  });
   CU(cs->d_seq.reserve(bytes + 16));
   CU(cs->d_off.reserve((size_t)n + 1));
   CU(cs->d_len.reserve((size_t)n + 1));
-  CU(cudaMemcpyAsync(cs->d_seq.p, hseq.data(), bytes, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(cs->d_seq.p, hseq, bytes, cudaMemcpyHostToDevice, st));
   if (n) {
     CU(cudaMemcpyAsync(cs->d_off.p, seq_off.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(cs->d_len.p, lens, (size_t)n * 4, cudaMemcpyHostToDevice, st));
@@ -1288,25 +1298,25 @@ int ngmlr_b200_cs_fetch(ngmlr_b200_ctx* ctx, int64_t* cand_start, const float** 
   cudaStream_t st = ctx->stream;
   const int n = cs->rn;
   const size_t m = (size_t)cs->n_cand;
-  cs->scores.assign(m, 0.0f);
-  cs->locs.assign(m, 0);
-  cs->reverse.assign(m, 0);
-  cs->sw_scores.assign(m, -1.0f);
+  CU(cs->p_score.reserve(m + 1));
+  CU(cs->p_loc.reserve(m + 1));
+  CU(cs->p_rev.reserve(m + 1));
+  CU(cs->p_sw.reserve(m + 1));
   static_assert(sizeof(unsigned long long) == sizeof(int64_t), "");
   if (n) CU(cudaMemcpyAsync(cand_start, cs->d_cstart.p, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, st));
   else cand_start[0] = 0;
   if (n && max_hits) CU(cudaMemcpyAsync(max_hits, cs->d_max.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
   if (m) {
-    CU(cudaMemcpyAsync(cs->scores.data(), cs->d_cscore.p, m * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(cs->locs.data(), cs->d_cloc.p, m * 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(cs->reverse.data(), cs->d_rev.p, m, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(cs->sw_scores.data(), cs->d_sw.p, m * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(cs->p_score.p, cs->d_cscore.p, m * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(cs->p_loc.p, cs->d_cloc.p, m * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(cs->p_rev.p, cs->d_rev.p, m, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(cs->p_sw.p, cs->d_sw.p, m * 4, cudaMemcpyDeviceToHost, st));
   }
   CU(cudaStreamSynchronize(st));
-  *cs_scores = cs->scores.data();
-  *locs = cs->locs.data();
-  *reverse = cs->reverse.data();
-  *sw_scores = cs->sw_scores.data();
+  *cs_scores = cs->p_score.p;
+  *locs = cs->p_loc.p;
+  *reverse = cs->p_rev.p;
+  *sw_scores = cs->p_sw.p;
   return n;
 }
 

@@ -361,9 +361,9 @@ convex_fill_kernel(const FillParams p) {
                 // with run lengths kept as floats (exact below 2^24; rows are < 32768 wide here).
                 const float upRunF = __uint_as_float(v.z);
                 const bool lr = lIsD, ur = upRunF > 0.0f;  // the left cell's run is > 0 iff it is a deletion
-                const bool X = (eU && ur) || eG;
-                const bool pD = eL && (lr || !X);
-                const bool pI = !pD && eU && (ur || !eG);
+                const bool X = (eU & ur) | eG;  // bitwise on purpose: straight PLOP3s, no short-circuit
+                const bool pD = eL & (lr | !X);
+                const bool pI = (!pD) & eU & (ur | !eG);
                 code = pD ? DIR_D : (pI ? DIR_I : (eG ? DIR_DIAG : DIR_STOP));
                 // at most one of the two run counters is alive after this cell
                 const float newD = pD ? __fadd_rn(lRunF, 1.0f) : 0.0f;
