@@ -160,6 +160,7 @@ struct ngmlr_b200_ctx {
   int max_ref_len = 0;
   int wide_problems = 0;  // problems whose corridor is >= 352 columns wide
   int force_team = -1;
+  int ctas_per_sm[4] = {0, 0, 0, 0};  // occupancy of the four fill-kernel variants
   PinBuf<uint8_t> h_seq;
   PinBuf<int32_t> h_coff, h_clen, h_order;
   PinBuf<AlnDesc> h_desc;
@@ -498,10 +499,9 @@ int ngmlr_b200_convex_run(ngmlr_b200_ctx* ctx) {
   // the first chunk of the next one: ~4 x 100 columns); NGMLR_B200_FILL_TEAM=0/1 overrides.
   bool team = ctx->wide_problems * 2 > n;
   if (ctx->force_team >= 0) team = ctx->force_team != 0;
-  static int ctas_per_sm[4] = {0, 0, 0, 0};
   const int variant = (raw ? 1 : 0) | (team ? 2 : 0);
-  if (!ctas_per_sm[variant]) ctas_per_sm[variant] = std::max(1, fill_max_ctas_per_sm(raw, team));
-  const int max_grid = ctx->num_sms * ctas_per_sm[variant];
+  if (!ctx->ctas_per_sm[variant]) ctx->ctas_per_sm[variant] = std::max(1, fill_max_ctas_per_sm(raw, team));
+  const int max_grid = ctx->num_sms * ctx->ctas_per_sm[variant];
   const int want_grid = team ? n : (n + FILL_WARPS_PER_CTA - 1) / FILL_WARPS_PER_CTA;
   const int grid = std::max(1, std::min(max_grid, want_grid));
   ctx->fill_grid = grid;
