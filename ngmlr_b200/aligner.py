@@ -264,6 +264,10 @@ class B200Aligner:
     def force_raw(self, v):
         self.lib.ngmlr_b200_set_force_raw(self.h, int(v))
 
+    def debug_set_arena_words(self, words):
+        """Test hook: initial size of the direction arena (-1 = the host's estimate)."""
+        self.lib.ngmlr_b200_debug_set_arena_words(self.h, int(words))
+
     def force_team(self, v):
         """-1 auto, 0 one warp per problem, 1 four-warp teams (fill kernel scheduling)."""
         self.lib.ngmlr_b200_set_force_team(self.h, int(v))

@@ -161,6 +161,7 @@ struct ngmlr_b200_ctx {
   int wide_problems = 0;  // problems whose corridor is >= 352 columns wide
   int force_team = -1;
   int ctas_per_sm[4] = {0, 0, 0, 0};  // occupancy of the four fill-kernel variants
+  long long debug_arena_words = -1;    // test hook: initial direction-arena size
   PinBuf<uint8_t> h_seq;
   PinBuf<int32_t> h_coff, h_clen, h_order;
   PinBuf<AlnDesc> h_desc;
@@ -313,6 +314,13 @@ int ngmlr_b200_set_stream(ngmlr_b200_ctx* ctx, void* s) {
 }
 
 void* ngmlr_b200_get_stream(ngmlr_b200_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+// Test hook: start convex_run with a direction arena of `words` 32-bit words (-1 = estimate).
+int ngmlr_b200_debug_set_arena_words(ngmlr_b200_ctx* ctx, long long words) {
+  if (!ctx) return -1;
+  ctx->debug_arena_words = words;
+  return 0;
+}
 
 // force_team: -1 auto, 0 one warp per problem, 1 four-warp teams. Test / tuning hook.
 int ngmlr_b200_set_force_team(ngmlr_b200_ctx* ctx, int v) {
@@ -509,9 +517,13 @@ int ngmlr_b200_convex_run(ngmlr_b200_ctx* ctx) {
   const size_t bnd_stride = align_up((size_t)ctx->max_ref_len + STRIP_SLACK, 8);
   CU(ctx->d_bnd.reserve(warps * bnd_stride));
   size_t dir_words = std::max(ctx->dir_words_needed, (size_t)4096);
+  if (ctx->debug_arena_words >= 0) {  // force the overflow -> grow -> re-run path (tests)
+    dir_words = (size_t)ctx->debug_arena_words;
+    ctx->d_dir.release();
+  }
   size_t runs_cap = ctx->d_runs.cap;
 
-  for (int attempt = 0; attempt < 6; ++attempt) {
+  for (int attempt = 0; attempt < 16; ++attempt) {
     CU(ctx->d_dir.reserve(dir_words));
     CU(ctx->d_runs.reserve(runs_cap));
     CU(cudaMemsetAsync(ctx->d_counters.p, 0, 4 * sizeof(unsigned long long), st));
@@ -562,7 +574,10 @@ int ngmlr_b200_convex_run(ngmlr_b200_ctx* ctx) {
     const unsigned long long dir_used = ctx->h_counters.p[0], runs_used = ctx->h_counters.p[1];
     bool again = false;
     if (dir_used > ctx->d_dir.cap) {
-      dir_words = (size_t)dir_used + (size_t)dir_used / 8 + 4096;
+      // the counter under-reports after an overflow (warps stop allocating), so also double and
+      // fall back to the host's estimate
+      dir_words = std::max({(size_t)dir_used + (size_t)dir_used / 8 + 4096, (size_t)ctx->d_dir.cap * 2,
+                            ctx->dir_words_needed});
       again = true;
     }
     if (runs_used > ctx->d_runs.cap) {
@@ -572,7 +587,7 @@ int ngmlr_b200_convex_run(ngmlr_b200_ctx* ctx) {
     ctx->dir_used = dir_used;
     ctx->runs_used = runs_used;
     if (!again) break;
-    if (attempt == 5) return ctx->fail("convex_run: arena sizing did not converge");
+    if (attempt == 15) return ctx->fail("convex_run: arena sizing did not converge");
   }
   ctx->dir_words_needed = std::max(ctx->dir_words_needed, (size_t)ctx->dir_used);
   float ms = 0;

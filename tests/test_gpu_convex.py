@@ -5,7 +5,7 @@ import pytest
 
 import cases
 import golden_util as gu
-from ngmlr_b200 import PackedBatch, synth
+from ngmlr_b200 import PackedBatch, corridor, synth
 from oracle_lib import DEFAULT_SCORING, same_alignment
 
 pytestmark = pytest.mark.gpu
@@ -146,3 +146,32 @@ def test_both_fill_schedules_are_bit_exact(aligner, oracle, team):
         _compare_batch(aligner, oracle, probs)
     finally:
         aligner.force_team(-1)
+
+
+def test_direction_arena_overflow_is_recovered(aligner, oracle):
+    """The fill kernel bump-allocates its direction words; a too-small arena must be detected,
+    grown and the batch re-run -- results unchanged."""
+    probs = cases.random_problems(24, 707, max_len=1200)
+    aligner.debug_set_arena_words(5000)
+    try:
+        _compare_batch(aligner, oracle, probs, check_dirs=True)
+        assert aligner.stats()["fill_launches"] >= 2
+    finally:
+        aligner.debug_set_arena_words(-1)
+
+
+def test_rows_wider_than_int16_use_the_as_coded_kernel(aligner, oracle):
+    """Rows wider than 32767 cells: indelRun is a C `short` in the reference; such batches are routed
+    to the RAW kernel, which keeps the 16-bit wrap. Full-matrix corridors over a 40 kb window."""
+    rng = np.random.default_rng(5)
+    g = synth.random_genome(41000, 77)
+    probs = []
+    for h in (40, 70):
+        q = g[20000:20000 + h].copy()
+        q[rng.integers(0, h, 3)] = ord("A")
+        o, l = corridor.corridor_full(h, 40000)
+        probs.append(synth.AlignProblem(g[:40000].tobytes(), q.tobytes(), o, l))
+    # a homopolymer reference: one zero-score deletion run along the whole row
+    o, l = corridor.corridor_full(34, 36000)
+    probs.append(synth.AlignProblem(b"A" * 36000, b"C" * 34, o, l))
+    _compare_batch(aligner, oracle, probs, check_dirs=True)
