@@ -163,7 +163,10 @@ struct ngmlr_b200_ctx {
   int ctas_per_sm[4] = {0, 0, 0, 0};  // occupancy of the four fill-kernel variants
   long long debug_arena_words = -1;    // test hook: initial direction-arena size
   PinBuf<uint8_t> h_seq;
-  PinBuf<int32_t> h_coff, h_clen, h_order;
+  PinBuf<int32_t> h_coff, h_clen, h_order, h_blkbase;
+  PinBuf<int8_t> h_delta;
+  std::vector<uint8_t> is_packed;
+  int no_corridor_packing = 0;  // NGMLR_B200_NO_CORRIDOR_PACKING=1: always ship raw CorridorLines
   PinBuf<AlnDesc> h_desc;
   PinBuf<FillOut> h_fill;
   PinBuf<TraceOut> h_trace;
@@ -171,7 +174,8 @@ struct ngmlr_b200_ctx {
   PinBuf<unsigned long long> h_counters;
   std::vector<int32_t> ext_qs, ext_qe;
   DevBuf<uint8_t> d_seq;
-  DevBuf<int32_t> d_coff, d_clen, d_order;
+  DevBuf<int32_t> d_coff, d_clen, d_order, d_blkbase;
+  DevBuf<int8_t> d_delta;
   DevBuf<AlnDesc> d_desc;
   DevBuf<BlockRec> d_blocks;
   DevBuf<uint32_t> d_dir;
@@ -274,6 +278,7 @@ int ngmlr_b200_create(int gpu_id, const ngmlr_b200_scoring* s, ngmlr_b200_ctx** 
   ctx->sc.decay = d.gap_decay;
   ctx->raw = scoring_needs_raw(ctx->sc);
   if (const char* e = getenv("NGMLR_B200_FILL_TEAM")) ctx->force_team = atoi(e);
+  if (const char* e = getenv("NGMLR_B200_NO_CORRIDOR_PACKING")) ctx->no_corridor_packing = atoi(e);
   *out = ctx;
   return 0;
 }
@@ -283,10 +288,10 @@ void ngmlr_b200_destroy(ngmlr_b200_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   nb_cs_release(ctx);
-  ctx->h_seq.release(); ctx->h_coff.release(); ctx->h_clen.release(); ctx->h_order.release();
+  ctx->h_seq.release(); ctx->h_coff.release(); ctx->h_clen.release(); ctx->h_order.release(); ctx->h_blkbase.release(); ctx->h_delta.release();
   ctx->h_desc.release(); ctx->h_fill.release(); ctx->h_trace.release(); ctx->h_runs.release();
   ctx->h_counters.release();
-  ctx->d_seq.release(); ctx->d_coff.release(); ctx->d_clen.release(); ctx->d_order.release();
+  ctx->d_seq.release(); ctx->d_coff.release(); ctx->d_clen.release(); ctx->d_order.release(); ctx->d_blkbase.release(); ctx->d_delta.release();
   ctx->d_desc.release(); ctx->d_blocks.release(); ctx->d_dir.release(); ctx->d_bnd.release();
   ctx->d_fill.release(); ctx->d_scratch.release(); ctx->d_trace.release(); ctx->d_runs.release();
   ctx->d_counters.release();
@@ -362,6 +367,9 @@ int ngmlr_b200_convex_upload(ngmlr_b200_ctx* ctx, int n, const char* const* refs
   CU(ctx->h_seq.reserve(seq_bytes + 64));
   CU(ctx->h_coff.reserve(rows + 32));
   CU(ctx->h_clen.reserve(rows + 32));
+  CU(ctx->h_delta.reserve(rows + 32));
+  CU(ctx->h_blkbase.reserve(nblocks + 1));
+  ctx->is_packed.assign(n, 0);
   CU(ctx->h_desc.reserve(n));
   CU(ctx->h_order.reserve(n));
   ctx->ext_qs.assign(n, 0);
@@ -406,18 +414,36 @@ int ngmlr_b200_convex_upload(ngmlr_b200_ctx* ctx, int n, const char* const* refs
     d.ref_cap = ql > 200000 ? ql + 1 : 200000;
     d.tb_cap = (int)std::min<long long>((long long)ql + rl + 4, d.ref_cap);
     d.tb_off = tb_at[i];
-    int32_t* lens = ctx->h_clen.p + d.row_off;
-    int32_t* offs = ctx->h_coff.p + d.row_off;
-    if (ql) {
-      memcpy(offs, corridor_offsets + row_start[i], (size_t)ql * sizeof(int32_t));
-      memcpy(lens, corridor_lengths + row_start[i], (size_t)ql * sizeof(int32_t));
-    }
+    // Corridor rows: one pass that writes the packed form (int8 offset deltas + one base per 32-row
+    // block) and finds out whether it is exact for this problem (constant length, |delta| < 128);
+    // only problems that fail ship their raw CorridorLines.
+    const int32_t* src_off = corridor_offsets + row_start[i];
+    const int32_t* src_len = corridor_lengths + row_start[i];
+    int8_t* delta = ctx->h_delta.p + d.row_off;
+    int32_t* blkbase = ctx->h_blkbase.p + d.blk_off;
     int ml = 0;
     unsigned long long sum = 0;
+    bool packable = !ctx->no_corridor_packing && ql > 0;
+    const int len0 = ql ? src_len[0] : 0;
     for (int y = 0; y < ql; ++y) {
-      ml = std::max(ml, lens[y]);
-      sum += (unsigned long long)std::max(lens[y], 0);
+      const int ln = src_len[y];
+      ml = std::max(ml, ln);
+      sum += (unsigned long long)std::max(ln, 0);
+      const long long dl = y ? (long long)src_off[y] - (long long)src_off[y - 1] : 0;
+      packable = packable && ln == len0 && dl >= -128 && dl <= 127;
+      delta[y] = (int8_t)dl;
+      if ((y & 31) == 0) blkbase[y >> 5] = src_off[y];
     }
+    int32_t* lens = ctx->h_clen.p + d.row_off;
+    int32_t* offs = ctx->h_coff.p + d.row_off;
+    if (!packable && ql) {
+      memcpy(offs, src_off, (size_t)ql * sizeof(int32_t));
+      memcpy(lens, src_len, (size_t)ql * sizeof(int32_t));
+    }
+    d.packed = packable ? 1 : 0;
+    d.const_len = len0;
+    ctx->is_packed[i] = packable ? 1 : 0;
+    offs = const_cast<int32_t*>(src_off);  // the arena estimate below only needs the end points
     d.max_len = ml;
     maxlen[i] = std::min(ml, rl);
     est[i] = sum;
@@ -475,9 +501,30 @@ int ngmlr_b200_convex_upload(ngmlr_b200_ctx* ctx, int n, const char* const* refs
   CU(ctx->h_fill.reserve(n));
   CU(ctx->h_trace.reserve(n));
   CU(cudaMemcpyAsync(ctx->d_seq.p, ctx->h_seq.p, so, cudaMemcpyHostToDevice, st));
+  size_t raw_rows = 0;
+  int raw_problems = 0;
+  for (int i = 0; i < n; ++i)
+    if (!ctx->is_packed[i]) {
+      raw_rows += (size_t)qry_lens[i];
+      ++raw_problems;
+    }
+  CU(ctx->d_delta.reserve(rows + 32));
+  CU(ctx->d_blkbase.reserve(bo + 1));
   if (rows) {
-    CU(cudaMemcpyAsync(ctx->d_coff.p, ctx->h_coff.p, rows * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ctx->d_clen.p, ctx->h_clen.p, rows * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->d_delta.p, ctx->h_delta.p, rows, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->d_blkbase.p, ctx->h_blkbase.p, bo * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (raw_problems > 64 || raw_rows * 2 > rows) {  // many raw problems: ship the arrays whole
+      CU(cudaMemcpyAsync(ctx->d_coff.p, ctx->h_coff.p, rows * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(ctx->d_clen.p, ctx->h_clen.p, rows * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+      raw_rows = rows;
+    } else {
+      for (int i = 0; i < n; ++i) {
+        if (ctx->is_packed[i] || !qry_lens[i]) continue;
+        const size_t ro = (size_t)ctx->h_desc.p[i].row_off, nb = (size_t)qry_lens[i] * sizeof(int32_t);
+        CU(cudaMemcpyAsync(ctx->d_coff.p + ro, ctx->h_coff.p + ro, nb, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->d_clen.p + ro, ctx->h_clen.p + ro, nb, cudaMemcpyHostToDevice, st));
+      }
+    }
   }
   CU(cudaMemcpyAsync(ctx->d_desc.p, ctx->h_desc.p, (size_t)n * sizeof(AlnDesc), cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(ctx->d_order.p, ctx->h_order.p, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
@@ -486,7 +533,7 @@ int ngmlr_b200_convex_upload(ngmlr_b200_ctx* ctx, int n, const char* const* refs
   ctx->stats.host_pack_ms = (float)(t_pack1 - t_pack0);
   ctx->stats.host_h2d_ms = (float)(now_ms() - t_pack1);
   ctx->stats.host_threads = host_threads();
-  ctx->stats.h2d_bytes = (int64_t)(so + rows * 8 + (size_t)n * (sizeof(AlnDesc) + 4));
+  ctx->stats.h2d_bytes = (int64_t)(so + rows + bo * 4 + raw_rows * 8 + (size_t)n * (sizeof(AlnDesc) + 4));
   ctx->stats.seq_bytes = (int64_t)so;
   return 0;
 }
@@ -531,6 +578,8 @@ int ngmlr_b200_convex_run(ngmlr_b200_ctx* ctx) {
     fp.seq = ctx->d_seq.p;
     fp.c_off = ctx->d_coff.p;
     fp.c_len = ctx->d_clen.p;
+    fp.c_blkbase = ctx->d_blkbase.p;
+    fp.c_delta = ctx->d_delta.p;
     fp.desc = ctx->d_desc.p;
     fp.order = ctx->d_order.p;
     fp.n = n;
@@ -547,6 +596,8 @@ int ngmlr_b200_convex_run(ngmlr_b200_ctx* ctx) {
     tp.seq = ctx->d_seq.p;
     tp.c_off = ctx->d_coff.p;
     tp.c_len = ctx->d_clen.p;
+    tp.c_blkbase = ctx->d_blkbase.p;
+    tp.c_delta = ctx->d_delta.p;
     tp.desc = ctx->d_desc.p;
     tp.n = n;
     tp.blocks = ctx->d_blocks.p;
@@ -713,8 +764,18 @@ int ngmlr_b200_convex_debug_directions(ngmlr_b200_ctx* ctx, int i, uint8_t* dirs
   FillOut f;
   CU(cudaMemcpy(&f, ctx->d_fill.p + i, sizeof(f), cudaMemcpyDeviceToHost));
   if (nblk) CU(cudaMemcpy(blocks.data(), ctx->d_blocks.p + d.blk_off, nblk * sizeof(BlockRec), cudaMemcpyDeviceToHost));
-  const int32_t* offs = ctx->h_coff.p + d.row_off;
-  const int32_t* lens = ctx->h_clen.p + d.row_off;
+  std::vector<int32_t> offs_v(H), lens_v(H);
+  for (int y = 0; y < H; ++y) {
+    if (d.packed) {
+      offs_v[y] = (y & 31) ? offs_v[y - 1] + ctx->h_delta.p[d.row_off + y] : ctx->h_blkbase.p[d.blk_off + (y >> 5)];
+      lens_v[y] = d.const_len;
+    } else {
+      offs_v[y] = ctx->h_coff.p[d.row_off + y];
+      lens_v[y] = ctx->h_clen.p[d.row_off + y];
+    }
+  }
+  const int32_t* offs = offs_v.data();
+  const int32_t* lens = lens_v.data();
   const char* ref = reinterpret_cast<const char*>(ctx->h_seq.p + d.ref_off);
   const char* qry = reinterpret_cast<const char*>(ctx->h_seq.p + d.qry_off);
   size_t total = 0;

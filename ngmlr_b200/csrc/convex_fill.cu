@@ -136,8 +136,13 @@ convex_fill_kernel(const FillParams p) {
     const AlnDesc d = p.desc[ai];
     const uint8_t* __restrict__ ref = p.seq + d.ref_off;
     const uint8_t* __restrict__ qry = p.seq + d.qry_off;
-    const int32_t* __restrict__ coff = p.c_off + d.row_off;
-    const int32_t* __restrict__ clen = p.c_len + d.row_off;
+    CorridorView cv;
+    cv.off = p.c_off + d.row_off;
+    cv.len = p.c_len + d.row_off;
+    cv.blk_base = p.c_blkbase + d.blk_off;
+    cv.delta = p.c_delta + d.row_off;
+    cv.const_len = d.const_len;
+    cv.packed = d.packed;
     const int H = d.height, ref_len = d.ref_len;
     const int nblk = (H + 31) >> 5;
 
@@ -156,11 +161,8 @@ convex_fill_kernel(const FillParams p) {
     // rows of this warp's next block are fetched one block ahead
     int n_off = 0, n_len = 0;
     uint32_t n_q = 0x100u;  // never equals a byte
-    if ((tw << 5) + lane < H) {
-      n_off = coff[(tw << 5) + lane];
-      n_len = clen[(tw << 5) + lane];
-      n_q = qry[(tw << 5) + lane];
-    }
+    load_corridor_rows(cv, tw, lane, H, n_off, n_len);
+    if ((tw << 5) + lane < H) n_q = qry[(tw << 5) + lane];
 
     for (int b = tw; b < nblk; b += NW) {
       const int y = (b << 5) + lane;
@@ -168,12 +170,9 @@ convex_fill_kernel(const FillParams p) {
       const uint32_t q = n_q;
       {
         const int yn = y + 32 * NW;
-        n_off = 0; n_len = 0; n_q = 0x100u;
-        if (yn < H) {
-          n_off = coff[yn];
-          n_len = clen[yn];
-          n_q = qry[yn];
-        }
+        n_q = 0x100u;
+        load_corridor_rows(cv, b + NW, lane, H, n_off, n_len);
+        if (yn < H) n_q = qry[yn];
       }
       int xlo, xhi, nsteps;
       unsigned rlen;
@@ -194,10 +193,10 @@ convex_fill_kernel(const FillParams p) {
         // what the warp filling block b-1 writes: recompute its geometry from its rows
         wlo = 0; whi = 0;
         if (b > 0) {
-          const int yp = y - 32;  // always < H
-          int pxlo, pxhi, pn;
+          int poff, plen, pxlo, pxhi, pn;
           unsigned prl;
-          row_span(coff[yp], clen[yp], ref_len, pxlo, pxhi, prl);
+          load_corridor_rows(cv, b - 1, lane, H, poff, plen);
+          row_span(poff, plen, ref_len, pxlo, pxhi, prl);
           const BlockGeom pg = block_geom(pxlo, pxhi, prl, lane, pn);
           wlo = pg.base - 31;
           whi = wlo + (pg.ngroups << 4);

@@ -55,8 +55,13 @@ __global__ void __launch_bounds__(TB_WARPS_PER_CTA * 32) convex_traceback_kernel
   const int H = d.height;
   const uint8_t* __restrict__ ref = p.seq + d.ref_off;
   const uint8_t* __restrict__ qry = p.seq + d.qry_off;
-  const int32_t* __restrict__ coff = p.c_off + d.row_off;
-  const int32_t* __restrict__ clen = p.c_len + d.row_off;
+  CorridorView cv;
+  cv.off = p.c_off + d.row_off;
+  cv.len = p.c_len + d.row_off;
+  cv.blk_base = p.c_blkbase + d.blk_off;
+  cv.delta = p.c_delta + d.row_off;
+  cv.const_len = d.const_len;
+  cv.packed = d.packed;
   const BlockRec* __restrict__ blocks = p.blocks + d.blk_off;
   int32_t* __restrict__ bc = p.scratch + d.tb_off;
   const int cap = d.tb_cap;        // our strip
@@ -97,12 +102,9 @@ __global__ void __launch_bounds__(TB_WARPS_PER_CTA * 32) convex_traceback_kernel
       br = blocks[blk];
       ngroups = (br.nsteps + 15) >> 4;
       const int yy = (blk << 5) + lane;
-      rw.off = 0; rw.len = 0; rw.q = 0;
-      if (yy < H) {
-        rw.off = coff[yy];
-        rw.len = clen[yy];
-        rw.q = qry[yy];
-      }
+      rw.q = 0;
+      load_corridor_rows(cv, blk, lane, H, rw.off, rw.len);
+      if (yy < H) rw.q = qry[yy];
       // expected step index of the path in row `lane`: two steps per row along the diagonal
       const int s_here = x - br.base + t;
       const int s_exp = s_here - 2 * (t - lane);

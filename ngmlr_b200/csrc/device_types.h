@@ -35,7 +35,9 @@ struct alignas(16) AlnDesc {
   int32_t tb_cap;     // ints of traceback scratch
   int32_t ref_cap;    // reference's binaryCigar capacity: max(200000, qryLen+1)  (:480-485)
   int32_t max_len;    // max corridor row length
-  int32_t pad0, pad1, pad2;
+  int32_t const_len;  // packed corridor: the (constant) row length
+  int32_t packed;     // 1: rows are stored as int8 offset deltas + one int32 base per 32-row block
+  int32_t pad2;
 };
 
 // One 32-row block of a problem: where its direction words live and how steps map to columns.
@@ -72,10 +74,24 @@ struct alignas(16) TraceOut {
   unsigned long long run_off;  // offset of the runs in the compact arena
 };
 
+// Corridor rows of one problem. Raw: CorridorLine::offset / ::length per row (8 B/row). Packed
+// (every builder of the reference produces constant lengths and offsets that advance by < 128 per
+// row): offset[32b] per block + int8 delta per row (1.1 B/row) -- the PCIe-dominant input shrinks 7x.
+struct CorridorView {
+  const int32_t* off;
+  const int32_t* len;
+  const int32_t* blk_base;
+  const int8_t* delta;
+  int const_len;
+  int packed;
+};
+
 struct FillParams {
   const uint8_t* seq;
   const int32_t* c_off;
   const int32_t* c_len;
+  const int32_t* c_blkbase;  // packed corridors: offset of row 32*b, indexed like BlockRec
+  const int8_t* c_delta;     // packed corridors: offset[y] - offset[y-1]
   const AlnDesc* desc;
   const int32_t* order;   // problem indices, largest first
   int n;
@@ -94,6 +110,8 @@ struct TraceParams {
   const uint8_t* seq;
   const int32_t* c_off;
   const int32_t* c_len;
+  const int32_t* c_blkbase;
+  const int8_t* c_delta;
   const AlnDesc* desc;
   int n;
   const BlockRec* blocks;
@@ -139,5 +157,26 @@ struct CsParams {
   int32_t* out_count;
   float* max_hits;
 };
+
+#ifdef __CUDACC__
+// (offset, length) of row 32*blk + lane for the whole warp; rows >= H read as {0, 0}.
+__device__ __forceinline__ void load_corridor_rows(const CorridorView& c, int blk, int lane, int H, int& off,
+                                                   int& len) {
+  const int y = (blk << 5) + lane;
+  if (!c.packed) {
+    off = y < H ? c.off[y] : 0;
+    len = y < H ? c.len[y] : 0;
+    return;
+  }
+  int acc = (lane > 0 && y < H) ? (int)c.delta[y] : 0;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, acc, o);
+    if (lane >= o) acc += v;
+  }
+  off = y < H ? c.blk_base[blk] + acc : 0;
+  len = y < H ? c.const_len : 0;
+}
+#endif
 
 }  // namespace nb
