@@ -11,6 +11,7 @@
 // Argument meaning, buffer ownership and error behaviour follow SURVEY.md section 8(b).
 #include <string.h>
 
+#include <mutex>
 #include <vector>
 
 #include "../../include/ngmlr_b200.h"
@@ -20,12 +21,46 @@ namespace {
 
 ngmlr_b200_scoring g_scoring = {2.0f, -5.0f, -5.0f, -5.0f, -1.0f, 0.15f};
 
+// ngmlr creates and destroys aligner objects freely (e.g. a fresh StrippedSW per inversion check,
+// src/AlignmentBuffer.cpp:1217). A context owns a stream, events and grown device/pinned arenas, so
+// retired contexts are parked here and handed to the next object with the same device and scoring.
+struct ParkedContext {
+  int gpu_id;
+  ngmlr_b200_scoring scoring;
+  ngmlr_b200_ctx* ctx;
+};
+std::mutex g_pool_mutex;
+std::vector<ParkedContext> g_pool;
+
+bool same_scoring(const ngmlr_b200_scoring& a, const ngmlr_b200_scoring& b) {
+  return memcmp(&a, &b, sizeof(a)) == 0;
+}
+
 class B200Alignment : public IAlignment {
  public:
-  explicit B200Alignment(int gpu_id) {
-    if (ngmlr_b200_create(gpu_id, &g_scoring, &ctx_) != 0) ctx_ = nullptr;
+  explicit B200Alignment(int gpu_id) : gpu_id_(gpu_id), scoring_(g_scoring) {
+    {
+      std::lock_guard<std::mutex> lock(g_pool_mutex);
+      for (size_t i = 0; i < g_pool.size(); ++i) {
+        if (g_pool[i].gpu_id == gpu_id && same_scoring(g_pool[i].scoring, scoring_)) {
+          ctx_ = g_pool[i].ctx;
+          g_pool.erase(g_pool.begin() + i);
+          return;
+        }
+      }
+    }
+    if (ngmlr_b200_create(gpu_id, &scoring_, &ctx_) != 0) ctx_ = nullptr;
   }
-  ~B200Alignment() override { ngmlr_b200_destroy(ctx_); }
+  ~B200Alignment() override {
+    if (!ctx_) return;
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (g_pool.size() < 256) {
+      ParkedContext p = {gpu_id_, scoring_, ctx_};
+      g_pool.push_back(p);
+    } else {
+      ngmlr_b200_destroy(ctx_);
+    }
+  }
   bool ok() const { return ctx_ != nullptr; }
 
   int GetScoreBatchSize() const override { return 1024; }
@@ -184,6 +219,8 @@ class B200Alignment : public IAlignment {
     if (threw && n == 1) throw 1;  // caller wraps SingleAlign in try/catch(...) -> unmapped
   }
 
+  int gpu_id_ = 0;
+  ngmlr_b200_scoring scoring_;
   ngmlr_b200_ctx* ctx_ = nullptr;
   std::vector<int32_t> ref_len_, qry_len_, off_, len_, qs_, qe_;
   std::vector<int64_t> row_start_;
