@@ -190,6 +190,16 @@ int ngmlr_b200_cs_fetch(ngmlr_b200_ctx* ctx, int64_t* cand_start, const float** 
                         const uint64_t** locs, const uint8_t** reverse, const float** sw_scores,
                         float* max_hits);
 
+/* Candidate selection once a (sub-)read's candidates are scored. Replaces ScoreBuffer::topNSE and
+ * ScoreBuffer::computeMQ (src/ScoreBuffer.cpp:170-192, 33-45). Host code (the reference's is too): for
+ * (sub-)read i the candidates [cand_start[i], cand_start[i+1]) are ordered by descending sw_scores with
+ * the reference's std::sort call (same order among equal scores); order[] receives the candidate
+ * indices in that order, kept[i] = how many exceed 0.75 x the best (MappedRead::Calculated: the
+ * candidates that go on to alignment), mq[i] = ceil(60 * (s0 - s1) / s0), 60 with fewer than two
+ * candidates (MappedRead::mappingQlty). No context: nothing runs on the device. Returns n or -1. */
+int ngmlr_b200_select_candidates(int n, const int64_t* cand_start, const float* sw_scores, int32_t* order,
+                                 int32_t* kept, int32_t* mq);
+
 #ifdef __cplusplus
 }
 #endif

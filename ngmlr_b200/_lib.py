@@ -43,7 +43,7 @@ C_API_SYMBOLS = (
     "ngmlr_b200_convex_fetch", "ngmlr_b200_convex_stats", "ngmlr_b200_convex_debug_directions",
     "ngmlr_b200_sw_score_batch", "ngmlr_b200_cs_set_index", "ngmlr_b200_cs_search_batch",
     "ngmlr_b200_cs_set_reference", "ngmlr_b200_cs_score_batch", "ngmlr_b200_cs_upload",
-    "ngmlr_b200_cs_run", "ngmlr_b200_cs_fetch",
+    "ngmlr_b200_cs_run", "ngmlr_b200_cs_fetch", "ngmlr_b200_select_candidates",
 )
 PLUGIN_SYMBOLS = ("CreateAlignment", "DeleteAlignment", "SetAlignmentScoring")
 
@@ -97,6 +97,7 @@ def load():
     lib.ngmlr_b200_cs_fetch.argtypes = [vp, i64p, C.POINTER(C.POINTER(C.c_float)),
                                         C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.POINTER(C.c_uint8)),
                                         C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_float)]
+    lib.ngmlr_b200_select_candidates.argtypes = [C.c_int, i64p, C.POINTER(C.c_float), i32p, i32p, i32p]
     lib.ngmlr_b200_sw_last_kernel_ms.argtypes = [vp]
     lib.ngmlr_b200_sw_last_kernel_ms.restype = C.c_float
     _lib = lib

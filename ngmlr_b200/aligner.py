@@ -111,6 +111,29 @@ def split_read(seq, part_length=256):
     return [seq[i * part_length:(i + 1) * part_length] for i in range(n)]
 
 
+def select_candidates(cand_start, sw_scores):
+    """ScoreBuffer::topNSE + computeMQ (src/ScoreBuffer.cpp:170-192, 33-45) for every (sub-)read of a
+    scored batch (the arrays cs_score/cs_fetch return). Returns (order, kept, mq): `order` lists the
+    candidate indices of each (sub-)read by descending score in the reference's std::sort order,
+    kept[i] candidates of (sub-)read i go on to alignment, mq[i] is its mapping quality."""
+    lib = _lib.load()
+    cand_start = np.ascontiguousarray(cand_start, dtype=np.int64)
+    sw_scores = np.ascontiguousarray(sw_scores, dtype=np.float32)
+    n = int(cand_start.size) - 1
+    if n < 0 or (n >= 0 and int(cand_start[-1]) != sw_scores.size):
+        raise ValueError("cand_start must have n+1 entries ending at len(sw_scores)")
+    order = np.zeros(max(sw_scores.size, 1), dtype=np.int32)
+    kept = np.zeros(max(n, 1), dtype=np.int32)
+    mq = np.zeros(max(n, 1), dtype=np.int32)
+    rc = lib.ngmlr_b200_select_candidates(
+        n, cand_start.ctypes.data_as(C.POINTER(C.c_int64)), sw_scores.ctypes.data_as(C.POINTER(C.c_float)),
+        order.ctypes.data_as(C.POINTER(C.c_int32)), kept.ctypes.data_as(C.POINTER(C.c_int32)),
+        mq.ctypes.data_as(C.POINTER(C.c_int32)))
+    if rc != n:
+        raise RuntimeError("ngmlr_b200_select_candidates failed")
+    return order[:sw_scores.size], kept[:n], mq[:n]
+
+
 class B200Aligner:
     def __init__(self, gpu_id=0, scoring=DEFAULT_SCORING, stream=None):
         self.lib = _lib.load()

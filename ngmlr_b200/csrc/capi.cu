@@ -5,6 +5,7 @@
 // launches fill -> traceback -> compact, and turns the binary CIGARs into the reference's `Align`
 // fields. There is no CPU compute path: every entry point needs a CUDA device.
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -1393,6 +1394,48 @@ int ngmlr_b200_cs_fetch(ngmlr_b200_ctx* ctx, int64_t* cand_start, const float** 
   *locs = cs->p_loc.p;
   *reverse = cs->p_rev.p;
   *sw_scores = cs->p_sw.p;
+  return n;
+}
+
+// Host glue after scoring: ScoreBuffer::topNSE + computeMQ (src/ScoreBuffer.cpp:170-192, 33-45).
+// Candidates of one (sub-)read are ordered with std::sort and the reference's comparator
+// (a.Score.f > b.Score.f, :25-27) -- the same libstdc++ routine, because the order of tied scores is
+// part of the behaviour --, then those scoring above 0.75 x best are kept.
+int ngmlr_b200_select_candidates(int n, const int64_t* cand_start, const float* sw_scores, int32_t* order,
+                                 int32_t* kept, int32_t* mq) {
+  if (n < 0 || (n > 0 && (!cand_start || !order || !kept || !mq))) return -1;
+  struct Item {
+    float score;
+    int32_t idx;
+  };
+  parallel_for(n, 512, [&](int i) {
+    const int64_t b = cand_start[i];
+    const int m = (int)(cand_start[i + 1] - b);
+    Item small[32];
+    std::vector<Item> big;
+    Item* it = small;
+    if (m > 32) {
+      big.resize((size_t)m);
+      it = big.data();
+    }
+    for (int j = 0; j < m; ++j) {
+      it[j].score = sw_scores[b + j];
+      it[j].idx = (int32_t)(b + j);
+    }
+    std::sort(it, it + m, [](Item x, Item y) { return x.score > y.score; });
+    int keep = m;
+    if (m > 1) {
+      const float min_score = it[0].score * 0.75f;
+      int j = 1;
+      while (j < m && it[j].score > min_score) ++j;
+      keep = j;
+    }
+    int q = 60;  // MAX_MQ (src/ScoreBuffer.cpp:16)
+    if (m > 1) q = (int)ceil(60.0f * (it[0].score - it[1].score) / it[0].score);
+    for (int j = 0; j < m; ++j) order[b + j] = it[j].idx;
+    kept[i] = keep;
+    mq[i] = q;
+  });
   return n;
 }
 

@@ -82,6 +82,10 @@ const uint32_t* or_cs_pos(const struct or_cs* h);
 int or_cs_search(const struct or_cs* h, const char* seq, int len, float sensitivity, float min_kmer_hits,
                  float* scores, uint64_t* locs, int* reverse, int cap, float* max_hits);
 
+/* ---- candidate selection after scoring (ScoreBuffer::topNSE / computeMQ): oracle/score_oracle.c - */
+int or_score_mq(float best, float second);
+int or_score_select(const float* scores, int n, int32_t* order, int* mq);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,7 @@
 #include "NGM.h"
 #include "PrefixTable.h"
 #include "SequenceProvider.h"
+#include "ScoreBuffer.h"
 #include "StrippedSW.h"
 #undef private
 #undef protected
@@ -165,6 +166,34 @@ float ref_full_ssw_score(void* h, const char* ref, const char* qry) {
 
 int ref_cs_search_p(void* probe, const char* seq, int len, int table_bits, float* scores,
                     unsigned long long* locs, int* reverse, int cap, float* max_hits);
+
+// ScoreBuffer::topNSE (src/ScoreBuffer.cpp:170-192) on one sub-read's scored candidates. tags[] rides
+// in Location.m_Location so that the caller can see the permutation std::sort produced.
+int ref_score_select(float* scores, unsigned long long* tags, int n, int* mq) {
+  if (!_config) {
+    _config = new IConfig();
+    _Log::Init(0, 0);
+    _log = &Log;
+  }
+  static ScoreBuffer* sb = new ScoreBuffer(new StrippedSW(), 0);
+  MappedRead* read = new MappedRead(0, 16);
+  LocationScore* tmp = new LocationScore[n > 0 ? n : 1];
+  for (int i = 0; i < n; ++i) {
+    tmp[i].Score.f = scores[i];
+    tmp[i].Location.m_Location = tags[i];
+  }
+  read->AllocScores(tmp, n);
+  delete[] tmp;
+  sb->topNSE(read);
+  for (int i = 0; i < n; ++i) {
+    scores[i] = read->Scores[i].Score.f;
+    tags[i] = read->Scores[i].Location.m_Location;
+  }
+  *mq = read->mappingQlty;
+  int kept = read->Calculated;
+  delete read;
+  return kept;
+}
 
 // One (sub-)read through the reference's vote. Outputs in the reference's emission order.
 int ref_cs_search(const char* seq, int len, int table_bits, float* scores, unsigned long long* locs,

@@ -5,7 +5,7 @@ by oracle/Makefile from /root/reference). Run in the build container only:
 
 The vectors pin: (a) ConvexAlignFast::SingleAlign outputs (return value, score bits, CIGAR, MD,
 NM, positions, nmPerPosition checksum, direction-matrix checksum, best cell) for seeded problems
-under three scorings, (b) StrippedSW scores. Inputs are regenerated from the seeds by
+under three scorings, (b) StrippedSW scores, (c) ScoreBuffer::topNSE candidate order / kept / MQ. Inputs are regenerated from the seeds by
 tests/cases.py, so only outputs are stored (plus an input checksum to detect generator drift)."""
 import hashlib
 import json
@@ -19,7 +19,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 import numpy as np  # noqa: E402
 
 import cases  # noqa: E402
-from oracle_lib import DEFAULT_SCORING, Reference, build_ref  # noqa: E402
+from oracle_lib import DEFAULT_SCORING, CsReference, Reference, build_ref, score_select_cases  # noqa: E402
 
 
 def digest(*arrays):
@@ -76,6 +76,14 @@ def main():
     ref.close()
     with open(os.path.join(HERE, "sw_golden.json"), "w") as f:
         json.dump(sw, f)
+    # (c) ScoreBuffer::topNSE / computeMQ: order produced by the reference's std::sort, kept count, MQ
+    sel = []
+    for sc in score_select_cases(77, 400):
+        order, kept, mq = CsReference.score_select(sc)
+        sel.append({"n": int(sc.size), "input_sha": digest(sc), "order_sha": digest(order), "kept": kept, "mq": mq,
+                    "order": [int(v) for v in order] if sc.size <= 24 else None})
+    with open(os.path.join(HERE, "score_select_golden.json"), "w") as f:
+        json.dump(sel, f)
     print("wrote golden vectors:", {k: len(v["records"]) for k, v in out.items()}, len(sw["scores"]))
 
 

@@ -95,9 +95,40 @@ class Oracle:
         offsets, lengths = _i32(offsets), _i32(lengths)
         return int(self.lib.or_convex_cells(ref_len, len(offsets), _p(offsets), _p(lengths)))
 
+    def score_select(self, scores):
+        """ScoreBuffer::topNSE restatement -> (order, kept, mq)."""
+        s = np.ascontiguousarray(scores, dtype=np.float32)
+        order = np.zeros(max(s.size, 1), dtype=np.int32)
+        mq = C.c_int()
+        kept = self.lib.or_score_select(s.ctypes.data_as(C.c_void_p), int(s.size),
+                                        order.ctypes.data_as(C.c_void_p), C.byref(mq))
+        return order[:s.size].copy(), int(kept), mq.value
+
     def ssw_score(self, ref, qry, striped=False):
         f = self.lib.or_ssw_score_striped if striped else self.lib.or_ssw_score
         return float(f(ref, qry))
+
+
+def score_select_cases(seed, count):
+    """Seeded score lists for ScoreBuffer::topNSE parity: small integer scores (ties everywhere),
+    lengths around the 16-element insertion-sort threshold of std::sort and beyond."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for t in range(count):
+        n = int(rng.choice([0, 1, 2, 3, 5, 16, 17, 18, 33, 64, 65, 100, 300])) if t % 3 else int(rng.integers(0, 40))
+        kind = t % 5
+        if kind == 0:
+            s = rng.integers(0, 8, n)
+        elif kind == 1:
+            s = rng.integers(100, 257, n)
+        elif kind == 2:
+            s = np.sort(rng.integers(0, 50, n))
+        elif kind == 3:
+            s = np.full(n, 7)
+        else:
+            s = np.sort(rng.integers(0, 300, n))[::-1]
+        out.append(np.ascontiguousarray(s, dtype=np.float32))
+    return out
 
 
 class Reference:
@@ -275,6 +306,18 @@ class CsReference:
         pos = np.ctypeslib.as_array(rt, shape=(rl.value + 1,))[:rl.value].copy()
         assert uo.value == 0 and uc.value == 1
         return tab, rci, pos
+
+    @classmethod
+    def score_select(cls, scores):
+        """The unmodified ScoreBuffer::topNSE on one (sub-)read's scores -> (order, kept, mq).
+        Needs no reference genome (usable before/without __init__)."""
+        lib = C.CDLL(cls.PATH)
+        s = np.ascontiguousarray(scores, dtype=np.float32).copy()
+        tags = np.arange(s.size, dtype=np.uint64)
+        mq = C.c_int()
+        kept = lib.ref_score_select(s.ctypes.data_as(C.c_void_p), tags.ctypes.data_as(C.c_void_p), int(s.size),
+                                    C.byref(mq))
+        return tags.astype(np.int32), int(kept), mq.value
 
     def decode(self, position, buffer_len=308):
         buf = C.create_string_buffer(buffer_len + 4)

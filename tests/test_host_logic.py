@@ -46,3 +46,24 @@ def test_synthetic_reads_have_requested_error_profile():
     # more insertions than deletions -> read longer than the reference window
     assert 20000 * 1.02 < read.size < 20000 * 1.12
     assert starts[-1] == read.size and (np.diff(starts) >= 0).all()
+
+
+def test_select_candidates_matches_oracle_and_golden(oracle):
+    """ngmlr_b200_select_candidates (host glue, no GPU) == ScoreBuffer::topNSE/computeMQ."""
+    import golden_util as gu
+    from ngmlr_b200 import select_candidates
+    from oracle_lib import score_select_cases
+    gold = gu.load("score_select_golden.json")
+    scs = score_select_cases(77, 400)
+    start = np.zeros(len(scs) + 1, dtype=np.int64)
+    start[1:] = np.cumsum([s.size for s in scs])
+    order, kept, mq = select_candidates(start, np.concatenate(scs))
+    for i, (sc, g) in enumerate(zip(scs, gold)):
+        local = order[start[i]:start[i + 1]] - start[i]
+        assert (int(kept[i]), int(mq[i])) == (g["kept"], g["mq"])
+        assert gu.digest(local.astype(np.int32)) == g["order_sha"]
+        o = oracle.score_select(sc)
+        assert np.array_equal(local, o[0]) and (int(kept[i]), int(mq[i])) == o[1:]
+    # empty batch
+    o2, k2, m2 = select_candidates(np.zeros(1, np.int64), np.zeros(0, np.float32))
+    assert o2.size == 0 and k2.size == 0 and m2.size == 0

@@ -86,3 +86,32 @@ def test_oracle_vs_compiled_reference(oracle, sc, seed):
             assert ref.ssw_score(r, q) == oracle.ssw_score(r, q) == oracle.ssw_score(r, q, striped=True)
     finally:
         ref.close()
+
+
+def test_oracle_score_select_matches_golden(oracle):
+    """ScoreBuffer::topNSE / computeMQ restatement (incl. libstdc++'s std::sort order among equal scores)
+    against vectors recorded from the unmodified reference."""
+    from oracle_lib import score_select_cases
+    gold = gu.load("score_select_golden.json")
+    scs = score_select_cases(77, 400)
+    assert len(gold) == len(scs)
+    for sc, g in zip(scs, gold):
+        assert gu.digest(sc) == g["input_sha"], "generator drifted"
+        order, kept, mq = oracle.score_select(sc)
+        assert (kept, mq) == (g["kept"], g["mq"])
+        assert gu.digest(order) == g["order_sha"]
+        if g["order"] is not None:
+            assert list(order) == g["order"]
+
+
+@pytest.mark.skipif(not Reference.available(), reason="compiled reference absent (GPU box / no /root/reference)")
+def test_oracle_score_select_vs_compiled_reference(oracle):
+    from oracle_lib import CsReference, score_select_cases
+    if not CsReference.available():
+        pytest.skip("libngmlr_full.so absent")
+    for sc in score_select_cases(5, 1500):
+        if sc.size == 0:
+            continue
+        o = oracle.score_select(sc)
+        r = CsReference.score_select(sc)
+        assert o[1:] == r[1:] and np.array_equal(o[0], r[0])
