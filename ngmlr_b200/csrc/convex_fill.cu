@@ -52,6 +52,9 @@ namespace {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int STRIP_PAD = 32;    // strip index = column + STRIP_PAD (lane 31 trails lane 0 by 31)
 constexpr unsigned X_BIAS = 1u << 20;
+#ifndef FILL_TEAM_CHUNK
+#define FILL_TEAM_CHUNK 16
+#endif
 
 __device__ __forceinline__ uint4 ld_strip(const uint4* p) { return __ldcg(p); }
 __device__ __forceinline__ void st_strip(uint4* p, uint4 v) { __stcg(p, v); }
@@ -97,7 +100,7 @@ struct TeamBest {
 template <bool RAW, int NW>
 __global__ void __launch_bounds__(FILL_WARPS_PER_CTA * 32, FILL_CTAS_PER_SM)
 convex_fill_kernel(const FillParams p) {
-  constexpr int CHUNK = NW == 1 ? 64 : 16;  // steps staged through shared memory at a time
+  constexpr int CHUNK = NW == 1 ? 64 : FILL_TEAM_CHUNK;  // steps staged through shared memory at a time
   constexpr int GPC = CHUNK / 16;           // 16-step groups per chunk
   static_assert(NW == 1 || NW == FILL_WARPS_PER_CTA, "a team is one warp or the whole CTA");
   __shared__ uint4 s_in[FILL_WARPS_PER_CTA][CHUNK + 1];  // +1: lane 31 reads one record ahead

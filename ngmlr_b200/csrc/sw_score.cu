@@ -11,11 +11,14 @@
 //   * H = max(diag + s, E, F) with signed-saturating 16-bit adds; E/F updates use unsigned
 //     saturating subtraction (clamp at 0); result = max H as uint16 -> float.
 //
-// Mapping: one warp per pair. Lane t owns SW_ROWS consecutive query rows; the warp sweeps the
-// reference columns as a wavefront (lane t is one column behind lane t-1), passing the H and F of
-// its last row down with __shfl_up. Queries longer than 32*SW_ROWS rows are processed in several
-// passes; the bottom row of a pass is carried to the next through a per-warp strip in global
-// memory. 32-bit integer lanes emulate the int16 saturation (values never exceed 32767).
+// Mapping: one warp per pair; the warp sweeps the reference columns as a wavefront (lane t is one
+// column behind lane t-1). The hot case (256-bp sub-read against a ~306-bp window) is provably
+// ungapped and runs in sw_ungapped() below: packed 16-bit rows, substitution scores by PRMT table
+// lookup, ~2 instructions per cell. Everything else takes the general affine path: lane t owns
+// SW_ROWS consecutive query rows and passes the H and F of its last row down with __shfl_up;
+// queries longer than 32*SW_ROWS rows are processed in several passes, the bottom row of a pass is
+// carried to the next through a per-warp strip in global memory; 32-bit integer lanes emulate the
+// int16 saturation (values never exceed 32767).
 #include <cuda_runtime.h>
 
 #include "device_types.h"
@@ -28,13 +31,22 @@ namespace {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int SW_ROWS = 9;  // 32 * 9 = 288 >= 257 = 256-bp sub-read + NUL: one pass for the hot case
 constexpr int SW_GAP = 255;
-constexpr int SW_PAIRS = 5;  // packed path: 5 registers x 2 rows per lane = 320 rows
+constexpr int SW_COLS = 384;  // widest window of the ungapped hot path (ScoreBuffer windows: 307)
 constexpr int SW_WARPS_PER_CTA = 4;
 
 __device__ __forceinline__ int nt_code(uint32_t c) {
-  // nt_table, src/StrippedSW.cpp:111-116
-  c &= 0xdfu;  // fold case
-  return c == 'A' ? 0 : (c == 'C' ? 1 : (c == 'G' ? 2 : (c == 'T' ? 3 : 4)));
+  // nt_table, src/StrippedSW.cpp:111-116 (A/a 0, C/c 1, G/g 2, T/t 3, everything else 4), branch-free:
+  // (c >> 1) & 3 orders the four letters A C T G; k ^ (k >> 1) swaps the last two
+  const uint32_t u = (c & 0xdfu) - 0x41u;  // A 0, C 2, G 6, T 19
+  const uint32_t k = (c >> 1) & 3u;
+  const bool acgt = u < 20u && ((0x80045u >> u) & 1u);
+  return acgt ? (int)(k ^ (k >> 1)) : 4;
+}
+
+// nt_code(cpl(c)) with cpl() of src/MappedRead.cpp:35-46: only the UPPER-case letters are complemented
+__device__ __forceinline__ int nt_code_cpl(uint32_t c) {
+  const int code = nt_code(c);
+  return (code < 4 && !(c & 0x20u)) ? 3 - code : code;
 }
 
 // DecodeRefSequence(sequence, 0, position, bufferLength) as a random-access function
@@ -66,12 +78,84 @@ struct GenomeWindow {
     const uint32_t byte = enc[b >> 1];
     const uint32_t c4 = (b & 1ull) ? (byte & 0xFu) : (byte >> 4);
     // enc4 A0 T1 G2 C3 N4 -> nt_table A0 C1 G2 T3 N4
-    return c4 == 0 ? 0 : (c4 == 1 ? 3 : (c4 == 2 ? 2 : (c4 == 3 ? 1 : 4)));
+    return (int)((0x41230u >> (4u * min(c4, 4u))) & 0xfu);
   }
 };
 
 __device__ __forceinline__ uint32_t cpl(uint32_t c) {  // src/MappedRead.cpp:35-46
   return c == 'A' ? 'T' : (c == 'T' ? 'A' : (c == 'C' ? 'G' : (c == 'G' ? 'C' : c)));
+}
+
+// Ungapped hot path. One warp per pair; lane t owns 2*PAIRS consecutive query rows, two rows per
+// register in 16-bit halves: register k holds rows (r0 + k, r0 + k + PAIRS), so the H values of
+// "the row above, one column back" of register k are simply the old register k-1 (no per-register
+// shuffling of halves); only register 0 needs the neighbour lane's last row (one SHFL per step).
+// The warp sweeps the columns as a wavefront (lane t one column behind lane t-1).
+//
+// Substitution scores by table lookup: for column base r the word A_r has byte q = 0x01 if q == r
+// else 0xff (q = 0..3), and is 0 for N / padding columns. PRMT with a per-register selector built
+// once from the two query codes (nibbles: q_lo, q_lo|8, q_hi, q_hi|8 -- |8 replicates the sign of
+// the selected byte) turns A_r into the packed (+1 | -1 | 0, +1 | -1 | 0) pair; query code 4 (N,
+// NUL, rows beyond the query) selects a zero byte. The A words of the window are decoded once per
+// pair into shared memory with 32 zero words of padding either side, so that lanes which have not
+// started or are already finished compute on zeros (H = relu(H + 0) never raises the maximum) and the
+// step loop needs no activity test. The terminating NULs (last query row, last column) score 0
+// against everything and are not evaluated. Per step and lane: 1 SHFL, 1 LDS, PAIRS x (PRMT,
+// VIADDMNMX.S16x2.RELU, VIMNMX.S16x2) + 3.
+template <int PAIRS, bool GATHER>
+__device__ __forceinline__ float sw_ungapped(const GenomeWindow& gw, const uint8_t* __restrict__ ref,
+                                             const uint8_t* __restrict__ qry, int qrows, int cols, bool q_rev,
+                                             uint32_t* tab, int lane, uint32_t zero) {
+  __syncwarp();
+  for (int i = lane; i < cols + 64; i += 32) {
+    const int c = i - 32;
+    uint32_t a = 0u;
+    if (c >= 0 && c < cols) {
+      const int rc = GATHER ? gw.code(c) : nt_code(ref[c]);
+      if (rc != 4) a = 0xffffffffu ^ (0xfeu << (8 * rc));
+    }
+    tab[i] = a;
+  }
+  const int row0 = lane * 2 * PAIRS;
+  uint32_t sel[PAIRS], H[PAIRS];
+#pragma unroll
+  for (int k = 0; k < PAIRS; ++k) {
+    uint32_t codes[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int row = row0 + k + h * PAIRS;
+      int cq = 4;
+      if (row < qrows) cq = q_rev ? nt_code_cpl(qry[qrows - 1 - row]) : nt_code(qry[row]);
+      codes[h] = (uint32_t)cq;
+    }
+    sel[k] = codes[0] | ((codes[0] | 8u) << 4) | (codes[1] << 8) | ((codes[1] | 8u) << 12);
+    H[k] = 0u;
+  }
+  __syncwarp();
+  uint32_t best2 = 0u, diag_top = 0u;
+  const uint32_t not_lane0 = lane ? 0xffffffffu : 0u;
+  const uint32_t* tp = tab + 32 - lane;
+  const int nsteps = cols + 31;
+#pragma unroll 4
+  for (int s = 0; s < nsteps; ++s) {
+    const uint32_t up = __shfl_up_sync(FULL, H[PAIRS - 1], 1) & not_lane0;
+    const uint32_t a = tp[s];
+    // (row r0-1 from the lane above, row r0+PAIRS-1 = low half of the last register), column c-1
+    const uint32_t d0 = __byte_perm(diag_top, H[PAIRS - 1], 0x5432);
+#pragma unroll
+    for (int k = PAIRS - 1; k >= 0; --k) {
+      uint32_t sub;
+      asm("prmt.b32 %0, %1, %2, %3;" : "=r"(sub) : "r"(a), "r"(0u), "r"(sel[k]));
+      const uint32_t h = __viaddmax_s16x2_relu(k ? H[k - 1] : d0, sub, zero);
+      H[k] = h;
+      best2 = __vmaxs2(best2, h);
+    }
+    diag_top = up;
+  }
+  int best = max((int)(best2 & 0xffffu), (int)(best2 >> 16));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(FULL, best, o));
+  return (float)(best & 0xffff);
 }
 
 template <bool GATHER>
@@ -80,6 +164,10 @@ __global__ void __launch_bounds__(SW_WARPS_PER_CTA * 32) sw_score_kernel(const S
   const int warp_global = blockIdx.x * SW_WARPS_PER_CTA + (threadIdx.x >> 5);
   const int nwarps = gridDim.x * SW_WARPS_PER_CTA;
   int2* strip = reinterpret_cast<int2*>(p.scratch) + (size_t)warp_global * p.scratch_stride;
+  __shared__ uint32_t s_tab[SW_WARPS_PER_CTA][SW_COLS + 64];
+  // 0 the compiler cannot see through: keeps the RELU floor of the packed ops in one register
+  // (a literal 0 is re-materialised with a PRMT per use)
+  const uint32_t zero = (uint32_t)p.n >> 31;
 
   for (int pair = warp_global; pair < p.n; pair += nwarps) {
     GenomeWindow gw;
@@ -97,60 +185,15 @@ __global__ void __launch_bounds__(SW_WARPS_PER_CTA * 32) sw_score_kernel(const S
     const uint8_t* __restrict__ ref = GATHER ? p.seq : p.seq + p.ref_off[pair];
     const uint8_t* __restrict__ qry = p.seq + p.qry_off[pair];
     int best = 0;
-    // ---- hot case: at most 320 query characters (256-bp sub-read + NUL) ----
+    // ---- hot case: at most 320 query characters (256-bp sub-read + NUL), window of <= 384 columns ----
     // A gap costs 255 per base, so a gapped path beats its best ungapped piece only if it gains
     // more than 255 before AND after the gap: impossible with fewer than 512 query characters.
     // Then E and F never influence the maximum and the recurrence is H = max(0, diag + s).
-    // Two rows per register (16-bit halves) with Blackwell's packed integer ops:
-    // VIMNMX.U16x2 (character mismatch), VIADDMNMX.S16x2.RELU (max(diag + s, 0)), VIMNMX.S16x2.
-    if (qlen <= 32 * 2 * SW_PAIRS) {
-      const int row0 = lane * 2 * SW_PAIRS;
-      uint32_t qc2[SW_PAIRS], vq2[SW_PAIRS], H2[SW_PAIRS];
-#pragma unroll
-      for (int pq = 0; pq < SW_PAIRS; ++pq) {
-        uint32_t codes[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int row = row0 + 2 * pq + h;
-          int cq = 4;  // NUL / beyond the query: scores 0 against everything
-          if (row < qlen - 1) cq = q_rev ? nt_code(cpl(qry[qlen - 2 - row])) : nt_code(qry[row]);
-          codes[h] = (uint32_t)cq;
-        }
-        qc2[pq] = codes[0] | (codes[1] << 16);
-        vq2[pq] = (codes[0] == 4u ? 0u : 0xffffu) | (codes[1] == 4u ? 0u : 0xffff0000u);
-        H2[pq] = 0u;
-      }
-      uint32_t best2 = 0u, diag_top = 0u;
-      const int nsteps = rlen + 31;
-      for (int s = 0; s < nsteps; ++s) {
-        const int c = s - lane;
-        uint32_t up2 = __shfl_up_sync(FULL, H2[SW_PAIRS - 1], 1);
-        if (lane == 0) up2 = 0u;
-        if (c >= 0 && c < rlen) {
-          const uint32_t rc = (uint32_t)(GATHER ? gw.code(c) : nt_code(ref[c]));
-          const uint32_t rc2 = rc * 0x00010001u;
-          const bool col_n = rc == 4u;
-          uint32_t prev = diag_top;  // H of the row above pair 0 at column c-1 sits in its high half
-#pragma unroll
-          for (int pq = 0; pq < SW_PAIRS; ++pq) {
-            const uint32_t old = H2[pq];
-            const uint32_t diag = __byte_perm(prev, old, 0x5432);     // (H[2p-1], H[2p]) of column c-1
-            const uint32_t ne = __vminu2(qc2[pq] ^ rc2, 0x00010001u);  // 1 per half where the bases differ
-            const uint32_t mism = ne * 0xffffu;                        // 0xffff per differing half
-            const uint32_t valid = col_n ? 0u : vq2[pq];
-            const uint32_t sub = (mism | 0x00010001u) & valid;         // +1 / -1, 0 against N
-            const uint32_t h = __viaddmax_s16x2_relu(diag, sub, 0u);
-            H2[pq] = h;
-            best2 = __vmaxs2(best2, h);
-            prev = old;
-          }
-          diag_top = up2;
-        }
-      }
-      best = max((int)(best2 & 0xffffu), (int)(best2 >> 16));
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(FULL, best, o));
-      if (lane == 0) p.out[pair] = (float)(best & 0xffff);
+    if (qlen - 1 <= 64 * 5 && rlen - 1 <= SW_COLS) {
+      const float r = (qlen - 1 <= 64 * 4)
+                          ? sw_ungapped<4, GATHER>(gw, ref, qry, qlen - 1, rlen - 1, q_rev, s_tab[threadIdx.x >> 5], lane, zero)
+                          : sw_ungapped<5, GATHER>(gw, ref, qry, qlen - 1, rlen - 1, q_rev, s_tab[threadIdx.x >> 5], lane, zero);
+      if (lane == 0) p.out[pair] = r;
       continue;
     }
     const int rows_per_pass = 32 * SW_ROWS;
@@ -165,7 +208,7 @@ __global__ void __launch_bounds__(SW_WARPS_PER_CTA * 32) sw_score_kernel(const S
         // the NUL at qlen-1 is part of the query and maps to 4; rows >= qlen do not exist (-1)
         if (q_rev) {  // RevSeq[j] = cpl(Seq[len - 1 - j]), then the NUL
           const int L = qlen - 1;
-          qc[r] = row < L ? nt_code(cpl(qry[L - 1 - row])) : (row < qlen ? 4 : -1);
+          qc[r] = row < L ? nt_code_cpl(qry[L - 1 - row]) : (row < qlen ? 4 : -1);
         } else {
           qc[r] = row < qlen ? nt_code(qry[row]) : -1;
         }
