@@ -9,9 +9,10 @@ reference, ~8 kb reads, 15 % errors ins:del:sub 9:4:2, anchored corridor) sharde
 ranks (weak scaling: every rank aligns its own `--reads` reads per step; no per-step collective;
 one NCCL broadcast of the reference at start-up).
 
-  value      whole-job Gbp/s with the batch already resident in HBM (K x convex_run, CUDA events)
-  e2e        same metric through the public call (B200Aligner.BatchAlign -> C ABI) from HOST
-             buffers: pack + H2D + kernels + D2H + CIGAR/MD text every step
+  value      whole-job Gbp/s with the batch already resident in HBM (K x kernels only, CUDA events);
+             the batch is dealt read by read to `--contexts` aligner contexts that run concurrently
+  e2e        same metric through the public calls (B200Aligner -> C ABI) from HOST buffers:
+             pack + H2D + kernels + D2H + CIGAR/MD text every step, same contexts
   roofline   fill kernel: algorithmic bytes per launch / mean launch time vs measured HBM peak
   cpu_baseline  the reference's own CPU ConvexAlignFast (oracle/_ref) or the oracle port, timed on
              this box's host cores on a bounded sample of the same workload
@@ -212,7 +213,7 @@ def main():
     ap.add_argument("--reads", type=int, default=8192, help="reads (alignment problems) per step per GPU")
     ap.add_argument("--genome-mb", type=float, default=50.0)
     ap.add_argument("--dp-only", action="store_true", help="time stage 4 (convex alignment) alone")
-    ap.add_argument("--contexts", type=int, default=2, help="aligner contexts (host threads/streams) per GPU")
+    ap.add_argument("--contexts", type=int, default=4, help="aligner contexts (host threads/streams) per GPU")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
@@ -315,9 +316,10 @@ def main():
     bases = batch.read_bases
     subreads = PackedReads([s for p in pool for s in split_read(p.qry)])   # ReadProvider::splitRead
     # S independent aligner contexts (own stream, own device arenas), driven by S host threads --
-    # the reference's model of one aligner object per worker thread. Batches of different contexts
-    # overlap on the GPU, which hides the tail of each fill launch and the traceback behind the
-    # other context's fill, and (end to end) packing/H2D/D2H/text behind kernels.
+    # the reference's model of one aligner object per worker thread. The step's batch is dealt to the
+    # contexts read by read (context j aligns reads j, j+S, ...); their work overlaps on the GPU, which
+    # hides the tail of each fill launch and the traceback behind another context's fill, and (end to
+    # end) packing/H2D/D2H/text of one slice behind the kernels of the others.
     S = max(1, args.contexts)
     streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
     als = [B200Aligner(local_rank, stream=st_.cuda_stream) for st_ in streams]
@@ -325,31 +327,30 @@ def main():
     for a_ in als:
         a_.set_index(kidx)
         a_.set_reference(enc_ref)
+    slices = [pool[j::S] for j in range(S)]
+    sl_batch = [PackedBatch.from_problems(sl) for sl in slices]
+    sl_reads = [PackedReads([s for p in sl for s in split_read(p.qry)]) for sl in slices]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def split(k):
-        return [k // S + (1 if j < k % S else 0) for j in range(S)]
-
-    def run_threads(fn, counts):
-        ts = [threading.Thread(target=fn, args=(j, counts[j])) for j in range(S) if counts[j] > 0]
+    def run_threads(fn):
+        ts = [threading.Thread(target=fn, args=(j,)) for j in range(S)]
         for t in ts:
             t.start()
         for t in ts:
             t.join()
 
-    # ---- device-resident: upload once per context, then time K x run() ----
-    for a_ in als:
-        a_.upload(batch)
-        a_.cs_upload(subreads)
-        for _ in range(args.warmup):
-            if not args.dp_only:
-                a_.cs_run()
-            a_.run()
-    # (a) one context alone: per-kernel durations for the roofline (kernel timed in isolation)
+    # ---- (a) one context alone on the whole batch: per-kernel durations for the roofline (the fill
+    # kernel timed in isolation, inputs resident) ----
+    al.upload(batch)
+    al.cs_upload(subreads)
+    for _ in range(args.warmup):
+        if not args.dp_only:
+            al.cs_run()
+        al.run()
     barrier()
     fill_ms, tb_ms, cp_ms, cs_ms = [], [], [], []
     n_cand = 0
@@ -366,7 +367,22 @@ def main():
     e1.record(streams[0])
     torch.cuda.synchronize(dev)
     solo_ms = e0.elapsed_time(e1)
-    # (b) the timed region: exactly K steps spread over the S contexts
+    res = al.fetch()
+    st = al.stats()
+    assert all(res.ret(i) == len(p.qry) for i, p in enumerate(pool)), "bench: invalid alignment in the timed batch"
+    cells = st["cells"]
+    del res
+
+    # ---- (b) device-resident timed region: every context keeps its slice in HBM, exactly K steps ----
+    def resident_warm(j):
+        als[j].upload(sl_batch[j])
+        als[j].cs_upload(sl_reads[j])
+        for _ in range(args.warmup):
+            if not args.dp_only:
+                als[j].cs_run()
+            als[j].run()
+
+    run_threads(resident_warm)
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
@@ -377,49 +393,58 @@ def main():
         st_.wait_event(e0)
     ends = [torch.cuda.Event() for _ in range(S)]
 
-    def dev_worker(j, k):
-        for _ in range(k):
+    def dev_worker(j):
+        for _ in range(args.steps):
             if not args.dp_only:
                 als[j].cs_run()
             als[j].run()
         ends[j].record(streams[j])
 
-    counts = split(args.steps)
-    run_threads(dev_worker, counts)
+    run_threads(dev_worker)
     for j in range(S):
-        if counts[j] > 0:
-            cur.wait_event(ends[j])
+        cur.wait_event(ends[j])
     e1.record(cur)
     barrier()
     clocks = sampler.stop()
     dev_ms = e0.elapsed_time(e1)
-    res = al.fetch()
-    st = al.stats()
-    assert all(res.ret(i) == len(p.qry) for i, p in enumerate(pool)), "bench: invalid alignment in the timed batch"
-    cells = st["cells"]
+    for j in range(S):
+        r_ = als[j].fetch()
+        assert all(r_.ret(i) == len(p.qry) for i, p in enumerate(slices[j])), "bench: invalid alignment in a slice"
+        del r_
 
-    # ---- end to end from host buffers through the public call ----
-    cs_bytes = {}
+    # ---- (c) end to end from host buffers through the public calls: per step every context takes its
+    # slice from host memory (pack + H2D), runs all kernels, and brings candidates, scores and
+    # alignments (binary CIGAR -> CIGAR/MD text) back to the host. Uploads are issued before the
+    # kernels and fetches after them so that a context's host work overlaps other contexts' kernels. ----
+    io = [dict() for _ in range(S)]
 
-    def e2e_worker(j, k):
+    def e2e_steps(j, k):
+        a_ = als[j]
         for _ in range(k):
             if not args.dp_only:
-                als[j].cs_upload(subreads)       # host buffers -> device
-                m_, _ms = als[j].cs_run()
-                cstart, _sc, _lo, _rv, sw_, _mx = als[j].cs_fetch()   # candidates + scores -> host
+                a_.cs_upload(sl_reads[j])            # host buffers -> device
+            a_.upload(sl_batch[j])
+            if not args.dp_only:
+                m_, _ms = a_.cs_run()
+            a_.run()
+            if not args.dp_only:
+                cstart, _sc, _lo, _rv, sw_, _mx = a_.cs_fetch()   # candidates + scores -> host
                 assert m_ == cstart[-1] and sw_.size == m_
-                cs_bytes["h2d"] = subreads.bases + 12 * subreads.n
-                cs_bytes["d2h"] = 17 * int(m_) + 12 * subreads.n
-            out = als[j].BatchAlign(batch)
-            assert len(out) == batch.n and out.ret(0) == len(pool[0].qry)
+                io[j]["h2d"] = sl_reads[j].bases + 12 * sl_reads[j].n
+                io[j]["d2h"] = 17 * int(m_) + 12 * sl_reads[j].n
+            out = a_.fetch()
+            assert len(out) == sl_batch[j].n and out.ret(0) == len(slices[j][0].qry)
+            del out
 
-    run_threads(e2e_worker, [1] * S)
+    run_threads(lambda j: e2e_steps(j, 1))
     barrier()
     t0 = time.perf_counter()
-    run_threads(e2e_worker, counts)
+    run_threads(lambda j: e2e_steps(j, args.steps))
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
-    st_e2e = al.stats()
+    st_e2e = [a_.stats() for a_ in als]
+    e2e_h2d = sum(x["h2d_bytes"] for x in st_e2e) + sum(x.get("h2d", 0) for x in io)
+    e2e_d2h = sum(x["d2h_bytes"] for x in st_e2e) + sum(x.get("d2h", 0) for x in io)
 
     t_dev = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     tot = torch.tensor([float(bases), float(cells)], dtype=torch.float64, device=dev)
@@ -484,14 +509,16 @@ def main():
                         "sw_cell_updates_per_step_per_gpu": int(n_cand) * 257 * 307,
                         "reference_setup_s": t_ref,
                         "note": "k-mer vote of every 256-bp sub-read + device decode + StrippedSW score of every candidate"},
-            "e2e": {"value": e2e_val, "unit": "Gbp/s", "h2d_bytes_per_step": st_e2e["h2d_bytes"] + cs_bytes.get("h2d", 0),
-                    "d2h_bytes_per_step": st_e2e["d2h_bytes"] + cs_bytes.get("d2h", 0), "ms_per_step": e2e_ms / args.steps,
-                    "host_ms": {k: st_e2e[k] for k in ("host_pack_ms", "host_h2d_ms", "host_run_ms",
-                                                       "host_d2h_ms", "host_text_ms")},
-                    "host_threads": st_e2e["host_threads"]},
+            "e2e": {"value": e2e_val, "unit": "Gbp/s", "h2d_bytes_per_step": e2e_h2d,
+                    "d2h_bytes_per_step": e2e_d2h, "ms_per_step": e2e_ms / args.steps,
+                    "host_ms_per_slice": {k: float(np.mean([x[k] for x in st_e2e]))
+                                          for k in ("host_pack_ms", "host_h2d_ms", "host_run_ms",
+                                                    "host_d2h_ms", "host_text_ms")},
+                    "host_threads_per_context": st_e2e[0]["host_threads"],
+                    "note": f"each of the {S} contexts takes every {S}-th read of the batch per step"},
             "solo": {"gbp_per_s": bases * args.steps / (solo_ms * 1e-3) / 1e9, "ms_per_step": solo_ms / args.steps,
-                     "note": "one context alone, same K steps (kernels not overlapped)"},
-            "gpu_launches": 14 * args.steps,
+                     "note": "one context alone on the whole batch, same K steps (kernels not overlapped)"},
+            "gpu_launches": 14 * S * args.steps,
             "clocks": clocks,
         }
         # CPU baseline on this box's host cores, bounded sample of the same workload
