@@ -305,11 +305,10 @@ convex_fill_kernel(const FillParams p) {
           const uint4* in_g = in_s + ((g % GPC) << 4);
           uint4* out_g = out_s + ((g % GPC) << 4);
           uint32_t dw = 0;
-#pragma unroll 1
-          for (int k4 = 0; k4 < 16; k4 += 4) {
+          {
 #pragma unroll 2  // 2 keeps the per-step predicates in registers; 4 makes ptxas spill them to a bit mask
-            for (int k = 0; k < 4; ++k) {
-              const int s = (g << 4) + k4 + k;
+            for (int k = 0; k < 16; ++k) {
+              const int s = (g << 4) + k;
               uint4 v;
               v.x = __float_as_uint(__shfl_sync(FULL, oS, src_lane));
               v.y = __float_as_uint(__shfl_sync(FULL, oU, src_lane));
@@ -392,8 +391,8 @@ convex_fill_kernel(const FillParams p) {
               }
               dw = __funnelshift_r(dw, code, 2);
               if (is31) {
-                out_g[k4 + k] = make_uint4(__float_as_uint(S), __float_as_uint(U), oP, 0u);
-                const uint4 t = in_g[k4 + k + 1];
+                out_g[k] = make_uint4(__float_as_uint(S), __float_as_uint(U), oP, 0u);
+                const uint4 t = in_g[k + 1];
                 oS = __uint_as_float(t.x);
                 oU = __uint_as_float(t.y);
                 oP = t.z;
