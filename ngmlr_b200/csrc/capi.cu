@@ -888,7 +888,8 @@ namespace {
 struct CsState {
   DevBuf<uint8_t> d_packed;
   DevBuf<uint32_t> d_tab, d_pos, d_order;
-  DevBuf<uint8_t> d_used, d_seq, d_tables;
+  DevBuf<uint32_t> d_used;  // bitmap
+  DevBuf<uint8_t> d_seq, d_tables;
   DevBuf<uint64_t> d_off;     // seq_off | table_off | order_off | out_off
   DevBuf<int32_t> d_len, d_count;
   DevBuf<uint32_t> d_cap;
@@ -976,7 +977,7 @@ int ngmlr_b200_cs_set_index(ngmlr_b200_ctx* ctx, const void* packed_index, uint3
   cudaStream_t st = ctx->stream;
   CU(cs->d_packed.reserve((size_t)index_len * 5));
   CU(cs->d_tab.reserve((size_t)index_len + 1));
-  CU(cs->d_used.reserve((size_t)index_len + 1));
+  CU(cs->d_used.reserve(((size_t)index_len + 255) / 256 * 8 + 8));  // one word per 32 prefixes, whole blocks
   CU(cs->d_pos.reserve((size_t)n_positions + 1));
   CU(cudaMemcpyAsync(cs->d_packed.p, packed_index, (size_t)index_len * 5, cudaMemcpyHostToDevice, st));
   if (n_positions)
@@ -1029,7 +1030,7 @@ int ngmlr_b200_cs_search_batch(ngmlr_b200_ctx* ctx, int n, const char* const* se
   CsParams p;
   memset(&p, 0, sizeof(p));
   p.tab = cs->d_tab.p;
-  p.used = cs->d_used.p;
+  p.used_bits = cs->d_used.p;
   p.pos = cs->d_pos.p;
   p.unit_offset = cs->unit_offset;
   p.k = cs->k;
@@ -1273,7 +1274,7 @@ int ngmlr_b200_cs_run(ngmlr_b200_ctx* ctx, float sensitivity, float min_kmer_hit
   CsParams p;
   memset(&p, 0, sizeof(p));
   p.tab = cs->d_tab.p;
-  p.used = cs->d_used.p;
+  p.used_bits = cs->d_used.p;
   p.pos = cs->d_pos.p;
   p.unit_offset = cs->unit_offset;
   p.k = cs->k;

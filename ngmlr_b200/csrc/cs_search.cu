@@ -11,7 +11,7 @@
 // parallelism comes from the hundreds of thousands of independent sub-reads of a batch (a 2048-
 // thread SM keeps 2048 of these latency-bound walks in flight). The index (5-byte Index records
 // unpacked to tab/used arrays + uint32 position lists) and the open-addressing vote tables live in
-// HBM; a first pass counts each read's hits so that its table can be sized (the reference instead
+// HBM (the used() flags as an L2-resident bitmap); a first pass counts each read's hits so that its table can be sized (the reference instead
 // restarts with a larger table on overflow -- results do not depend on the table size).
 //
 // Assumes, like the reference's 1000-N leading spacer guarantees, position >= offset-in-read.
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(128) cs_search_kernel(const CsParams p) {
 
   auto kmer = [&](uint32_t prefix, int pos) {
     // forward list, then the list of the reverse-complement k-mer (GetRefEntry)
-    if (p.used[prefix]) {
+    if ((p.used_bits[prefix >> 5] >> (prefix & 31u)) & 1u) {
       const uint32_t start = p.tab[prefix] - 1u, n = p.tab[prefix + 1] - 1u - start;
       if (COUNT_ONLY) {
         hits += n;
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(128) cs_search_kernel(const CsParams p) {
       }
     }
     const uint32_t rc = rev_comp(prefix, k, mask);
-    if (p.used[rc]) {
+    if ((p.used_bits[rc >> 5] >> (rc & 31u)) & 1u) {
       const uint32_t start = p.tab[rc] - 1u, n = p.tab[rc + 1] - 1u - start;
       if (COUNT_ONLY) {
         hits += n;
@@ -181,14 +181,20 @@ __global__ void __launch_bounds__(128) cs_search_kernel(const CsParams p) {
 }
 
 // Unpack the reference's 5-byte Index records {uint m_TabIndex; char m_RevCompIndex}
-// (#pragma pack(1), src/PrefixTable.h:17-35) into aligned arrays.
+// (#pragma pack(1), src/PrefixTable.h:17-35) into an aligned uint32 array plus a bitmap of
+// Index::used() (m_RevCompIndex != 0). The bitmap of a 13-mer index is 8 MB and stays in L2, so the
+// ~75 % of lookups that hit an unused prefix never go to HBM.
 __global__ void unpack_index_kernel(const uint8_t* __restrict__ packed, uint32_t n, uint32_t* __restrict__ tab,
-                                    uint8_t* __restrict__ used) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint8_t* r = packed + (size_t)i * 5;
-  tab[i] = (uint32_t)r[0] | ((uint32_t)r[1] << 8) | ((uint32_t)r[2] << 16) | ((uint32_t)r[3] << 24);
-  used[i] = r[4] != 0;
+                                    uint32_t* __restrict__ used_bits) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // blockDim is a multiple of 32
+  bool used = false;
+  if (i < n) {
+    const uint8_t* r = packed + (size_t)i * 5;
+    tab[i] = (uint32_t)r[0] | ((uint32_t)r[1] << 8) | ((uint32_t)r[2] << 16) | ((uint32_t)r[3] << 24);
+    used = r[4] != 0;
+  }
+  const uint32_t word = __ballot_sync(0xffffffffu, used);
+  if ((threadIdx.x & 31) == 0) used_bits[i >> 5] = word;
 }
 
 }  // namespace
@@ -203,10 +209,10 @@ cudaError_t launch_cs_search(const CsParams& p, bool count_only, cudaStream_t st
   return cudaGetLastError();
 }
 
-cudaError_t launch_unpack_index(const uint8_t* packed, uint32_t n, uint32_t* tab, uint8_t* used,
+cudaError_t launch_unpack_index(const uint8_t* packed, uint32_t n, uint32_t* tab, uint32_t* used_bits,
                                 cudaStream_t stream) {
   if (!n) return cudaSuccess;
-  unpack_index_kernel<<<(n + 255) / 256, 256, 0, stream>>>(packed, n, tab, used);
+  unpack_index_kernel<<<(n + 255) / 256, 256, 0, stream>>>(packed, n, tab, used_bits);
   return cudaGetLastError();
 }
 

@@ -134,7 +134,7 @@ struct alignas(16) CsCandidate {
 struct CsParams {
   // index (one table unit)
   const uint32_t* tab;     // Index::m_TabIndex, 4^k + 1 entries
-  const uint8_t* used;     // Index::used()
+  const uint32_t* used_bits;  // Index::used() as a bitmap, bit (prefix & 31) of word prefix >> 5
   const uint32_t* pos;     // Location::m_Location lists
   unsigned long long unit_offset;
   int k, bin_shift;
