@@ -471,7 +471,7 @@ def main():
         algo_bytes = cells * 0.25 + seq_b + rows * 8
         fill_s = float(np.mean(fill_ms)) * 1e-3
         achieved = algo_bytes / fill_s / 1e9
-        issue_bound_cells = 148 * 4 * 32 * float(clocks.get("sm_mhz") or 1965.0) * 1e6 / (38.0 * 2.0)
+        issue_bound_cells = 148 * 4 * 32 * float(clocks.get("sm_mhz") or 1965.0) * 1e6 / (27.0 * 2.0)
         traffic = None
         try:  # DRAM bytes of one fill launch from the committed ncu capture (same reads/step only)
             tr = json.load(open(os.path.join(ROOT, "profiles", "fill_traffic.json")))
@@ -500,8 +500,8 @@ def main():
                          "gcells_per_s_kernel": cells / fill_s / 1e9,
                          "alu_pipe_bound_gcells_per_s": issue_bound_cells / 1e9,
                          "frac_of_alu_pipe_bound": cells / fill_s / issue_bound_cells,
-                         "note": "ALU-pipe-bound kernel (~38 ALU-pipe SASS instr per 32-cell step, 2 cycles each "
-                                 "per SMSP, DESIGN.md 4.1); HBM frac is structurally ~0.015"},
+                         "note": "ALU-pipe-bound kernel (~27 ALU-pipe SASS instr per 32-cell step, 2 cycles each "
+                                 "per SMSP, DESIGN.md 4.1); HBM frac is structurally ~0.02"},
             "kernel_ms_per_step": {"fill": float(np.mean(fill_ms)), "traceback": float(np.mean(tb_ms)),
                                    "compact": float(np.mean(cp_ms)),
                                    "stage02_cs_vote_decode_score": float(np.mean(cs_ms))},
