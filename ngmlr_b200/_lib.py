@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libngmlr_b200.so")
+# NGMLR_B200_LIBRARY: developer override to A/B-test another build of the same library (still CUDA only)
+LIB_PATH = os.environ.get("NGMLR_B200_LIBRARY") or os.path.join(_HERE, "libngmlr_b200.so")
 
 
 class Scoring(C.Structure):

@@ -600,6 +600,7 @@ int ngmlr_b200_convex_run(ngmlr_b200_ctx* ctx) {
     tp.c_blkbase = ctx->d_blkbase.p;
     tp.c_delta = ctx->d_delta.p;
     tp.desc = ctx->d_desc.p;
+    tp.order = ctx->d_order.p;
     tp.n = n;
     tp.blocks = ctx->d_blocks.p;
     tp.dir = ctx->d_dir.p;

@@ -59,6 +59,10 @@ constexpr unsigned X_BIAS = 1u << 20;
 __device__ __forceinline__ uint4 ld_strip(const uint4* p) { return __ldcg(p); }
 __device__ __forceinline__ void st_strip(uint4* p, uint4 v) { __stcg(p, v); }
 
+// CTA-scope fence ordering the strip records (st.cg / ld.cg) against the progress word in shared memory
+// (fence.acq_rel.cta instead of the sequentially consistent fence measured no difference)
+__device__ __forceinline__ void team_fence() { __threadfence_block(); }
+
 __device__ __forceinline__ unsigned long long prog_key(int blk, int x) {
   return ((unsigned long long)(unsigned)(blk + 1) << 32) | (unsigned long long)((unsigned)x + X_BIAS);
 }
@@ -216,7 +220,7 @@ convex_fill_kernel(const FillParams p) {
               while (s_prog[prev_tw] < key) __nanosleep(64);
             }
             __syncwarp();
-            __threadfence_block();
+            team_fence();
           }
         }
       };
@@ -417,7 +421,7 @@ convex_fill_kernel(const FillParams p) {
           if (lane < done) st_strip(strip + xo + lane, out_s[lane]);
           if (CHUNK > 32 && lane + 32 < done) st_strip(strip + xo + lane + 32, out_s[lane + 32]);
           if (NW > 1) {
-            __threadfence_block();
+            team_fence();
             __syncwarp();
             if (is0) s_prog[tw] = prog_key(b, xo + done);
           }

@@ -28,15 +28,17 @@ constexpr int NW = 4;  // direction words (16 steps each) a lane keeps per block
 
 struct RowWindow {
   int off, len;        // corridor line of row 32*blk + lane
+  int min_c, max_c;    // validPath bounds of that row (exclusive)
   uint32_t q;          // read byte of that row
   int g0;              // first 16-step group held in w[]
   uint32_t w[NW];
 };
 
 __global__ void __launch_bounds__(TB_WARPS_PER_CTA * 32) convex_traceback_kernel(const TraceParams p) {
-  const int i = blockIdx.x * TB_WARPS_PER_CTA + (threadIdx.x >> 5);
+  const int slot = blockIdx.x * TB_WARPS_PER_CTA + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (i >= p.n) return;
+  if (slot >= p.n) return;
+  const int i = p.order[slot];  // longest walks first: no straggler warps at the end of the launch
   const AlnDesc d = p.desc[i];
   const FillOut f = p.fill[i];
   TraceOut o;
@@ -87,7 +89,7 @@ __global__ void __launch_bounds__(TB_WARPS_PER_CTA * 32) convex_traceback_kernel
   br.word_off = 0; br.base = 0; br.nsteps = 0;
   int ngroups = 0;
   RowWindow rw;
-  rw.off = 0; rw.len = 0; rw.q = 0; rw.g0 = 0;
+  rw.off = 0; rw.len = 0; rw.q = 0; rw.g0 = 0; rw.min_c = 0; rw.max_c = 0;
 #pragma unroll
   for (int j = 0; j < NW; ++j) rw.w[j] = 0;
   int xw0 = 1 << 30;       // reference byte window [xw0, xw0 + 128), 4 bytes per lane
@@ -105,6 +107,11 @@ __global__ void __launch_bounds__(TB_WARPS_PER_CTA * 32) convex_traceback_kernel
       rw.q = 0;
       load_corridor_rows(cv, blk, lane, H, rw.off, rw.len);
       if (yy < H) rw.q = qry[yy];
+      {  // validPath(x, y) bounds: float math then truncation, as in the reference (:213-220)
+        const float wf = (float)rw.len;
+        rw.min_c = (int)__fadd_rn((float)rw.off, __fmul_rn(0.1f, wf));
+        rw.max_c = (int)__fsub_rn((float)(rw.min_c + rw.len), __fmul_rn(0.1f, wf));
+      }
       // expected step index of the path in row `lane`: two steps per row along the diagonal
       const int s_here = x - br.base + t;
       const int s_exp = s_here - 2 * (t - lane);
@@ -130,12 +137,7 @@ __global__ void __launch_bounds__(TB_WARPS_PER_CTA * 32) convex_traceback_kernel
         const int j2 = (s2 >> 4) - rw.g0;
         if ((unsigned)j2 < (unsigned)NW) {
           const uint32_t w2 = j2 == 0 ? rw.w[0] : (j2 == 1 ? rw.w[1] : (j2 == 2 ? rw.w[2] : rw.w[3]));
-          if (((w2 >> ((s2 & 15) * 2)) & 3u) == DIR_DIAG) {
-            const float wf = (float)rw.len;
-            const int min_c = (int)__fadd_rn((float)rw.off, __fmul_rn(0.1f, wf));
-            const int max_c = (int)__fsub_rn((float)(min_c + rw.len), __fmul_rn(0.1f, wf));
-            okd = xx > min_c && xx < max_c;
-          }
+          okd = ((w2 >> ((s2 & 15) * 2)) & 3u) == DIR_DIAG && xx > rw.min_c && xx < rw.max_c;
         }
       }
       const unsigned okm = __ballot_sync(FULL, okd) << (31 - t);
@@ -195,11 +197,10 @@ __global__ void __launch_bounds__(TB_WARPS_PER_CTA * 32) convex_traceback_kernel
     }
     const uint32_t code = (wd >> ((s & 15) * 2)) & 3u;
     if (code == DIR_STOP) break;
-    // ---- validPath(x, y): float math then truncation, as in the reference ----
+    // ---- validPath(x, y) ----
     {
-      const float w = (float)len;
-      const int min_c = (int)__fadd_rn((float)off, __fmul_rn(0.1f, w));
-      const int max_c = (int)__fsub_rn((float)(min_c + len), __fmul_rn(0.1f, w));
+      const int min_c = __shfl_sync(FULL, rw.min_c, t);
+      const int max_c = __shfl_sync(FULL, rw.max_c, t);
       if (!(x > min_c && x < max_c)) {
         ok = false;
         break;

@@ -113,6 +113,7 @@ struct TraceParams {
   const int32_t* c_blkbase;
   const int8_t* c_delta;
   const AlnDesc* desc;
+  const int32_t* order;                // problems by decreasing matrix size (longest walks first)
   int n;
   const BlockRec* blocks;
   const uint32_t* dir;
