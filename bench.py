@@ -214,6 +214,9 @@ def main():
     ap.add_argument("--genome-mb", type=float, default=50.0)
     ap.add_argument("--dp-only", action="store_true", help="time stage 4 (convex alignment) alone")
     ap.add_argument("--contexts", type=int, default=4, help="aligner contexts (host threads/streams) per GPU")
+    ap.add_argument("--fill-ctas", type=int, default=4,
+                    help="fill CTAs per SM per launch in the concurrent phases (0 = full occupancy; the solo "
+                         "roofline phase always runs at full occupancy)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
@@ -374,6 +377,11 @@ def main():
     del res
 
     # ---- (b) device-resident timed region: every context keeps its slice in HBM, exactly K steps ----
+    # Smaller persistent fill grids per launch so that the launches of the S contexts (and their
+    # memory-bound candidate-search / traceback kernels) share the SMs instead of queueing.
+    for a_ in als:
+        a_.set_fill_ctas_per_sm(args.fill_ctas if S > 1 else 0)
+
     def resident_warm(j):
         als[j].upload(sl_batch[j])
         als[j].cs_upload(sl_reads[j])
@@ -486,7 +494,8 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "reads_per_step_per_gpu": args.reads,
                        "read_bases_per_step": tot_bases, "dp_cells_per_step": tot_cells,
-                       "parallelism": f"read-sharded x{world}, no per-step collective; {S} aligner contexts/GPU",
+                       "parallelism": f"read-sharded x{world}, no per-step collective; {S} aligner contexts/GPU, "
+                                      f"fill grid {args.fill_ctas or 'full'} CTAs/SM per launch",
                        "l2": "inputs+direction arena per step exceed L2 (direction writes alone "
                              f"{st['dir_bytes'] / 1e6:.0f} MB/step/GPU)",
                        "vs_baseline_note": "README.md:25 end-to-end 5.56e-4 Gbp/s on 10 Opteron cores (whole "

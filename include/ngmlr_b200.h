@@ -92,6 +92,12 @@ const char* ngmlr_b200_last_error(const ngmlr_b200_ctx* ctx); /* ctx may be NULL
 int ngmlr_b200_set_stream(ngmlr_b200_ctx* ctx, void* cuda_stream);
 void* ngmlr_b200_get_stream(ngmlr_b200_ctx* ctx);
 
+/* Tuning: cap the persistent grid of the fill kernel at `ctas_per_sm` CTAs per SM (0 = full occupancy,
+ * the default; also NGMLR_B200_FILL_CTAS_PER_SM). A process that drives several contexts on one GPU
+ * gets more overlap between their launches with a smaller grid per launch (bench.py uses 4). No
+ * reference counterpart. Results do not depend on it. */
+int ngmlr_b200_set_fill_ctas_per_sm(ngmlr_b200_ctx* ctx, int ctas_per_sm);
+
 /* ---- convex banded alignment: IAlignment::SingleAlign(mode, CorridorLine*, ...) batched -------
  * Replaces ConvexAlignFast::SingleAlign (src/ConvexAlignFast.cpp:452-559) for n independent
  * problems. Problem i: refs[i]/qrys[i] are the reference window and read part (need not be

@@ -291,6 +291,10 @@ class B200Aligner:
         """Test hook: initial size of the direction arena (-1 = the host's estimate)."""
         self.lib.ngmlr_b200_debug_set_arena_words(self.h, int(words))
 
+    def set_fill_ctas_per_sm(self, v):
+        """Cap the persistent fill grid (0 = full occupancy); see ngmlr_b200_set_fill_ctas_per_sm."""
+        self.lib.ngmlr_b200_set_fill_ctas_per_sm(self.h, int(v))
+
     def force_team(self, v):
         """-1 auto, 0 one warp per problem, 1 four-warp teams (fill kernel scheduling)."""
         self.lib.ngmlr_b200_set_force_team(self.h, int(v))

@@ -161,6 +161,7 @@ struct ngmlr_b200_ctx {
   int max_ref_len = 0;
   int wide_problems = 0;  // problems whose corridor is >= 352 columns wide
   int force_team = -1;
+  int fill_ctas_cap = 0;  // 0 = full occupancy
   int ctas_per_sm[4] = {0, 0, 0, 0};  // occupancy of the four fill-kernel variants
   long long debug_arena_words = -1;    // test hook: initial direction-arena size
   PinBuf<uint8_t> h_seq;
@@ -279,6 +280,7 @@ int ngmlr_b200_create(int gpu_id, const ngmlr_b200_scoring* s, ngmlr_b200_ctx** 
   ctx->sc.decay = d.gap_decay;
   ctx->raw = scoring_needs_raw(ctx->sc);
   if (const char* e = getenv("NGMLR_B200_FILL_TEAM")) ctx->force_team = atoi(e);
+  if (const char* e = getenv("NGMLR_B200_FILL_CTAS_PER_SM")) ctx->fill_ctas_cap = std::max(0, atoi(e));
   if (const char* e = getenv("NGMLR_B200_NO_CORRIDOR_PACKING")) ctx->no_corridor_packing = atoi(e);
   *out = ctx;
   return 0;
@@ -325,6 +327,16 @@ void* ngmlr_b200_get_stream(ngmlr_b200_ctx* ctx) { return ctx ? (void*)ctx->stre
 int ngmlr_b200_debug_set_arena_words(ngmlr_b200_ctx* ctx, long long words) {
   if (!ctx) return -1;
   ctx->debug_arena_words = words;
+  return 0;
+}
+
+// Cap the persistent fill grid at v CTAs per SM (0 = full occupancy, the default). With several
+// contexts sharing a GPU a smaller grid per launch lets the launches of different contexts -- and
+// their memory-bound candidate-search / traceback kernels -- reside on the SMs together.
+// NGMLR_B200_FILL_CTAS_PER_SM sets the initial value. Tuning hook.
+int ngmlr_b200_set_fill_ctas_per_sm(ngmlr_b200_ctx* ctx, int v) {
+  if (!ctx) return -1;
+  ctx->fill_ctas_cap = v > 0 ? v : 0;
   return 0;
 }
 
@@ -557,7 +569,9 @@ int ngmlr_b200_convex_run(ngmlr_b200_ctx* ctx) {
   if (ctx->force_team >= 0) team = ctx->force_team != 0;
   const int variant = (raw ? 1 : 0) | (team ? 2 : 0);
   if (!ctx->ctas_per_sm[variant]) ctx->ctas_per_sm[variant] = std::max(1, fill_max_ctas_per_sm(raw, team));
-  const int max_grid = ctx->num_sms * ctx->ctas_per_sm[variant];
+  int per_sm = ctx->ctas_per_sm[variant];
+  if (ctx->fill_ctas_cap > 0) per_sm = std::min(per_sm, ctx->fill_ctas_cap);
+  const int max_grid = ctx->num_sms * per_sm;
   const int want_grid = team ? n : (n + FILL_WARPS_PER_CTA - 1) / FILL_WARPS_PER_CTA;
   const int grid = std::max(1, std::min(max_grid, want_grid));
   ctx->fill_grid = grid;
