@@ -196,6 +196,32 @@ int ngmlr_b200_cs_fetch(ngmlr_b200_ctx* ctx, int64_t* cand_start, const float** 
                         const uint64_t** locs, const uint8_t** reverse, const float** sw_scores,
                         float* max_hits);
 
+/* ---- reference windows for alignment, decoded on the device -------------------------------------
+ * refStartPos as _SequenceProvider holds it (src/SequenceProvider.cpp:416-424): the concatenated
+ * start position of every contig (forward strand entries only) followed by one artificial entry
+ * last_start + last_len + 1000. Needs ngmlr_b200_cs_set_reference (the encoded genome). */
+int ngmlr_b200_set_ref_starts(ngmlr_b200_ctx* ctx, const uint64_t* ref_start_pos, int n_entries);
+
+/* Replaces _SequenceProvider::DecodeRefSequenceExact(sequence, start, seq_len, 0)
+ * (src/SequenceProvider.cpp:493-565) for n windows: window i is written to out + out_off[i],
+ * seq_len[i] bytes with the NUL at seq_len[i] - 1; 'x' where the window runs past its contig or
+ * starts in the spacer in front of it. Contract (as far as the reference itself is well defined):
+ * 0 < start < GetConcatRefLen(), and start lies inside a contig or inside the 1000-N spacer in front
+ * of one; otherwise -1. Returns n. */
+int ngmlr_b200_decode_windows(ngmlr_b200_ctx* ctx, int n, const uint64_t* start, const int32_t* seq_len,
+                              char* out, const int64_t* out_off);
+
+/* ngmlr_b200_convex_upload with the reference windows named by position instead of shipped as text:
+ * problem i aligns qrys[i] against extractReferenceSequenceForAlignment(on_ref_start[i], on_ref_stop[i])
+ * (src/AlignmentBuffer.cpp:203-223: DecodeRefSequenceExact of stop - start + 1 characters incl. NUL),
+ * decoded on the device straight into the sequence arena; run/fetch as usual. Same contract for the
+ * start positions as ngmlr_b200_decode_windows, and start < stop. */
+int ngmlr_b200_convex_upload_windows(ngmlr_b200_ctx* ctx, int n, const uint64_t* on_ref_start,
+                                     const uint64_t* on_ref_stop, const char* const* qrys,
+                                     const int32_t* qry_lens, const int32_t* corridor_offsets,
+                                     const int32_t* corridor_lengths, const int64_t* row_start,
+                                     const int32_t* ext_qstart, const int32_t* ext_qend);
+
 /* Candidate selection once a (sub-)read's candidates are scored. Replaces ScoreBuffer::topNSE and
  * ScoreBuffer::computeMQ (src/ScoreBuffer.cpp:170-192, 33-45). Host code (the reference's is too): for
  * (sub-)read i the candidates [cand_start[i], cand_start[i+1]) are ordered by descending sw_scores with

@@ -221,6 +221,39 @@ class B200Aligner:
         enc = np.ascontiguousarray(ref.enc, dtype=np.uint8)
         self._check(self.lib.ngmlr_b200_cs_set_reference(self.h, enc.ctypes.data_as(C.c_void_p), enc.size,
                                                          ref.concat_len))
+        if ref.ref_start:
+            # refStartPos: contig starts + one artificial end entry (src/SequenceProvider.cpp:416-424)
+            starts = np.array(list(ref.ref_start) + [ref.ref_start[-1] + ref.ref_len[-1] + 1000], dtype=np.uint64)
+            self._check(self.lib.ngmlr_b200_set_ref_starts(self.h, starts.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                                           int(starts.size)))
+
+    def decode_windows(self, starts, seq_lens):
+        """DecodeRefSequenceExact(buf, start, seq_len, 0) for every window -> list of bytes (the C
+        strings, i.e. seq_len - 1 characters unless the reference data holds a NUL)."""
+        starts = np.ascontiguousarray(starts, dtype=np.uint64)
+        seq_lens = np.ascontiguousarray(seq_lens, dtype=np.int32)
+        n = int(starts.size)
+        off = np.zeros(n + 1, dtype=np.int64)
+        off[1:] = np.cumsum(seq_lens.astype(np.int64))
+        buf = C.create_string_buffer(int(off[-1]) + 1)
+        self._check(self.lib.ngmlr_b200_decode_windows(
+            self.h, n, starts.ctypes.data_as(C.POINTER(C.c_uint64)), seq_lens.ctypes.data_as(C.POINTER(C.c_int32)),
+            buf, off.ctypes.data_as(C.POINTER(C.c_int64))))
+        raw = buf.raw
+        return [raw[off[i]:off[i + 1]].split(b"\0")[0] for i in range(n)]
+
+    def upload_windows(self, batch, on_ref_start, on_ref_stop):
+        """upload() with the reference windows of `batch` named by concatenated-genome positions
+        (extractReferenceSequenceForAlignment(onRefStart, onRefStop)) and decoded on the device;
+        batch.refs / ref_lens are ignored."""
+        a = np.ascontiguousarray(on_ref_start, dtype=np.uint64)
+        b = np.ascontiguousarray(on_ref_stop, dtype=np.uint64)
+        assert a.size == batch.n and b.size == batch.n
+        args = batch.c_args()
+        u64p = C.POINTER(C.c_uint64)
+        self._n = batch.n
+        self._check(self.lib.ngmlr_b200_convex_upload_windows(self.h, batch.n, a.ctypes.data_as(u64p),
+                                                             b.ctypes.data_as(u64p), *args[3:]))
 
     def cs_score(self, seqs, sensitivity=0.8, min_kmer_hits=0.0, corridor=40, read_part_length=256):
         """CS::RunRead + ScoreBuffer::DoRun for sub-reads: per read [(cs_score, location, reverse,

@@ -162,6 +162,9 @@ struct ngmlr_b200_ctx {
   int wide_problems = 0;  // problems whose corridor is >= 352 columns wide
   int force_team = -1;
   int fill_ctas_cap = 0;  // 0 = full occupancy
+  PinBuf<unsigned long long> h_win;   // windows mode: start | arena offset | (sequenceLength, span) pairs
+  DevBuf<unsigned long long> d_win;
+  int64_t upload_d2h_bytes = 0;
   int ctas_per_sm[4] = {0, 0, 0, 0};  // occupancy of the four fill-kernel variants
   long long debug_arena_words = -1;    // test hook: initial direction-arena size
   PinBuf<uint8_t> h_seq;
@@ -294,7 +297,7 @@ void ngmlr_b200_destroy(ngmlr_b200_ctx* ctx) {
   ctx->h_seq.release(); ctx->h_coff.release(); ctx->h_clen.release(); ctx->h_order.release(); ctx->h_blkbase.release(); ctx->h_delta.release();
   ctx->h_desc.release(); ctx->h_fill.release(); ctx->h_trace.release(); ctx->h_runs.release();
   ctx->h_counters.release();
-  ctx->d_seq.release(); ctx->d_coff.release(); ctx->d_clen.release(); ctx->d_order.release(); ctx->d_blkbase.release(); ctx->d_delta.release();
+  ctx->d_seq.release(); ctx->d_coff.release(); ctx->d_clen.release(); ctx->d_order.release(); ctx->d_blkbase.release(); ctx->d_delta.release(); ctx->d_win.release(); ctx->h_win.release();
   ctx->d_desc.release(); ctx->d_blocks.release(); ctx->d_dir.release(); ctx->d_bnd.release();
   ctx->d_fill.release(); ctx->d_scratch.release(); ctx->d_trace.release(); ctx->d_runs.release();
   ctx->d_counters.release();
@@ -354,11 +357,24 @@ int ngmlr_b200_set_force_raw(ngmlr_b200_ctx* ctx, int v) {
   return 0;
 }
 
-int ngmlr_b200_convex_upload(ngmlr_b200_ctx* ctx, int n, const char* const* refs,
-                             const int32_t* ref_lens, const char* const* qrys,
-                             const int32_t* qry_lens, const int32_t* corridor_offsets,
-                             const int32_t* corridor_lengths, const int64_t* row_start,
-                             const int32_t* ext_qstart, const int32_t* ext_qend) {
+}  // extern "C"
+
+namespace {
+
+// Reference windows decoded on the device instead of shipped as text (convex_upload_windows).
+struct RefWindows {
+  const uint8_t* d_enc;
+  const unsigned long long* d_ref_starts;
+  int n_starts;
+  const uint64_t* win_start;  // host, n entries
+};
+
+// refs == nullptr <=> windows mode: the sequence arena then holds all reference windows first (filled
+// by decode_windows_kernel and copied back for the host CIGAR/MD stage), then all reads.
+int convex_upload_impl(ngmlr_b200_ctx* ctx, int n, const char* const* refs, const RefWindows* win,
+                       const int32_t* ref_lens, const char* const* qrys, const int32_t* qry_lens,
+                       const int32_t* corridor_offsets, const int32_t* corridor_lengths,
+                       const int64_t* row_start, const int32_t* ext_qstart, const int32_t* ext_qend) {
   if (!ctx) return -1;
   if (n < 0) return ctx->fail("convex_upload: n < 0");
   CU(cudaSetDevice(ctx->device));
@@ -390,13 +406,25 @@ int ngmlr_b200_convex_upload(ngmlr_b200_ctx* ctx, int n, const char* const* refs
   // ---- pack (parallel over problems) ----
   const double t_pack0 = now_ms();
   const int64_t r0 = row_start[0];
-  std::vector<size_t> seq_at(n), blk_at(n), tb_at(n);
+  std::vector<size_t> ref_at(n), qry_at(n), blk_at(n), tb_at(n);
+  size_t ref_region = 0;  // windows mode: bytes of the leading reference region
+  if (!refs)
+    for (int i = 0; i < n; ++i) ref_region += align_up((size_t)ref_lens[i] + SEQ_PAD, 16);
   {
-    size_t so_ = 0, bo_ = 0, tb_ = 0;
+    size_t so_ = 0, ro_ = 0, qo_ = ref_region, bo_ = 0, tb_ = 0;
     for (int i = 0; i < n; ++i) {
       const int rl = ref_lens[i], ql = qry_lens[i];
-      seq_at[i] = so_;
-      so_ += align_up((size_t)rl + SEQ_PAD, 16) + align_up((size_t)ql + SEQ_PAD, 16);
+      const size_t rspan = align_up((size_t)rl + SEQ_PAD, 16), qspan = align_up((size_t)ql + SEQ_PAD, 16);
+      if (refs) {
+        ref_at[i] = so_;
+        qry_at[i] = so_ + rspan;
+        so_ += rspan + qspan;
+      } else {
+        ref_at[i] = ro_;
+        qry_at[i] = qo_;
+        ro_ += rspan;
+        qo_ += qspan;
+      }
       blk_at[i] = bo_;
       bo_ += ((size_t)ql + 31) / 32;
       tb_at[i] = tb_;
@@ -412,11 +440,13 @@ int ngmlr_b200_convex_upload(ngmlr_b200_ctx* ctx, int n, const char* const* refs
     AlnDesc& d = ctx->h_desc.p[i];
     memset(&d, 0, sizeof(d));
     const int rl = ref_lens[i], ql = qry_lens[i];
-    size_t so = seq_at[i];
+    size_t so = ref_at[i];
     d.ref_off = so;
-    memcpy(ctx->h_seq.p + so, refs[i], rl);
-    memset(ctx->h_seq.p + so + rl, 0, align_up((size_t)rl + SEQ_PAD, 16) - rl);
-    so += align_up((size_t)rl + SEQ_PAD, 16);
+    if (refs) {
+      memcpy(ctx->h_seq.p + so, refs[i], rl);
+      memset(ctx->h_seq.p + so + rl, 0, align_up((size_t)rl + SEQ_PAD, 16) - rl);
+    }
+    so = qry_at[i];
     d.qry_off = so;
     memcpy(ctx->h_seq.p + so, qrys[i], ql);
     memset(ctx->h_seq.p + so + ql, 0, align_up((size_t)ql + SEQ_PAD, 16) - ql);
@@ -513,7 +543,34 @@ int ngmlr_b200_convex_upload(ngmlr_b200_ctx* ctx, int n, const char* const* refs
   CU(ctx->h_counters.reserve(4));
   CU(ctx->h_fill.reserve(n));
   CU(ctx->h_trace.reserve(n));
-  CU(cudaMemcpyAsync(ctx->d_seq.p, ctx->h_seq.p, so, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->d_seq.p + ref_region, ctx->h_seq.p + ref_region, so - ref_region,
+                     cudaMemcpyHostToDevice, st));
+  if (!refs) {
+    // window descriptors -> device, decode into the reference region, bring the text back for fetch()
+    CU(ctx->h_win.reserve((size_t)n * 3 + 2));
+    CU(ctx->d_win.reserve((size_t)n * 3 + 2));
+    unsigned long long* hw = ctx->h_win.p;
+    int32_t* hl = reinterpret_cast<int32_t*>(hw + 2 * (size_t)n);
+    for (int i = 0; i < n; ++i) {
+      hw[i] = win->win_start[i];
+      hw[n + i] = ctx->h_desc.p[i].ref_off;
+      hl[i] = ref_lens[i] + 1;                                               // sequenceLength incl. NUL
+      hl[n + i] = (int32_t)align_up((size_t)ref_lens[i] + SEQ_PAD, 16);     // text + zero padding
+    }
+    CU(cudaMemcpyAsync(ctx->d_win.p, hw, (size_t)n * 24, cudaMemcpyHostToDevice, st));
+    RefDecodeParams rp;
+    rp.enc = win->d_enc;
+    rp.ref_starts = win->d_ref_starts;
+    rp.n_starts = win->n_starts;
+    rp.n = n;
+    rp.win_start = ctx->d_win.p;
+    rp.out_off = reinterpret_cast<const uint64_t*>(ctx->d_win.p + n);
+    rp.win_len = reinterpret_cast<const int32_t*>(ctx->d_win.p + 2 * (size_t)n);
+    rp.out_span = rp.win_len + n;
+    rp.out = ctx->d_seq.p;
+    CU(launch_decode_windows(rp, st));
+    CU(cudaMemcpyAsync(ctx->h_seq.p, ctx->d_seq.p, ref_region, cudaMemcpyDeviceToHost, st));
+  }
   size_t raw_rows = 0;
   int raw_problems = 0;
   for (int i = 0; i < n; ++i)
@@ -546,9 +603,25 @@ int ngmlr_b200_convex_upload(ngmlr_b200_ctx* ctx, int n, const char* const* refs
   ctx->stats.host_pack_ms = (float)(t_pack1 - t_pack0);
   ctx->stats.host_h2d_ms = (float)(now_ms() - t_pack1);
   ctx->stats.host_threads = host_threads();
-  ctx->stats.h2d_bytes = (int64_t)(so + rows + bo * 4 + raw_rows * 8 + (size_t)n * (sizeof(AlnDesc) + 4));
+  ctx->stats.h2d_bytes = (int64_t)(so - ref_region + (refs ? 0 : (size_t)n * 24) + rows + bo * 4 + raw_rows * 8 +
+                                   (size_t)n * (sizeof(AlnDesc) + 4));
+  ctx->upload_d2h_bytes = (int64_t)ref_region;
   ctx->stats.seq_bytes = (int64_t)so;
   return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ngmlr_b200_convex_upload(ngmlr_b200_ctx* ctx, int n, const char* const* refs,
+                             const int32_t* ref_lens, const char* const* qrys,
+                             const int32_t* qry_lens, const int32_t* corridor_offsets,
+                             const int32_t* corridor_lengths, const int64_t* row_start,
+                             const int32_t* ext_qstart, const int32_t* ext_qend) {
+  if (ctx && n > 0 && !refs) return ctx->fail("convex_upload: refs is NULL");
+  return convex_upload_impl(ctx, n, refs, nullptr, ref_lens, qrys, qry_lens, corridor_offsets, corridor_lengths,
+                            row_start, ext_qstart, ext_qend);
 }
 
 int ngmlr_b200_convex_run(ngmlr_b200_ctx* ctx) {
@@ -687,7 +760,8 @@ int ngmlr_b200_convex_fetch(ngmlr_b200_ctx* ctx, ngmlr_b200_align_result* result
                        cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   const double t_f1 = now_ms();
-  ctx->stats.d2h_bytes = (int64_t)((size_t)n * (sizeof(FillOut) + sizeof(TraceOut)) + ctx->runs_used * 4);
+  ctx->stats.d2h_bytes = (int64_t)((size_t)n * (sizeof(FillOut) + sizeof(TraceOut)) + ctx->runs_used * 4) +
+                         ctx->upload_d2h_bytes;
   if ((int)ctx->texts.size() < n) ctx->texts.resize(n);
   for (int i = 0; i < n; ++i)
     if (ctx->h_trace.p[i].status == ST_DIR_OVERFLOW)
@@ -922,6 +996,8 @@ struct CsState {
   // candidate scoring
   DevBuf<uint8_t> d_enc, d_rev;
   uint64_t enc_bytes = 0, concat_len = 0;
+  DevBuf<unsigned long long> d_ref_starts;   // refStartPos (set_ref_starts)
+  std::vector<unsigned long long> ref_starts;
   DevBuf<unsigned long long> d_winpos;
   DevBuf<uint64_t> d_qoff;
   DevBuf<int32_t> d_qlen;
@@ -962,7 +1038,7 @@ void nb_cs_release(ngmlr_b200_ctx* ctx) {
   for (size_t i = 0; i < g_cs_states.size(); ++i) {
     if (g_cs_states[i].first != ctx) continue;
     CsState* cs = g_cs_states[i].second;
-    cs->d_packed.release(); cs->d_tab.release(); cs->d_pos.release(); cs->d_order.release();
+    cs->d_packed.release(); cs->d_tab.release(); cs->d_pos.release(); cs->d_order.release(); cs->d_ref_starts.release();
     cs->d_used.release(); cs->d_seq.release(); cs->d_tables.release(); cs->d_off.release();
     cs->d_len.release(); cs->d_count.release(); cs->d_cap.release(); cs->d_hits.release();
     cs->d_max.release(); cs->d_out.release(); cs->d_enc.release(); cs->d_rev.release();
@@ -1151,6 +1227,113 @@ int ngmlr_b200_cs_set_reference(ngmlr_b200_ctx* ctx, const uint8_t* bin_ref, uin
   cs->enc_bytes = n_bytes;
   cs->concat_len = concat_len;
   return 0;
+}
+
+int ngmlr_b200_set_ref_starts(ngmlr_b200_ctx* ctx, const uint64_t* ref_start_pos, int n_entries) {
+  if (!ctx) return -1;
+  if (n_entries < 2 || !ref_start_pos) return ctx->fail("set_ref_starts: need the contig starts plus the end entry");
+  for (int i = 1; i < n_entries; ++i)
+    if (ref_start_pos[i] <= ref_start_pos[i - 1]) return ctx->fail("set_ref_starts: entries must increase");
+  CU(cudaSetDevice(ctx->device));
+  CsState* cs = cs_state(ctx, true);
+  cs->ref_starts.assign(ref_start_pos, ref_start_pos + n_entries);
+  CU(cs->d_ref_starts.reserve((size_t)n_entries));
+  CU(cudaMemcpyAsync(cs->d_ref_starts.p, cs->ref_starts.data(), (size_t)n_entries * 8, cudaMemcpyHostToDevice,
+                     ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+namespace {
+
+// The contract of the window calls: the window starts inside a contig or inside the 1000-N spacer in
+// front of one (where the reference itself is well defined).
+int check_windows(ngmlr_b200_ctx* ctx, const CsState* cs, int n, const uint64_t* start, const char* who) {
+  if (!cs || !cs->enc_bytes || cs->ref_starts.empty())
+    return ctx->fail("%s: call cs_set_reference and set_ref_starts first", who);
+  const auto& rs = cs->ref_starts;
+  for (int i = 0; i < n; ++i) {
+    const uint64_t p = start[i];
+    if (p >= cs->concat_len || p >= rs.back() || p == 0)
+      return ctx->fail("%s: window %d starts outside the reference", who, i);
+    size_t u = std::upper_bound(rs.begin(), rs.end(), (unsigned long long)p) - rs.begin();
+    if (rs[u] - p < 1000ull) ++u;
+    if (u >= rs.size() || p > rs[u] - 1000ull)
+      return ctx->fail("%s: window %d starts behind the end of a contig", who, i);
+  }
+  return 0;
+}
+
+}  // namespace
+
+int ngmlr_b200_decode_windows(ngmlr_b200_ctx* ctx, int n, const uint64_t* start, const int32_t* seq_len,
+                              char* out, const int64_t* out_off) {
+  if (!ctx) return -1;
+  if (n <= 0) return 0;
+  CsState* cs = cs_state(ctx, false);
+  if (check_windows(ctx, cs, n, start, "decode_windows")) return -1;
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  size_t total = 0;
+  for (int i = 0; i < n; ++i) {
+    if (seq_len[i] < 1) return ctx->fail("decode_windows: sequence length %d < 1", seq_len[i]);
+    total += align_up((size_t)seq_len[i], 16);
+  }
+  CU(ctx->h_win.reserve((size_t)n * 3 + 2));
+  CU(ctx->d_win.reserve((size_t)n * 3 + 2));
+  CU(ctx->d_sw_seq.reserve(total + 64));
+  CU(ctx->h_sw_seq.reserve(total + 64));
+  unsigned long long* hw = ctx->h_win.p;
+  int32_t* hl = reinterpret_cast<int32_t*>(hw + 2 * (size_t)n);
+  size_t at = 0;
+  for (int i = 0; i < n; ++i) {
+    hw[i] = start[i];
+    hw[n + i] = at;
+    hl[i] = seq_len[i];
+    hl[n + i] = seq_len[i];
+    at += align_up((size_t)seq_len[i], 16);
+  }
+  CU(cudaMemcpyAsync(ctx->d_win.p, hw, (size_t)n * 24, cudaMemcpyHostToDevice, st));
+  RefDecodeParams rp;
+  rp.enc = cs->d_enc.p;
+  rp.ref_starts = cs->d_ref_starts.p;
+  rp.n_starts = (int)cs->ref_starts.size();
+  rp.n = n;
+  rp.win_start = ctx->d_win.p;
+  rp.out_off = reinterpret_cast<const uint64_t*>(ctx->d_win.p + n);
+  rp.win_len = reinterpret_cast<const int32_t*>(ctx->d_win.p + 2 * (size_t)n);
+  rp.out_span = rp.win_len + n;
+  rp.out = ctx->d_sw_seq.p;
+  CU(launch_decode_windows(rp, st));
+  CU(cudaMemcpyAsync(ctx->h_sw_seq.p, ctx->d_sw_seq.p, total, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  parallel_for(n, 64, [&](int i) { memcpy(out + out_off[i], ctx->h_sw_seq.p + hw[n + i], (size_t)seq_len[i]); });
+  return n;
+}
+
+int ngmlr_b200_convex_upload_windows(ngmlr_b200_ctx* ctx, int n, const uint64_t* on_ref_start,
+                                     const uint64_t* on_ref_stop, const char* const* qrys,
+                                     const int32_t* qry_lens, const int32_t* corridor_offsets,
+                                     const int32_t* corridor_lengths, const int64_t* row_start,
+                                     const int32_t* ext_qstart, const int32_t* ext_qend) {
+  if (!ctx) return -1;
+  if (n < 0) return ctx->fail("convex_upload_windows: n < 0");
+  CsState* cs = cs_state(ctx, false);
+  if (n > 0 && check_windows(ctx, cs, n, on_ref_start, "convex_upload_windows")) return -1;
+  std::vector<int32_t> ref_lens((size_t)std::max(n, 1));
+  for (int i = 0; i < n; ++i) {
+    // extractReferenceSequenceForAlignment: onRefStart >= onRefStop -> no sequence (src/AlignmentBuffer.cpp:204-207)
+    if (on_ref_start[i] >= on_ref_stop[i] || on_ref_stop[i] - on_ref_start[i] > 0x7ffffff0ull)
+      return ctx->fail("convex_upload_windows: window %d is empty or too long", i);
+    ref_lens[i] = (int32_t)(on_ref_stop[i] - on_ref_start[i]);  // strlen of the decoded refSeqLength = stop-start+1 buffer
+  }
+  RefWindows w;
+  w.d_enc = cs ? cs->d_enc.p : nullptr;
+  w.d_ref_starts = cs ? cs->d_ref_starts.p : nullptr;
+  w.n_starts = cs ? (int)cs->ref_starts.size() : 0;
+  w.win_start = on_ref_start;
+  return convex_upload_impl(ctx, n, nullptr, &w, ref_lens.data(), qrys, qry_lens, corridor_offsets,
+                            corridor_lengths, row_start, ext_qstart, ext_qend);
 }
 
 int ngmlr_b200_cs_score_batch(ngmlr_b200_ctx* ctx, int n, const char* const* seqs,

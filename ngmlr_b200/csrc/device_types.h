@@ -125,6 +125,19 @@ struct TraceParams {
   unsigned long long* runs_alloc;
 };
 
+// ---- reference windows (DecodeRefSequenceExact) -------------------------------------------
+struct RefDecodeParams {
+  const uint8_t* enc;                    // binRef
+  const unsigned long long* ref_starts;  // refStartPos: contig starts + one artificial end entry
+  int n_starts;
+  int n;
+  const unsigned long long* win_start;   // startPosition
+  const int32_t* win_len;                // sequenceLength (incl. the NUL)
+  const uint64_t* out_off;               // byte offset of the window in `out`
+  const int32_t* out_span;               // bytes to write: text, NUL, zero padding
+  uint8_t* out;
+};
+
 // ---- candidate search -------------------------------------------------------------------
 struct alignas(16) CsCandidate {
   unsigned long long loc;  // LocationScore::Location.m_Location = ResolveBin(bin)

@@ -39,6 +39,8 @@ struct SwParams {
 cudaError_t launch_sw_score(const SwParams& p, int grid, cudaStream_t stream);
 cudaError_t launch_sw_score_gather(const SwParams& p, int grid, cudaStream_t stream);
 
+cudaError_t launch_decode_windows(const RefDecodeParams& p, cudaStream_t stream);
+
 cudaError_t launch_cs_search(const CsParams& p, bool count_only, cudaStream_t stream);
 cudaError_t launch_unpack_index(const uint8_t* packed, uint32_t n, uint32_t* tab, uint32_t* used_bits,
                                 cudaStream_t stream);

@@ -1,0 +1,76 @@
+// ngmlr_b200/csrc/ref_decode.cu -- reference windows for alignment, decoded on the device (sm_100a).
+//
+// Replaces _SequenceProvider::DecodeRefSequenceExact(sequence, startPosition, sequenceLength, 0)
+// (src/SequenceProvider.cpp:493-565 with decode :475-490 and getChrStart :157-178) as called by
+// AlignmentBuffer::extractReferenceSequenceForAlignment (src/AlignmentBuffer.cpp:203-223): the
+// window [onRefStart, onRefStop] of the 4-bit encoded concatenated genome as characters, 'x' where
+// the window runs past the end of its contig or starts inside the spacer in front of it. decode()
+// writes whole byte pairs, so up to two characters beyond the contig end come out as the spacer's
+// 'N' before the 'x' padding starts -- kept.
+//
+// One CTA per window, one thread per character: pure HBM streaming (0.5 B read, 1 B written per
+// base).
+#include <cuda_runtime.h>
+
+#include "device_types.h"
+#include "kernels.h"
+
+namespace nb {
+
+namespace {
+
+__global__ void __launch_bounds__(256) decode_windows_kernel(const RefDecodeParams p) {
+  const int w = blockIdx.x;
+  const unsigned long long start = p.win_start[w];
+  const int len = p.win_len[w];  // sequenceLength: characters incl. the terminating NUL
+  uint8_t* __restrict__ out = p.out + p.out_off[w];
+  const int padded = p.out_span[w];
+  // getChrStart: first refStartPos entry > position; one further if the position lies in the
+  // 1000-N spacer in front of that contig
+  int u = 0;
+  {
+    int lo = 0, hi = p.n_starts;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (p.ref_starts[mid] > start) hi = mid; else lo = mid + 1;
+    }
+    u = max(1, min(lo, p.n_starts - 1));
+    if (p.ref_starts[u] - start < 1000ull) u = min(u + 1, p.n_starts - 1);
+  }
+  const unsigned long long chr_start = p.ref_starts[u - 1], chr_end = p.ref_starts[u] - 1000ull;
+  const unsigned long long end = start + (unsigned long long)len;
+  const unsigned long long dend = end > chr_end ? chr_end : end;
+  // characters [skip, skip + nwritten) are decoded from position dstart on, the rest stays 'x'
+  unsigned long long dstart = start, skip = 0, nwritten = 0;
+  bool any = true;
+  if (start < chr_start) {
+    skip = chr_start - start;
+    dstart = chr_start;
+    any = dend > chr_start;
+  }
+  if (any) nwritten = (dstart & 1ull) + 2ull * ((dend - dstart + 1ull) / 2ull);
+  for (int i = threadIdx.x; i < padded; i += blockDim.x) {
+    uint8_t c = 0;
+    if (i < len - 1) {
+      c = 'x';
+      const unsigned long long k = (unsigned long long)i - skip;
+      if ((unsigned long long)i >= skip && k < nwritten) {
+        const unsigned long long b = dstart + k;
+        const uint32_t byte = p.enc[b >> 1];
+        const uint32_t c4 = (b & 1ull) ? (byte & 0xFu) : (byte >> 4);
+        c = (uint8_t)((0x4E43475441ull >> (8u * min(c4, 4u))) & 0xffu);  // "ATGCN"
+      }
+    }
+    out[i] = c;
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_decode_windows(const RefDecodeParams& p, cudaStream_t stream) {
+  if (p.n <= 0) return cudaSuccess;
+  decode_windows_kernel<<<p.n, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace nb

@@ -181,6 +181,68 @@ int or_cs_decode(const struct or_cs* h, uint64_t position, uint64_t buffer_len, 
   return 1;
 }
 
+/* _SequenceProvider::getChrStart (src/SequenceProvider.cpp:157-178) over refStartPos (:416-424:
+ * the start of every contig plus one artificial entry last_start + last_len + 1000). */
+static void chr_bounds(const struct or_cs* h, uint64_t position, uint64_t* chr_start, uint64_t* chr_end) {
+  /* std::upper_bound: first entry > position */
+  int n = h->nref + 1, u = 0;
+  while (u < n) {
+    uint64_t v = u < h->nref ? h->ref_start[u] : h->ref_start[h->nref - 1] + h->ref_len[h->nref - 1] + 1000;
+    if (v > position) break;
+    ++u;
+  }
+  uint64_t up = u < h->nref ? h->ref_start[u] : h->ref_start[h->nref - 1] + h->ref_len[h->nref - 1] + 1000;
+  if (up - position < 1000) { /* inside the spacer before the next contig */
+    ++u;
+    up = u < h->nref ? h->ref_start[u] : h->ref_start[h->nref - 1] + h->ref_len[h->nref - 1] + 1000;
+  }
+  *chr_start = h->ref_start[u - 1];
+  *chr_end = up - 1000;
+}
+
+/* _SequenceProvider::decode (src/SequenceProvider.cpp:475-490) */
+static uint64_t decode_range(const struct or_cs* h, uint64_t start_pos, uint64_t end_pos, char* out) {
+  uint64_t ci = 0, start = (start_pos + 1) / 2, n = (end_pos - start_pos + 1) / 2;
+  if (start_pos & 1) out[ci++] = DEC4[h->enc[start - 1] & 0xF];
+  for (uint64_t i = 0; i < n; ++i) {
+    out[ci++] = DEC4[h->enc[start + i] >> 4];
+    out[ci++] = DEC4[h->enc[start + i] & 0xF];
+  }
+  return ci;
+}
+
+/* _SequenceProvider::DecodeRefSequenceExact(sequence, startPosition, sequenceLength, corridor)
+ * (src/SequenceProvider.cpp:493-565), the call extractReferenceSequenceForAlignment makes with
+ * corridor 0 (src/AlignmentBuffer.cpp:215). `out` needs sequence_len + 2 bytes (decode() writes whole
+ * byte pairs and may run up to 2 characters past the requested length, hence the reference's
+ * "+ 100"); bytes [0, sequence_len) are the result, NUL-terminated. Returns 0 for an invalid start. */
+int or_cs_decode_exact(const struct or_cs* h, uint64_t start, uint64_t sequence_len, int corridor, char* out) {
+  if (start >= h->concat_len) return 0;
+  memset(out, 'x', sequence_len);
+  const uint64_t half = (uint64_t)(corridor / 2);
+  uint64_t chr_start, chr_end;
+  chr_bounds(h, start, &chr_start, &chr_end);
+  uint64_t dstart = start - half;
+  const uint64_t end = start + sequence_len - half;
+  uint64_t dend = end;
+  if (end > chr_end) dend -= end - chr_end;
+  if (half > start) {
+    dstart = chr_start;
+    const uint64_t diff = half - dstart + 1000 - (start - chr_start);
+    decode_range(h, dstart, dend, out + diff);
+  } else if (dstart < chr_start) {
+    if (dend > chr_start) {
+      const uint64_t diff = chr_start - dstart;
+      dstart += diff;
+      decode_range(h, dstart, dend, out + diff);
+    }
+  } else {
+    decode_range(h, dstart, dend, out);
+  }
+  out[sequence_len - 1] = 0;
+  return 1;
+}
+
 /* ---- index build --------------------------------------------------------------------------- */
 
 typedef struct {

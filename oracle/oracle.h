@@ -73,6 +73,7 @@ int or_cs_ref_count(const struct or_cs* h);
 uint64_t or_cs_ref_start(const struct or_cs* h, int i);
 const uint8_t* or_cs_encoded(const struct or_cs* h, uint64_t* bytes);
 int or_cs_decode(const struct or_cs* h, uint64_t position, uint64_t buffer_len, char* out);
+int or_cs_decode_exact(const struct or_cs* h, uint64_t start, uint64_t sequence_len, int corridor, char* out);
 int or_cs_build_index(struct or_cs* h, int k, int skip, int bin_shift, int max_freq);
 uint32_t or_cs_index_len(const struct or_cs* h);
 uint32_t or_cs_npos(const struct or_cs* h);

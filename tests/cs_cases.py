@@ -36,3 +36,24 @@ def subreads(n, seed, contigs=None):
         out.append(sub.tobytes())
     out += [b"", b"N" * 40, b"ACGT" * 64, b"A" * 256]
     return out
+
+
+def exact_windows(ref_starts, ref_lens, seed=3, n_random=300):
+    """(start, sequence_len) pairs for DecodeRefSequenceExact(seq, start, sequence_len, 0): inside
+    contigs (odd/even starts and lengths), running over a contig end ('x' padding), starting in the
+    1000-N spacer before a contig. Starts behind a contig end but not within 1000 of the next contig
+    make the reference decode a negative length (it crashes), so they are not part of the contract."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for s0, L in zip(ref_starts, ref_lens):
+        end = s0 + L
+        for st in (s0, s0 + 1, s0 + 2, s0 + 7, max(s0, end - 50), max(s0, end - 51), max(s0 + 1, end - 2), end - 1):
+            for ln in (2, 3, 10, 11, 64, 301):
+                out.append((int(st), int(ln)))
+        for back in (1, 2, 17, 500, 998, 999):      # inside the spacer before the contig
+            for ln in (5, 18, 700, 1301):
+                out.append((int(s0 - back), int(ln)))
+        for _ in range(n_random // len(ref_starts)):
+            st = int(rng.integers(s0, end))
+            out.append((st, int(rng.integers(2, 3000))))
+    return out

@@ -5,7 +5,8 @@ by oracle/Makefile from /root/reference). Run in the build container only:
 
 The vectors pin: (a) ConvexAlignFast::SingleAlign outputs (return value, score bits, CIGAR, MD,
 NM, positions, nmPerPosition checksum, direction-matrix checksum, best cell) for seeded problems
-under three scorings, (b) StrippedSW scores, (c) ScoreBuffer::topNSE candidate order / kept / MQ. Inputs are regenerated from the seeds by
+under three scorings, (b) StrippedSW scores, (c) ScoreBuffer::topNSE candidate order / kept / MQ,
+(d) DecodeRefSequenceExact windows. Inputs are regenerated from the seeds by
 tests/cases.py, so only outputs are stored (plus an input checksum to detect generator drift)."""
 import hashlib
 import json
@@ -84,6 +85,24 @@ def main():
                     "order": [int(v) for v in order] if sc.size <= 24 else None})
     with open(os.path.join(HERE, "score_select_golden.json"), "w") as f:
         json.dump(sel, f)
+    # (d) DecodeRefSequenceExact windows (alignment reference windows) on the cs_cases genome
+    import tempfile
+    import cs_cases
+    from ngmlr_b200 import refindex
+    contigs = cs_cases.genome_contigs()
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "ref.fa")
+        with open(path, "w") as f:
+            for i, c in enumerate(contigs):
+                f.write(f">c{i}\n{c.tobytes().decode()}\n")
+        csref = CsReference(path)
+        enc = refindex.encode_reference(contigs)
+        wins = cs_cases.exact_windows(enc.ref_start, enc.ref_len)
+        dec = [csref.decode_exact(st, ln) for st, ln in wins]
+    with open(os.path.join(HERE, "decode_exact_golden.json"), "w") as f:
+        json.dump({"windows_sha": digest(np.array(wins, dtype=np.int64)), "n": len(wins),
+                   "text_sha": [digest(d) for d in dec],
+                   "samples": [[wins[i][0], wins[i][1], dec[i].decode()] for i in range(0, len(wins), 37) if wins[i][1] <= 64]}, f)
     print("wrote golden vectors:", {k: len(v["records"]) for k, v in out.items()}, len(sw["scores"]))
 
 

@@ -256,6 +256,12 @@ class CsOracle:
         ok = self.lib.or_cs_decode(self.h, C.c_uint64(position), C.c_uint64(buffer_len), buf)
         return buf.value if ok else None
 
+    def decode_exact(self, start, seq_len, corridor=0):
+        """DecodeRefSequenceExact -> bytes before the terminating NUL, or None for an invalid start."""
+        buf = C.create_string_buffer(seq_len + 8)
+        ok = self.lib.or_cs_decode_exact(self.h, C.c_uint64(start), C.c_uint64(seq_len), int(corridor), buf)
+        return buf.raw[:seq_len].split(b"\0")[0] if ok else None
+
     def search(self, seq, sensitivity=0.8, min_kmer_hits=0.0, cap=4096):
         sc = (C.c_float * cap)()
         lo = (C.c_uint64 * cap)()
@@ -323,6 +329,11 @@ class CsReference:
         buf = C.create_string_buffer(buffer_len + 4)
         ok = self.lib.ref_cs_decode(C.c_ulonglong(position), C.c_ulonglong(buffer_len), buf)
         return buf.value if ok else None
+
+    def decode_exact(self, start, seq_len, corridor=0):
+        buf = C.create_string_buffer(seq_len + 128)
+        ok = self.lib.ref_cs_decode_exact(C.c_ulonglong(start), C.c_ulonglong(seq_len), int(corridor), buf)
+        return buf.raw[:seq_len].split(b"\0")[0] if ok else None
 
     def search(self, seq, table_bits=16, cap=4096):
         sc = (C.c_float * cap)()

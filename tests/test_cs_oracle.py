@@ -62,3 +62,26 @@ def test_oracle_equals_whole_reference(contigs, cs_oracle, tmp_path_factory):
             assert ref.search(sub, table_bits=bits) == cs_oracle.search(sub)
     for p in (0, 1, 999, 1000, 1001, 5555, 61000, ref.concat_len - 100, ref.concat_len - 1, ref.concat_len):
         assert ref.decode(p) == cs_oracle.decode(p)
+    # DecodeRefSequenceExact (alignment windows, corridor 0 as in extractReferenceSequenceForAlignment)
+    from ngmlr_b200 import refindex
+    enc = refindex.encode_reference(contigs)
+    wins = cs_cases.exact_windows(enc.ref_start, enc.ref_len)
+    assert len(wins) > 500
+    for st, ln in wins:
+        assert ref.decode_exact(st, ln) == cs_oracle.decode_exact(st, ln), (st, ln)
+    assert ref.decode_exact(ref.concat_len, 10) is None and cs_oracle.decode_exact(ref.concat_len, 10) is None
+    for st, ln, c in ((5000, 100, 12), (5001, 101, 12), (61000, 64, 40)):   # non-zero corridor as well
+        assert ref.decode_exact(st, ln, c) == cs_oracle.decode_exact(st, ln, c)
+
+
+def test_oracle_decode_exact_matches_golden(contigs, cs_oracle):
+    import golden_util as gu
+    from ngmlr_b200 import refindex
+    g = gu.load("decode_exact_golden.json")
+    enc = refindex.encode_reference(contigs)
+    wins = cs_cases.exact_windows(enc.ref_start, enc.ref_len)
+    assert len(wins) == g["n"] and gu.digest(np.array(wins, dtype=np.int64)) == g["windows_sha"], "generator drifted"
+    for (st, ln), sha in zip(wins, g["text_sha"]):
+        assert gu.digest(cs_oracle.decode_exact(st, ln)) == sha, (st, ln)
+    for st, ln, text in g["samples"]:
+        assert cs_oracle.decode_exact(st, ln) == text.encode()

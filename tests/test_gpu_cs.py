@@ -86,3 +86,63 @@ def test_resident_pipeline_equals_one_shot_call(aligner):
             got = [(sc[j], int(lo[j]), int(rv[j]), sw[j]) for j in range(start[i], start[i + 1])]
             assert got == w, i
         assert np.array_equal(mx, wmx)
+
+
+def test_decode_windows_matches_oracle_and_golden(aligner):
+    """DecodeRefSequenceExact on the device: contig interiors, contig ends ('x' padding after the
+    byte-pair overshoot), starts inside a spacer, odd/even positions and lengths."""
+    import golden_util as gu
+    from ngmlr_b200 import refindex
+    contigs = cs_cases.genome_contigs()
+    orc = CsOracle([c.tobytes() for c in contigs])
+    enc = refindex.encode_reference(contigs)
+    aligner.set_reference(enc)
+    wins = cs_cases.exact_windows(enc.ref_start, enc.ref_len)
+    got = aligner.decode_windows([w[0] for w in wins], [w[1] for w in wins])
+    g = gu.load("decode_exact_golden.json")
+    assert len(got) == g["n"]
+    for (st, ln), text, sha in zip(wins, got, g["text_sha"]):
+        assert text == orc.decode_exact(st, ln), (st, ln)
+        assert gu.digest(text) == sha
+    # outside the contract: the call refuses instead of guessing
+    with pytest.raises(RuntimeError):
+        aligner.decode_windows([enc.concat_len + 5], [10])
+    with pytest.raises(RuntimeError):
+        aligner.decode_windows([enc.ref_start[-1] + enc.ref_len[-1] + 300], [10])   # behind the last contig
+    orc.close()
+
+
+def test_align_from_reference_windows_equals_text_upload(aligner):
+    """convex_upload_windows (reference decoded on the device) == convex_upload with the same windows
+    decoded by the oracle: identical alignments incl. CIGAR/MD text."""
+    from ngmlr_b200 import PackedBatch, corridor, refindex, synth
+    contigs = cs_cases.genome_contigs()
+    orc = CsOracle([c.tobytes() for c in contigs])
+    enc = refindex.encode_reference(contigs)
+    aligner.set_reference(enc)
+    rng = np.random.default_rng(11)
+    starts, stops, refs, qrys, offs, lens = [], [], [], [], [], []
+    for k in range(24):
+        c = int(rng.integers(0, 2))
+        L = int(rng.integers(300, 2500))
+        s0 = int(rng.integers(10, contigs[c].size - L - 10)) if k % 6 else contigs[c].size - L   # some end at the contig end
+        read, _ = synth.mutate(contigs[c][s0:s0 + L], rng, err=0.12)
+        on_start = enc.ref_start[c] + s0 - (37 if s0 > 40 else 0)
+        on_stop = enc.ref_start[c] + s0 + L + (53 if k % 6 else 9)   # k % 6 == 0: runs past the contig end
+        text = orc.decode_exact(on_start, on_stop - on_start + 1)
+        assert len(text) == on_stop - on_start
+        o, l = corridor.corridor_endpoints(len(read), len(text), corridor.estimate_corridor(len(read), len(text)), realign=True)
+        starts.append(on_start); stops.append(on_stop); refs.append(text); qrys.append(read.tobytes())
+        offs.append(o); lens.append(l)
+    batch = PackedBatch(refs, qrys, offs, lens)
+    aligner.upload(batch)
+    aligner.run()
+    want = [r.as_dict() for r in aligner.fetch()]
+    aligner.upload_windows(batch, starts, stops)
+    aligner.run()
+    got = [r.as_dict() for r in aligner.fetch()]
+    from oracle_lib import same_alignment
+    for a, b in zip(want, got):
+        assert same_alignment(a, b) == []
+    assert sum(1 for r in want if r["ret"] > 0) >= 20
+    orc.close()
