@@ -355,7 +355,7 @@ def main():
             al.cs_run()
         al.run()
     barrier()
-    fill_ms, tb_ms, cp_ms, cs_ms = [], [], [], []
+    fill_ms, tb_ms, cs_ms = [], [], []
     n_cand = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(streams[0])
@@ -366,7 +366,6 @@ def main():
         st = al.stats()
         fill_ms.append(st["fill_ms"])
         tb_ms.append(st["traceback_ms"])
-        cp_ms.append(st["compact_ms"])
     e1.record(streams[0])
     torch.cuda.synchronize(dev)
     solo_ms = e0.elapsed_time(e1)
@@ -512,7 +511,6 @@ def main():
                          "note": "ALU-pipe-bound kernel (~27 ALU-pipe SASS instr per 32-cell step, 2 cycles each "
                                  "per SMSP, DESIGN.md 4.1); HBM frac is structurally ~0.02"},
             "kernel_ms_per_step": {"fill": float(np.mean(fill_ms)), "traceback": float(np.mean(tb_ms)),
-                                   "compact": float(np.mean(cp_ms)),
                                    "stage02_cs_vote_decode_score": float(np.mean(cs_ms))},
             "stage02": {"subreads_per_step_per_gpu": subreads.n, "candidates_per_step_per_gpu": int(n_cand),
                         "sw_cell_updates_per_step_per_gpu": int(n_cand) * 257 * 307,

@@ -71,7 +71,8 @@ typedef struct {
   int64_t seq_bytes;        /* sequence bytes staged */
   int64_t path_steps;       /* traceback steps */
   int64_t cigar_runs;       /* binary CIGAR runs emitted */
-  float fill_ms, traceback_ms, compact_ms; /* CUDA-event durations on the context's stream */
+  float fill_ms, traceback_ms, compact_ms; /* CUDA-event durations on the context's stream; compact_ms
+                                            * is 0 (compaction is part of the traceback kernel) */
   int32_t fill_launches, traceback_launches, compact_launches;
   int64_t h2d_bytes, d2h_bytes;
   /* host wall-clock of the last upload / run / fetch phases (ms) */
@@ -114,7 +115,7 @@ int ngmlr_b200_convex_align_batch(ngmlr_b200_ctx* ctx, int n, const char* const*
 /* The same work split into its three phases, so that benchmarks can time the kernels with the
  * inputs already resident in HBM:
  *   upload : pack + H2D (no kernels)
- *   run    : fill -> traceback -> compact kernels on resident inputs (no host<->device copies
+ *   run    : fill -> traceback (+ CIGAR compaction) kernels on resident inputs (no host<->device copies
  *            except the 16-byte allocation counters); may be called repeatedly on one upload
  *   fetch  : D2H of the binary CIGARs + host CIGAR/MD text, fills results[n] */
 int ngmlr_b200_convex_upload(ngmlr_b200_ctx* ctx, int n, const char* const* refs,

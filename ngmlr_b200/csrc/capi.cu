@@ -2,7 +2,7 @@
 //
 // Owns the device arenas (sequences, corridor rows, descriptors, direction arena, traceback
 // strips), the pinned staging buffers and the stream; packs a batch of SingleAlign problems,
-// launches fill -> traceback -> compact, and turns the binary CIGARs into the reference's `Align`
+// launches fill -> traceback (which also compacts the binary CIGARs), and turns the binary CIGARs into the reference's `Align`
 // fields. There is no CPU compute path: every entry point needs a CUDA device.
 #include <cuda_runtime.h>
 #include <math.h>
@@ -703,14 +703,11 @@ int ngmlr_b200_convex_run(ngmlr_b200_ctx* ctx) {
     CU(cudaEventRecord(ctx->ev[1], st));
     CU(launch_convex_traceback(tp, st));
     CU(cudaEventRecord(ctx->ev[2], st));
-    CU(launch_convex_compact(tp, st));
-    CU(cudaEventRecord(ctx->ev[3], st));
     CU(cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, 4 * sizeof(unsigned long long),
                        cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     ctx->stats.fill_launches++;
     ctx->stats.traceback_launches++;
-    ctx->stats.compact_launches++;
     const unsigned long long dir_used = ctx->h_counters.p[0], runs_used = ctx->h_counters.p[1];
     bool again = false;
     if (dir_used > ctx->d_dir.cap) {
@@ -735,8 +732,7 @@ int ngmlr_b200_convex_run(ngmlr_b200_ctx* ctx) {
   ctx->stats.fill_ms = ms;
   cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]);
   ctx->stats.traceback_ms = ms;
-  cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
-  ctx->stats.compact_ms = ms;
+  ctx->stats.compact_ms = 0.0f;  // compaction is fused into the traceback kernel (fields kept for ABI stability)
   ctx->stats.dir_bytes = (int64_t)ctx->dir_used * 4;
   ctx->stats.cigar_runs = (int64_t)ctx->runs_used;
   ctx->stats.host_run_ms = (float)(now_ms() - t_run0);

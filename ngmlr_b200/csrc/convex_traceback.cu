@@ -295,8 +295,4 @@ cudaError_t launch_convex_traceback(const TraceParams& p, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_convex_compact(const TraceParams&, cudaStream_t) {
-  return cudaSuccess;  // compaction is fused into the traceback kernel
-}
-
 }  // namespace nb

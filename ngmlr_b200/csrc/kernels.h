@@ -14,7 +14,6 @@ cudaError_t launch_convex_fill(const FillParams& p, bool raw, bool team, int gri
 int fill_max_ctas_per_sm(bool raw, bool team);
 
 cudaError_t launch_convex_traceback(const TraceParams& p, cudaStream_t stream);
-cudaError_t launch_convex_compact(const TraceParams& p, cudaStream_t stream);
 
 // StrippedSW score-only kernel: one warp per (ref, qry) pair.
 struct SwParams {
