@@ -148,6 +148,19 @@ def test_both_fill_schedules_are_bit_exact(aligner, oracle, team):
         aligner.force_team(-1)
 
 
+@pytest.mark.parametrize("team", [0, 1])
+def test_fill_grid_cap_does_not_change_results(aligner, oracle, team):
+    """ngmlr_b200_set_fill_ctas_per_sm: a persistent grid of 1 CTA per SM (every CTA walks many
+    problems) gives the same matrices as full occupancy."""
+    aligner.force_team(team)
+    aligner.set_fill_ctas_per_sm(1)
+    try:
+        _compare_batch(aligner, oracle, cases.random_problems(300, 909, max_len=400), check_dirs=True)
+    finally:
+        aligner.set_fill_ctas_per_sm(0)
+        aligner.force_team(-1)
+
+
 def test_direction_arena_overflow_is_recovered(aligner, oracle):
     """The fill kernel bump-allocates its direction words; a too-small arena must be detected,
     grown and the batch re-run -- results unchanged."""
