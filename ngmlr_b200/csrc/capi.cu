@@ -343,6 +343,27 @@ int ngmlr_b200_set_fill_ctas_per_sm(ngmlr_b200_ctx* ctx, int v) {
   return 0;
 }
 
+// Test hook (host only, no context): the CIGAR/MD/nmPerPosition text stage on a given binary CIGAR.
+// Outputs: ints[0..11] = ret, qstart, qend, nm, alignment_length, cigar_op_count, sv_type, first_ref,
+// first_read, last_ref, last_read, nm_count (triples); *identity; cigar/md NUL-terminated (truncated
+// to the caps); nm_out receives min(3 * nm_count, nm_cap) ints. Returns 1, or 0 where the reference throws.
+int ngmlr_b200_debug_cigar_text(const int32_t* runs, int n_runs, const char* ref, int ref_len, int ref_position,
+                                int ext_qstart, int ext_qend, int32_t* ints, float* identity, char* cigar,
+                                int cigar_cap, char* md, int md_cap, int32_t* nm_out, int nm_cap) {
+  AlignText t;
+  t.nm_positions.assign(7, -1);  // stale content of a reused buffer must not leak into the result
+  const bool ok = binary_cigar_to_text(runs, n_runs, ref, ref_len, ref_position, ext_qstart, ext_qend, t);
+  const int v[12] = {t.ret, t.qstart, t.qend, t.nm, t.alignment_length, t.cigar_op_count, t.sv_type, t.first_ref,
+                     t.first_read, t.last_ref, t.last_read, (int)(t.nm_positions.size() / 3)};
+  memcpy(ints, v, sizeof(v));
+  *identity = t.identity;
+  snprintf(cigar, (size_t)cigar_cap, "%s", t.cigar.c_str());
+  snprintf(md, (size_t)md_cap, "%s", t.md.c_str());
+  const size_t n = std::min(t.nm_positions.size(), (size_t)std::max(nm_cap, 0));
+  if (n) memcpy(nm_out, t.nm_positions.data(), n * sizeof(int32_t));
+  return ok ? 1 : 0;
+}
+
 // force_team: -1 auto, 0 one warp per problem, 1 four-warp teams. Test / tuning hook.
 int ngmlr_b200_set_force_team(ngmlr_b200_ctx* ctx, int v) {
   if (!ctx) return -1;

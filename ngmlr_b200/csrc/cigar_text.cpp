@@ -55,10 +55,12 @@ bool binary_cigar_to_text(const int32_t* runs, int n_runs, const char* ref, int 
   // reuse the caller's buffers (capacity survives across batches)
   out.cigar.clear();
   out.md.clear();
-  out.nm_positions.clear();
   out.ret = -1;
   out.sv_type = 0;
-  if (n_runs < 2) return false;
+  if (n_runs < 2) {
+    out.nm_positions.clear();
+    return false;
+  }
   const char* aref = ref + ref_position;  // convertCigar receives refSeq + ref_position (:489)
   std::string& cg = out.cigar;
   std::string& md = out.md;
@@ -80,11 +82,21 @@ bool binary_cigar_to_text(const int32_t* runs, int n_runs, const char* ref, int 
   int matches = 0, columns = 0, exact = 0;
   int pending_m = 0, md_run = 0, ri = 0;
   ErrorWindow win;
+  // nmPerPosition records are written through a raw pointer into a buffer sized for every
+  // alignment column (the hot loop of this stage: 12 bytes per column)
+  {
+    size_t cols = 0;
+    for (int j = 1; j < n_runs - 1; ++j)
+      if ((runs[j] & 15) != OP_I) cols += (size_t)(runs[j] >> 4);
+    out.nm_positions.resize(cols * 3);  // not cleared first: only growth is zero-filled, every kept record is rewritten
+  }
+  int32_t* np = out.nm_positions.data();
   auto note = [&](int pr, int pq) {  // addPosition (:76-99)
     if (pq > 16 && pr > 16) {
-      out.nm_positions.push_back(pr - 16);
-      out.nm_positions.push_back(pq - 16);
-      out.nm_positions.push_back(win.level);
+      np[0] = pr - 16;
+      np[1] = pq - 16;
+      np[2] = win.level;
+      np += 3;
     }
   };
   auto flush_m = [&]() {
@@ -112,18 +124,32 @@ bool binary_cigar_to_text(const int32_t* runs, int n_runs, const char* ref, int 
           ++pos_read;
         }
         break;
-      case OP_EQ:
+      case OP_EQ: {
         pending_m += n;
         md_run += n;
         matches += n;
-        for (int k = 0; k < n; ++k) {
+        int k = 0;
+        // while error bits are still sliding out of the 32-event window, or the positions have not
+        // passed the 16-base margin, go column by column
+        for (; k < n && (win.bits != 0u || pos_ref <= 16 || pos_read <= 16); ++k) {
           win.match();
           note(pos_ref, pos_read);
           ++pos_ref;
           ++pos_read;
         }
+        // then the window is empty and stays empty: level 0 for the rest of the run
+        win.level = k < n ? 0 : win.level;
+        for (; k < n; ++k) {
+          np[0] = pos_ref - 16;
+          np[1] = pos_read - 16;
+          np[2] = 0;
+          np += 3;
+          ++pos_ref;
+          ++pos_read;
+        }
         ri += n;
         break;
+      }
       case OP_D:
         flush_m();
         put_op(cg, n, 'D', ops);
@@ -145,9 +171,11 @@ bool binary_cigar_to_text(const int32_t* runs, int n_runs, const char* ref, int 
         pos_read += n;
         break;
       default:
+        out.nm_positions.clear();
         return false;  // "Invalid cigar string" -> throw 1 (:272-274)
     }
   }
+  out.nm_positions.resize((size_t)(np - out.nm_positions.data()));
   put_int(md, md_run);
   flush_m();
   out.qend = trail + ext_qend;

@@ -6,7 +6,8 @@
  *
  * Parity status: PINNED. Every function here is checked against the unmodified reference
  * compiled from /root/reference (oracle/_ref/libngmlr_ref.so, built by oracle/Makefile) in
- * tests/test_oracle_vs_reference.py, and against the committed golden vectors that library
+ * tests/test_oracle.py and tests/test_cs_oracle.py (the whole-reference library oracle/_ref/libngmlr_full.so for the
+ * candidate search, window decoding and candidate selection), and against the committed golden vectors that library
  * produced (tests/golden/, generator tests/golden/make_golden.py).
  */
 #ifndef NGMLR_B200_ORACLE_H

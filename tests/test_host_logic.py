@@ -67,3 +67,107 @@ def test_select_candidates_matches_oracle_and_golden(oracle):
     # empty batch
     o2, k2, m2 = select_candidates(np.zeros(1, np.int64), np.zeros(0, np.float32))
     assert o2.size == 0 and k2.size == 0 and m2.size == 0
+
+
+def _text_stage_simple(runs, ref, ref_position, ext_qs, ext_qe):
+    """Column-by-column restatement of convertCigar's bookkeeping (src/ConvexAlignFast.cpp:112-333):
+    CIGAR with EQ/X merged into M, MD, NM, and the nmPerPosition triples {ref-16, read-16, errors in
+    the last 32 alignment events} recorded once both positions passed 16 (addPosition :76-99)."""
+    lead, trail = runs[0] >> 4, runs[-1] >> 4
+    cig, md, nm_pos = [], [], []
+    qstart = lead + ext_qs
+    if qstart > 0:
+        cig.append(f"{qstart}S")
+    pos_ref, pos_read, ri = 0, lead, ref_position
+    bits, level = 0, 0
+    pend, md_run, matches, cols = 0, 0, 0, 0
+
+    def note():
+        if pos_read > 16 and pos_ref > 16:
+            nm_pos.extend((pos_ref - 16, pos_read - 16, level))
+
+    for r in runs[1:-1]:
+        op, n = r & 15, r >> 4
+        cols += n
+        if op in (7, 8):
+            pend += n
+            for _ in range(n):
+                if op == 8:
+                    md.append(f"{md_run}{chr(ref[ri])}")
+                    md_run = 0
+                    bits = ((bits << 1) | 1) & 0xFFFFFFFF
+                else:
+                    md_run += 1
+                    matches += 1
+                    bits = (bits << 1) & 0xFFFFFFFF
+                level = bin(bits).count("1")
+                ri += 1
+                note()
+                pos_ref += 1
+                pos_read += 1
+        else:
+            if pend:
+                cig.append(f"{pend}M")
+                pend = 0
+            cig.append(f"{n}{'D' if op == 2 else 'I'}")
+            if op == 2:
+                md.append(f"{md_run}^")
+                md_run = 0
+            for k in range(n):
+                bits = (bits << 1) & 0xFFFFFFFF
+                if k == 0:
+                    bits |= 1
+                    level = max(level + 1, 0)
+                if op == 2:
+                    md.append(chr(ref[ri]))
+                    ri += 1
+                    note()
+                    pos_ref += 1
+            if op == 1:
+                pos_read += n
+    md.append(str(md_run))
+    if pend:
+        cig.append(f"{pend}M")
+    qend = trail + ext_qe
+    if qend > 0:
+        cig.append(f"{qend}S")
+    return "".join(cig), "".join(md), cols - matches, nm_pos, pos_ref, pos_read
+
+
+def test_text_stage_fast_paths_equal_column_by_column_version():
+    """binary_cigar_to_text writes the nmPerPosition triples of long match runs in bulk once the
+    32-event error window is empty; compare with the column-by-column bookkeeping on random CIGARs
+    (short and very long match runs, indel runs, leading positions below the 16-base margin)."""
+    import ctypes as C
+    from ngmlr_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(8)
+    for case in range(300):
+        runs, ref_need = [int(rng.integers(0, 40)) << 4 | 4], 0
+        last = None
+        for _ in range(int(rng.integers(1, 60))):
+            op = int(rng.choice([7, 7, 7, 8, 1, 2]))
+            if op == last:
+                continue
+            n = int(rng.choice([1, 2, 3, 5, 17, 31, 32, 33, 40, 100, 700])) if op == 7 else int(rng.integers(1, 6))
+            runs.append(n << 4 | op)
+            if op != 1:
+                ref_need += n
+            last = op
+        runs.append(int(rng.integers(0, 30)) << 4 | 4)
+        ref_position = int(rng.integers(0, 5))
+        ref = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, ref_position + ref_need + 8)].tobytes()
+        ext_qs, ext_qe = int(rng.integers(0, 3)), int(rng.integers(0, 3))
+        arr = np.array(runs, dtype=np.int32)
+        ints = (C.c_int32 * 12)()
+        ident = C.c_float()
+        cig, md = C.create_string_buffer(1 << 16), C.create_string_buffer(1 << 16)
+        nm = np.zeros(3 * (ref_need + 8), dtype=np.int32)
+        ok = lib.ngmlr_b200_debug_cigar_text(arr.ctypes.data_as(C.c_void_p), len(runs), ref, len(ref), ref_position,
+                                             ext_qs, ext_qe, ints, C.byref(ident), cig, 1 << 16, md, 1 << 16,
+                                             nm.ctypes.data_as(C.c_void_p), int(nm.size))
+        assert ok == 1
+        w_cig, w_md, w_nm, w_pos, w_lr, w_lq = _text_stage_simple(runs, ref, ref_position, ext_qs, ext_qe)
+        assert cig.value.decode() == w_cig and md.value.decode() == w_md, case
+        assert ints[3] == w_nm and ints[9] == w_lr and ints[10] == w_lq
+        assert ints[11] * 3 == len(w_pos) and list(nm[:len(w_pos)]) == w_pos, case
