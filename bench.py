@@ -110,6 +110,9 @@ class CpuStage02:
                 lib.ref_full_ssw_create.restype = C.c_void_p
                 lib.ref_full_ssw_score.restype = C.c_float
                 lib.ref_full_ssw_score.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+                self.fast = hasattr(lib, "ref_stage02_read")   # the whole per-read loop in C (no GIL between calls)
+                if self.fast:
+                    lib.ref_stage02_read.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int]
                 self.lib = lib
                 self.kind = "reference"
                 os.unlink(fasta)
@@ -129,6 +132,8 @@ class CpuStage02:
     def read(self, st, qry):
         """All sub-reads of one read: vote, then score every candidate. Returns #candidates."""
         C = self.C
+        if self.kind == "reference" and self.fast:
+            return self.lib.ref_stage02_read(st[0], st[1], bytes(qry), len(qry), 256, 20, 308)
         n_c = 0
         for k in range(len(qry) // 256):
             sub = qry[k * 256:(k + 1) * 256]
@@ -154,12 +159,28 @@ class CpuStage02:
         return n_c
 
 
+def tune_malloc_for_threads():
+    """The reference allocates its multi-megabyte direction matrix per SingleAlign call; with glibc's
+    defaults every such allocation is an mmap/munmap pair and the threads of one process serialise on
+    the kernel's address-space lock (measured here: 4 threads = 1.0x one thread). Keeping large blocks
+    in per-thread arenas lets the CPU arm scale with the host threads -- the faster, fairer baseline."""
+    import ctypes as C
+    try:
+        libc = C.CDLL("libc.so.6")
+        libc.mallopt(C.c_int(-3), C.c_int(1 << 30))    # M_MMAP_THRESHOLD
+        libc.mallopt(C.c_int(-1), C.c_int(1 << 30))    # M_TRIM_THRESHOLD
+        libc.mallopt(C.c_int(-8), C.c_int(256))        # M_ARENA_MAX
+    except OSError:
+        pass
+
+
 def cpu_reference_run(problems, threads, impl, stage02=None):
     """Run problems through the CPU implementation on `threads` host threads (ctypes releases the
     GIL). impl: 'reference' = oracle/_ref (unmodified ConvexAlignFast), 'port' = oracle C port.
     stage02: CpuStage02 or None (stage 4 only)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
+    tune_malloc_for_threads()
     work = list(range(len(problems)))
     lock = threading.Lock()
     engines = [(oracle_lib.Reference() if impl == "reference" else oracle_lib.Oracle(),
@@ -240,14 +261,15 @@ def main():
         kind = cpu_impl_kind()
         genome = synth.random_genome(int(args.genome_mb * 1e6), 1)
         threads = cores
-        # bounded sample: ~2 reads per thread per step keeps a K+W run within minutes
-        n = args.cpu_sample or max(threads, min(args.reads, 2 * threads))
+        # bounded sample: ~8 reads per thread per step (dynamic scheduling evens out the read lengths) keeps a
+        # K+W run within minutes
+        n = args.cpu_sample or max(threads, min(args.reads, 8 * threads))
         pool = make_pool(genome, n, seed=2)
         bases = sum(len(p.qry) for p in pool)
         cells = sum(p.cells for p in pool)
         st02 = None if args.dp_only else CpuStage02(genome)
-        for _ in range(min(args.warmup, 1)):
-            cpu_reference_run(pool[:threads], threads, kind, st02)
+        for _ in range(max(1, min(args.warmup, 1))):   # grows the per-thread malloc arenas, warms the caches
+            cpu_reference_run(pool, threads, kind, st02)
         times = [cpu_reference_run(pool, threads, kind, st02) for _ in range(args.steps)]
         t = float(np.sum(times))
         val = bases * args.steps / t / 1e9
@@ -532,9 +554,10 @@ def main():
         try:
             kind = cpu_impl_kind()
             threads = cores
-            n = args.cpu_sample or max(threads, min(len(pool), 2 * threads))
+            n = args.cpu_sample or max(threads, min(len(pool), 8 * threads))
             sample = pool[:n]
             st02 = None if args.dp_only else CpuStage02(genome)
+            cpu_reference_run(sample, threads, kind, st02)   # warm-up: per-thread malloc arenas, caches
             t = cpu_reference_run(sample, threads, kind, st02)
             sb = sum(len(p.qry) for p in sample)
             sc = sum(p.cells for p in sample)

@@ -223,4 +223,47 @@ int ref_cs_search_p(void* probe_, const char* seq, int len, int table_bits, floa
   return n < 0 ? -1 : m;
 }
 
+// Stage 0/2 of one read entirely inside the reference's code (used by bench.py's CPU arm so that no
+// Python runs between the calls): every 256-bp sub-read through the CS vote (src/CS.cpp:324-398),
+// every candidate through DecodeRefSequence (src/ScoreBuffer.cpp:110-116) and StrippedSW::SingleScore.
+// Returns the number of candidates scored.
+int ref_stage02_read(void* probe, void* ssw, const char* qry, int len, int part_len, int half_corridor,
+                     int ref_max_len) {
+  float scores[512];
+  unsigned long long locs[512];
+  int reverse[512];
+  float mh = 0.0f;
+  std::vector<char> buf((size_t)ref_max_len + 8), fwd((size_t)part_len + 1), rev((size_t)part_len + 1);
+  int n_cand = 0;
+  for (int k = 0; k + part_len <= len; k += part_len) {
+    memcpy(fwd.data(), qry + k, (size_t)part_len);
+    fwd[part_len] = 0;
+    const int n = ref_cs_search_p(probe, fwd.data(), part_len, 16, scores, locs, reverse, 512, &mh);
+    bool have_rev = false;
+    for (int j = 0; j < n && j < 512; ++j) {
+      if (!SequenceProvider.DecodeRefSequence(buf.data(), 0, locs[j] - (unsigned long long)half_corridor,
+                                              (unsigned long long)ref_max_len)) {
+        memset(buf.data(), 'N', (size_t)ref_max_len);
+        buf[ref_max_len] = 0;
+      }
+      const char* q = fwd.data();
+      if (reverse[j]) {
+        if (!have_rev) {  // MappedRead::computeReverseSeq: complement, reversed
+          for (int i = 0; i < part_len; ++i) {
+            const char c = fwd[part_len - 1 - i];
+            rev[i] = c == 'A' ? 'T' : (c == 'T' ? 'A' : (c == 'C' ? 'G' : (c == 'G' ? 'C' : c)));
+          }
+          rev[part_len] = 0;
+          have_rev = true;
+        }
+        q = rev.data();
+      }
+      float r = -1.0f;
+      static_cast<StrippedSW*>(ssw)->SingleScore(0, 0, buf.data(), q, r, 0);
+      ++n_cand;
+    }
+  }
+  return n_cand;
+}
+
 }  // extern "C"
