@@ -547,7 +547,9 @@ def main():
                     "note": f"each of the {S} contexts takes every {S}-th read of the batch per step"},
             "solo": {"gbp_per_s": bases * args.steps / (solo_ms * 1e-3) / 1e9, "ms_per_step": solo_ms / args.steps,
                      "note": "one context alone on the whole batch, same K steps (kernels not overlapped)"},
-            "gpu_launches": 14 * S * args.steps,
+            # per context and step: cs count, sizes, 4 x (scan init + scan), vote, count widening, compaction,
+            # window decode + score, fill, traceback = 16 kernels (2 with --dp-only); profiles/launches_r01_fullpath.csv
+            "gpu_launches": (2 if args.dp_only else 16) * S * args.steps,
             "clocks": clocks,
         }
         # CPU baseline on this box's host cores, bounded sample of the same workload
