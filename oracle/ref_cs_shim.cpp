@@ -127,6 +127,25 @@ int ref_cs_init(const char* fasta) {
   return 0;
 }
 
+// Same, but lets the reference write its on-disk caches next to the FASTA file
+// (<fasta>-enc.2.ngm, src/SequenceProvider.cpp:250-272; <fasta>-ht-13-2.2.ngm, src/PrefixTable.cpp:534-567).
+int ref_cs_init_save(const char* fasta) {
+  IConfig* c = new IConfig();
+  c->referenceFile = strdup(fasta);
+  c->queryFile = strdup(fasta);
+  c->outputFile = strdup("/dev/null");
+  c->skipSave = false;
+  c->progress = false;
+  _config = c;
+  _Log::Init(0, 0);
+  _log = &Log;
+  CS::Init();
+  SequenceProvider.Init();
+  g_table = new CompactPrefixTable();
+  g_probe = new CSProbe();
+  return 0;
+}
+
 unsigned long long ref_cs_concat_len() { return SequenceProvider.GetConcatRefLen(); }
 int ref_cs_ref_count() { return SequenceProvider.GetRefCount(); }
 unsigned long long ref_cs_ref_start(int n) { return SequenceProvider.GetRefStart(n); }

@@ -85,3 +85,61 @@ def test_oracle_decode_exact_matches_golden(contigs, cs_oracle):
         assert gu.digest(cs_oracle.decode_exact(st, ln)) == sha, (st, ln)
     for st, ln, text in g["samples"]:
         assert cs_oracle.decode_exact(st, ln) == text.encode()
+
+
+def test_cache_files_round_trip(contigs, tmp_path):
+    """ngmfiles: what is written is read back identically (always runnable)."""
+    from ngmlr_b200 import ngmfiles, refindex
+    ref = refindex.encode_reference(contigs)
+    idx = refindex.build_index(ref)
+    ngmfiles.write_encoded_reference(str(tmp_path / "r-enc.2.ngm"), ref, skipped_lens=[8])
+    ngmfiles.write_index(str(tmp_path / "r-ht-13-2.2.ngm"), idx)
+    ref2, names = ngmfiles.read_encoded_reference(str(tmp_path / "r-enc.2.ngm"))
+    assert np.array_equal(ref2.enc, ref.enc) and ref2.concat_len == ref.concat_len
+    assert ref2.ref_start == ref.ref_start and ref2.ref_len == ref.ref_len and names[0] == "c0"
+    idx2, skip, off = ngmfiles.read_index(str(tmp_path / "r-ht-13-2.2.ngm"))
+    assert (idx2.k, skip, off) == (13, 2, 0)
+    assert np.array_equal(idx2.tab, idx.tab) and np.array_equal(idx2.rci, idx.rci) and np.array_equal(idx2.pos, idx.pos)
+    with open(tmp_path / "bad.ngm", "wb") as f:
+        f.write(b"\0" * 64)
+    with pytest.raises(ValueError):
+        ngmfiles.read_index(str(tmp_path / "bad.ngm"))
+
+
+@pytest.mark.skipif(not CsReference.available(), reason="oracle/_ref/libngmlr_full.so not built")
+def test_cache_files_are_byte_compatible_with_the_reference(contigs, tmp_path):
+    """The UNMODIFIED reference writes <fasta>-enc.2.ngm and <fasta>-ht-13-2.2.ngm (in a subprocess:
+    its singletons initialise once per process); ngmfiles reads them into the arrays refindex builds,
+    and writes the same bytes (the index file entirely; the encoded reference up to the end of the used
+    part of binRef -- the reference writes its uninitialised allocation tail)."""
+    import subprocess
+    import sys
+    from ngmlr_b200 import ngmfiles, refindex
+    fasta = str(tmp_path / "ref.fa")
+    with open(fasta, "w") as f:
+        for i, c in enumerate(contigs):
+            f.write(f">contig{i} some description\n{c.tobytes().decode()}\n")
+    code = ("import ctypes, sys; lib = ctypes.CDLL(sys.argv[1]); "
+            "sys.exit(lib.ref_cs_init_save(sys.argv[2].encode()))")
+    run = subprocess.run([sys.executable, "-c", code, CsReference.PATH, fasta], capture_output=True, text=True,
+                         timeout=600)
+    assert run.returncode == 0, run.stderr[-2000:]
+    enc_path, idx_path = fasta + "-enc.2.ngm", fasta + "-ht-13-2.2.ngm"
+    ref = refindex.encode_reference(contigs)
+    idx = refindex.build_index(ref)
+    got_ref, names = ngmfiles.read_encoded_reference(enc_path)
+    assert np.array_equal(got_ref.enc, ref.enc) and got_ref.concat_len == ref.concat_len
+    assert got_ref.ref_start == ref.ref_start and got_ref.ref_len == ref.ref_len
+    assert names == [f"contig{i}" for i in range(len(contigs)) if contigs[i].size > 10]
+    got_idx, skip, off = ngmfiles.read_index(idx_path)
+    assert (got_idx.k, skip, off) == (13, 2, 0)
+    assert np.array_equal(got_idx.tab, idx.tab) and np.array_equal(got_idx.rci, idx.rci)
+    assert np.array_equal(got_idx.pos, idx.pos)
+    # writers: same bytes
+    ngmfiles.write_index(str(tmp_path / "mine-ht.ngm"), idx)
+    assert open(tmp_path / "mine-ht.ngm", "rb").read() == open(idx_path, "rb").read()
+    skipped = [int(c.size) for c in contigs if not c.size > 10]
+    ngmfiles.write_encoded_reference(str(tmp_path / "mine-enc.ngm"), ref, names, skipped_lens=skipped)
+    mine, theirs = open(tmp_path / "mine-enc.ngm", "rb").read(), open(enc_path, "rb").read()
+    defined = 24 + 128 * len(ref.ref_start) + int(ref.enc.size)
+    assert len(mine) == len(theirs) and mine[:defined] == theirs[:defined]
