@@ -9,9 +9,14 @@
 //     SingleScore (StrippedSW, src/StrippedSW.cpp:118-202); GetScoreBatchSize() = 1024 like
 //     StrippedSW.h:53-55.
 // Argument meaning, buffer ownership and error behaviour follow SURVEY.md section 8(b).
+#include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
+#include <condition_variable>
 #include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/ngmlr_b200.h"
@@ -35,6 +40,19 @@ std::vector<ParkedContext> g_pool;
 bool same_scoring(const ngmlr_b200_scoring& a, const ngmlr_b200_scoring& b) {
   return memcmp(&a, &b, sizeof(a)) == 0;
 }
+
+// One SingleAlign call parked in the cross-thread batcher (below).
+struct AlignRequest {
+  char const* ref;
+  char const* qry;
+  Align* result;
+  NgmlrB200BatchAlignArgs args;
+  int ret = -1;
+  bool threw = false, done = false;
+  const char* error = nullptr;
+};
+class B200Alignment;
+bool batcher_submit(int gpu_id, const ngmlr_b200_scoring& scoring, AlignRequest& r);
 
 class B200Alignment : public IAlignment {
  public:
@@ -92,8 +110,21 @@ class B200Alignment : public IAlignment {
                   char const* const refSeq, char const* const qrySeq, Align& result,
                   int const externalQStart, int const externalQEnd, void*) override {
     NgmlrB200BatchAlignArgs a = {corridor, corridorHeight, externalQStart, externalQEnd};
+    if (corridorHeight >= (int)strlen(qrySeq)) {  // (a malformed call keeps the direct path and its throw)
+      AlignRequest req;
+      req.ref = refSeq;
+      req.qry = qrySeq;
+      req.result = &result;
+      req.args = a;
+      if (batcher_submit(gpu_id_, scoring_, req)) {  // false: batching is off -> direct path below
+        if (req.error) throw req.error;
+        if (req.threw) throw 1;
+        return req.ret;
+      }
+    }
     int ret = -1;
-    align_many(1, &refSeq, &qrySeq, &result, &a, &ret);
+    Align* rp = &result;
+    align_many(1, &refSeq, &qrySeq, &rp, &a, &ret, nullptr);
     return ret;
   }
 
@@ -104,15 +135,19 @@ class B200Alignment : public IAlignment {
     if (batchSize <= 0) return 0;
     if (!extData) throw "BatchAlign: extData must point to NgmlrB200BatchAlignArgs[batchSize]";
     std::vector<int> rets(batchSize);
-    align_many(batchSize, refSeqList, qrySeqList, results,
-               static_cast<NgmlrB200BatchAlignArgs*>(extData), rets.data());
+    std::vector<Align*> rp(batchSize);
+    for (int i = 0; i < batchSize; ++i) rp[i] = results + i;
+    align_many(batchSize, refSeqList, qrySeqList, rp.data(),
+               static_cast<NgmlrB200BatchAlignArgs*>(extData), rets.data(), nullptr);
     // A failed problem is reported exactly like SingleAlign does: Score == -1.0f.
     return batchSize;
   }
 
- private:
-  void align_many(int n, char const* const* refs, char const* const* qrys, Align* results,
-                  NgmlrB200BatchAlignArgs* args, int* rets) {
+  // n problems through one batched call; results[i] is the caller's Align of problem i. threw_out
+  // (optional) receives which problems the reference would have thrown on; without it a throwing
+  // single problem throws 1 like SingleAlign.
+  void align_many(int n, char const* const* refs, char const* const* qrys, Align* const* results,
+                  NgmlrB200BatchAlignArgs* args, int* rets, bool* threw_out) {
     ref_len_.resize(n);
     qry_len_.resize(n);
     row_start_.resize(n + 1);
@@ -152,9 +187,10 @@ class B200Alignment : public IAlignment {
     }
     res_.resize(n);
     for (int i = 0; i < n; ++i) {
-      results[i].svType = 0;  // (:454-457)
-      results[i].Score = -1.0f;
+      results[i]->svType = 0;  // (:454-457)
+      results[i]->Score = -1.0f;
       rets[i] = -1;
+      if (threw_out) threw_out[i] = false;
     }
     int rc = ngmlr_b200_convex_align_batch(ctx_, n, refs, ref_len_.data(), qrys, qry_len_.data(),
                                            off_.data(), len_.data(), row_start_.data(), qs_.data(),
@@ -166,17 +202,19 @@ class B200Alignment : public IAlignment {
     bool threw = false;
     for (int i = 0; i < n; ++i) {
       const ngmlr_b200_align_result& r = res_[i];
-      Align& a = results[i];
+      Align& a = *results[i];
       if (too_big_[i]) continue;
       if (a.pBuffer2) a.pBuffer2[0] = '\0';  // (:469)
       if (r.threw) {
         threw = true;
+        if (threw_out) threw_out[i] = true;
         continue;
       }
       if (r.ret < 0) continue;
       // caller-owned buffers; grow MD / nmPerPosition like checkMdBufferLength / addPosition do
       if (r.cigar_len + 1 > a.maxBufferLength || !a.pBuffer1) {
         threw = true;  // "CIGAR/MD buffer not long enough" -> throw 1 (:289-294)
+        if (threw_out) threw_out[i] = true;
         continue;
       }
       memcpy(a.pBuffer1, r.cigar, (size_t)r.cigar_len + 1);
@@ -216,9 +254,10 @@ class B200Alignment : public IAlignment {
       rets[i] = r.ret;
     }
     too_big_.clear();
-    if (threw && n == 1) throw 1;  // caller wraps SingleAlign in try/catch(...) -> unmapped
+    if (threw && n == 1 && !threw_out) throw 1;  // caller wraps SingleAlign in try/catch(...) -> unmapped
   }
 
+ private:
   int gpu_id_ = 0;
   ngmlr_b200_scoring scoring_;
   ngmlr_b200_ctx* ctx_ = nullptr;
@@ -227,6 +266,121 @@ class B200Alignment : public IAlignment {
   std::vector<ngmlr_b200_align_result> res_;
   std::vector<bool> too_big_;
 };
+
+// ---- cross-thread batcher ("a GPU implementation that batches across threads
+// must do its own cross-thread queueing behind these blocking calls") ----------------------------
+// ngmlr runs one aligner object per worker thread and every SingleAlign blocks. With
+// NGMLR_B200_BATCH_WINDOW_US=<n> (> 0; off by default) the calls of all threads are parked in one
+// queue; a dispatcher thread collects what arrives within the window (or NGMLR_B200_BATCH_MAX
+// problems, default 256), runs ONE batched launch on its own context and hands every caller its
+// result. Results are those of n independent SingleAlign calls; the call sites stay untouched.
+class Batcher {
+ public:
+  Batcher(int gpu_id, const ngmlr_b200_scoring& sc, int window_us, int max_batch)
+      : gpu_id_(gpu_id), scoring_(sc), window_us_(window_us), max_batch_(max_batch) {
+    const ngmlr_b200_scoring saved = g_scoring;
+    g_scoring = sc;  // the server object takes the scoring of its first client
+    server_ = new B200Alignment(gpu_id);
+    g_scoring = saved;
+    if (server_->ok()) {
+      worker_ = std::thread([this] { loop(); });
+      worker_.detach();  // lives for the process: never torn down behind the CUDA runtime's back
+    }
+  }
+  bool usable(int gpu_id, const ngmlr_b200_scoring& sc) const {
+    return server_->ok() && gpu_id == gpu_id_ && same_scoring(sc, scoring_);
+  }
+  void submit(AlignRequest& r) {
+    std::unique_lock<std::mutex> lk(m_);
+    queue_.push_back(&r);
+    cv_work_.notify_one();
+    cv_done_.wait(lk, [&] { return r.done; });
+  }
+
+ private:
+  void loop() {
+    std::vector<AlignRequest*> batch;
+    std::vector<char const*> refs, qrys;
+    std::vector<Align*> results;
+    std::vector<NgmlrB200BatchAlignArgs> args;
+    std::vector<int> rets;
+    std::vector<char> threw;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_work_.wait(lk, [&] { return !queue_.empty(); });
+        // linger: give the other worker threads a chance to join this launch
+        const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(window_us_);
+        while ((int)queue_.size() < max_batch_ &&
+               cv_work_.wait_until(lk, deadline) != std::cv_status::timeout) {
+        }
+        const size_t take = std::min(queue_.size(), (size_t)max_batch_);
+        batch.assign(queue_.begin(), queue_.begin() + take);
+        queue_.erase(queue_.begin(), queue_.begin() + take);
+      }
+      const int n = (int)batch.size();
+      refs.resize(n); qrys.resize(n); results.resize(n); args.resize(n); rets.assign(n, -1); threw.assign(n, 0);
+      for (int i = 0; i < n; ++i) {
+        refs[i] = batch[i]->ref;
+        qrys[i] = batch[i]->qry;
+        results[i] = batch[i]->result;
+        args[i] = batch[i]->args;
+      }
+      const char* error = nullptr;
+      try {
+        server_->align_many(n, refs.data(), qrys.data(), results.data(), args.data(), rets.data(),
+                            reinterpret_cast<bool*>(threw.data()));
+      } catch (const char* e) {
+        error_ = e ? e : "batched alignment failed";
+        error = error_.c_str();
+      } catch (...) {
+        error_ = "batched alignment failed";
+        error = error_.c_str();
+      }
+      {
+        std::lock_guard<std::mutex> lk(m_);
+        for (int i = 0; i < n; ++i) {
+          batch[i]->ret = rets[i];
+          batch[i]->threw = threw[i] != 0;
+          batch[i]->error = error;
+          batch[i]->done = true;
+        }
+      }
+      cv_done_.notify_all();
+    }
+  }
+
+  int gpu_id_;
+  ngmlr_b200_scoring scoring_;
+  int window_us_, max_batch_;
+  B200Alignment* server_ = nullptr;
+  std::thread worker_;
+  std::mutex m_;
+  std::condition_variable cv_work_, cv_done_;
+  std::vector<AlignRequest*> queue_;
+  std::string error_;
+};
+
+bool batcher_submit(int gpu_id, const ngmlr_b200_scoring& scoring, AlignRequest& r) {
+  static const int window_us = [] {
+    const char* e = getenv("NGMLR_B200_BATCH_WINDOW_US");
+    return e ? atoi(e) : 0;
+  }();
+  if (window_us <= 0) return false;
+  static std::mutex create_mutex;
+  static Batcher* batcher = nullptr;  // leaked on purpose (see the detach above)
+  {
+    std::lock_guard<std::mutex> lk(create_mutex);
+    if (!batcher) {
+      const char* e = getenv("NGMLR_B200_BATCH_MAX");
+      const int mx = e && atoi(e) > 0 ? atoi(e) : 256;
+      batcher = new Batcher(gpu_id, scoring, window_us, mx);
+    }
+  }
+  if (!batcher->usable(gpu_id, scoring)) return false;
+  batcher->submit(r);
+  return true;
+}
 
 }  // namespace
 

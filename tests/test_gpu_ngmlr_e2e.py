@@ -34,3 +34,22 @@ def test_sam_identical_with_plugin(tmp_path):
     assert len(outs["cpu"]) == len(outs["b200"])
     for a, b in zip(outs["cpu"], outs["b200"]):
         assert a == b, f"SAM record differs:\nCPU : {a[:300]}\nB200: {b[:300]}"
+
+
+@pytest.mark.skipif(not (os.path.exists(PLAIN) and os.path.exists(SWAPPED)),
+                    reason="oracle/_ref/ngmlr{,_b200} not built (needs /root/reference at build time)")
+def test_sam_identical_with_cross_thread_batcher(tmp_path):
+    """8 ngmlr worker threads, every blocking SingleAlign parked in the plugin's cross-thread batcher
+    (NGMLR_B200_BATCH_WINDOW_US): the same records as the single-threaded CPU run (record order in the
+    file depends on thread timing, so compare sorted)."""
+    ref, fq = e2e_data.write_dataset(str(tmp_path))
+    outs = {}
+    for name, exe, threads, extra in (("cpu", PLAIN, "1", {}),
+                                      ("b200", SWAPPED, "8", {"NGMLR_B200_BATCH_WINDOW_US": "300"})):
+        sam = str(tmp_path / f"{name}.sam")
+        env = dict(os.environ, NGMLR_B200_LIB=os.path.join(ROOT, "ngmlr_b200", "libngmlr_b200.so"), **extra)
+        r = subprocess.run([exe, "-r", ref, "-q", fq, "-o", sam, "-t", threads, "--skip-write", "--no-progress"],
+                           capture_output=True, text=True, env=env, timeout=900)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[name] = sorted(e2e_data.sam_records(sam))
+    assert len(outs["cpu"]) >= 24 and outs["cpu"] == outs["b200"]
