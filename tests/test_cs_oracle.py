@@ -21,10 +21,16 @@ def cs_oracle(contigs):
     o.close()
 
 
-def test_numpy_index_builder_equals_oracle(contigs, cs_oracle):
+@pytest.fixture(scope="module")
+def built(contigs):
+    """(EncodedReference, KmerIndex) of the test genome from the numpy builder, built once."""
     from ngmlr_b200 import refindex
     ref = refindex.encode_reference(contigs)
-    idx = refindex.build_index(ref)
+    return ref, refindex.build_index(ref)
+
+
+def test_numpy_index_builder_equals_oracle(contigs, cs_oracle, built):
+    ref, idx = built
     assert ref.concat_len == cs_oracle.concat_len and ref.ref_start == cs_oracle.ref_starts()
     assert np.array_equal(ref.enc, cs_oracle.encoded())
     tab, rci, pos = cs_oracle.index()
@@ -87,11 +93,10 @@ def test_oracle_decode_exact_matches_golden(contigs, cs_oracle):
         assert cs_oracle.decode_exact(st, ln) == text.encode()
 
 
-def test_cache_files_round_trip(contigs, tmp_path):
+def test_cache_files_round_trip(contigs, tmp_path, built):
     """ngmfiles: what is written is read back identically (always runnable)."""
-    from ngmlr_b200 import ngmfiles, refindex
-    ref = refindex.encode_reference(contigs)
-    idx = refindex.build_index(ref)
+    from ngmlr_b200 import ngmfiles
+    ref, idx = built
     ngmfiles.write_encoded_reference(str(tmp_path / "r-enc.2.ngm"), ref, skipped_lens=[8])
     ngmfiles.write_index(str(tmp_path / "r-ht-13-2.2.ngm"), idx)
     ref2, names = ngmfiles.read_encoded_reference(str(tmp_path / "r-enc.2.ngm"))
@@ -107,7 +112,7 @@ def test_cache_files_round_trip(contigs, tmp_path):
 
 
 @pytest.mark.skipif(not CsReference.available(), reason="oracle/_ref/libngmlr_full.so not built")
-def test_cache_files_are_byte_compatible_with_the_reference(contigs, tmp_path):
+def test_cache_files_are_byte_compatible_with_the_reference(contigs, tmp_path, built):
     """The UNMODIFIED reference writes <fasta>-enc.2.ngm and <fasta>-ht-13-2.2.ngm (in a subprocess:
     its singletons initialise once per process); ngmfiles reads them into the arrays refindex builds,
     and writes the same bytes (the index file entirely; the encoded reference up to the end of the used
@@ -125,8 +130,7 @@ def test_cache_files_are_byte_compatible_with_the_reference(contigs, tmp_path):
                          timeout=600)
     assert run.returncode == 0, run.stderr[-2000:]
     enc_path, idx_path = fasta + "-enc.2.ngm", fasta + "-ht-13-2.2.ngm"
-    ref = refindex.encode_reference(contigs)
-    idx = refindex.build_index(ref)
+    ref, idx = built
     got_ref, names = ngmfiles.read_encoded_reference(enc_path)
     assert np.array_equal(got_ref.enc, ref.enc) and got_ref.concat_len == ref.concat_len
     assert got_ref.ref_start == ref.ref_start and got_ref.ref_len == ref.ref_len
