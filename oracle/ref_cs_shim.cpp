@@ -17,6 +17,7 @@
 
 #define private public
 #define protected public
+#include "AlignmentBuffer.h"
 #include "CS.h"
 #include "IConfig.h"
 #include "Log.h"
@@ -240,6 +241,79 @@ int ref_cs_search_p(void* probe_, const char* seq, int len, int table_bits, floa
   }
   delete read;
   return n < 0 ? -1 : m;
+}
+
+// ---- corridor builders of the caller (src/AlignmentBuffer.cpp:68-197, 1454-1467) ----------------
+}  // extern "C"
+CorridorLine* getCorridorLinear(int const corridor, char const* readSeq, int& corridorHeight);
+CorridorLine* getCorridorFull(int const corridor, char const* readSeq, int& corridorHeight);
+CorridorLine* getCorridorEndpoints(Interval const* interval, int const corridor, char const* refSeq,
+                                   char const* readSeq, int& corridorHeight, bool const realign);
+extern "C" {
+
+static void ensure_config() {
+  if (!_config) {
+    IConfig* c = new IConfig();
+    c->outputFile = strdup("/dev/null");
+    _config = c;
+    _Log::Init(0, 0);
+    _log = &Log;
+  }
+}
+
+// AlignmentBuffer's two member functions touch no member data except pacbioDebug; they are called on
+// zeroed storage instead of a constructed object (the constructor wants a live SAM writer).
+static AlignmentBuffer* fake_alignment_buffer() {
+  static void* mem = calloc(1, sizeof(AlignmentBuffer) + 64);
+  return static_cast<AlignmentBuffer*>(mem);
+}
+
+// kind 0: getCorridorLinear(corridor), 1: getCorridorFull(corridor), 2: getCorridorEndpoints(corridor,
+// realign), 3: getCorridorEndpointsWithAnchors(multiplier = corridor). Only strlen of the sequences
+// matters. Returns corridorHeight.
+int ref_corridor(int kind, int qry_len, int ref_len, int corridor, int realign, int n_anchors,
+                 const int* a_on_read, const unsigned long long* a_on_ref, const int* a_rev,
+                 unsigned long long on_ref_start, int ext_qstart, int read_part_len, int full_read_len,
+                 int* off_out, int* len_out) {
+  ensure_config();
+  std::vector<char> q((size_t)qry_len + 1, 'A'), r((size_t)ref_len + 1, 'A');
+  q[qry_len] = 0;
+  r[ref_len] = 0;
+  Interval iv;
+  std::vector<Anchor> anchors((size_t)(n_anchors > 0 ? n_anchors : 1));
+  for (int i = 0; i < n_anchors; ++i) {
+    anchors[i].onRead = a_on_read[i];
+    anchors[i].onRef = (loc)a_on_ref[i];
+    anchors[i].isReverse = a_rev[i] != 0;
+  }
+  iv.anchors = anchors.data();
+  iv.anchorLength = n_anchors;
+  iv.onRefStart = (loc)on_ref_start;
+  int h = 0;
+  CorridorLine* c = 0;
+  if (kind == 0) c = getCorridorLinear(corridor, q.data(), h);
+  else if (kind == 1) c = getCorridorFull(corridor, q.data(), h);
+  else if (kind == 2) c = getCorridorEndpoints(&iv, corridor, r.data(), q.data(), h, realign != 0);
+  else c = fake_alignment_buffer()->getCorridorEndpointsWithAnchors(&iv, corridor, r.data(), q.data(), h, ext_qstart,
+                                                                  read_part_len, full_read_len, realign != 0);
+  for (int i = 0; i < h; ++i) {
+    off_out[i] = c[i].offset;
+    len_out[i] = c[i].length;
+  }
+  delete[] c;
+  iv.anchors = 0;  // not ours to free in ~Interval
+  iv.anchorLength = 0;
+  return h;
+}
+
+int ref_estimate_corridor(int on_read_start, int on_read_stop, long long on_ref_start, long long on_ref_stop) {
+  ensure_config();
+  Interval iv;
+  iv.onReadStart = on_read_start;
+  iv.onReadStop = on_read_stop;
+  iv.onRefStart = (loc)on_ref_start;
+  iv.onRefStop = (loc)on_ref_stop;
+  return fake_alignment_buffer()->estimateCorridor(&iv);
 }
 
 // Stage 0/2 of one read entirely inside the reference's code (used by bench.py's CPU arm so that no

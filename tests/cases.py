@@ -107,3 +107,22 @@ def sw_pairs(n, seed):
         refs.append(bytes(win.tobytes()))
         qrys.append(bytes(np.asarray(sub, dtype=np.uint8).tobytes()))
     return refs, qrys
+
+
+def corridor_cases(seed=33, n=48):
+    """Seeded parameter sets for the corridor builders (row 7): dicts with q, r, corridor, realign,
+    multiplier, anchors [(onRead, onRef, isReverse)], on_ref_start, ext_qstart, full_len."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        q = int(rng.integers(1, 5000))
+        r = int(max(1, q + rng.integers(-q // 3 - 1, q // 3 + 2)))
+        on_ref_start = int(rng.integers(1000, 10**9))
+        ext_qs = int(rng.integers(0, 50))
+        full_len = q + ext_qs + int(rng.integers(0, 300))
+        anchors = [(int(rng.integers(0, q + 1)) + ext_qs, on_ref_start + int(rng.integers(0, r + 1)),
+                    int(rng.integers(0, 2))) for _a in range(int(rng.integers(0, 12)))]
+        out.append(dict(q=q, r=r, corridor=int(rng.choice([40, 400, 1600, 3333, 8192])),
+                        realign=int(rng.integers(0, 2)), multiplier=int(rng.choice([1, 1, 2, 4])),
+                        anchors=anchors, on_ref_start=on_ref_start, ext_qstart=ext_qs, full_len=full_len))
+    return out

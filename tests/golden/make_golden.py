@@ -6,7 +6,7 @@ by oracle/Makefile from /root/reference). Run in the build container only:
 The vectors pin: (a) ConvexAlignFast::SingleAlign outputs (return value, score bits, CIGAR, MD,
 NM, positions, nmPerPosition checksum, direction-matrix checksum, best cell) for seeded problems
 under three scorings, (b) StrippedSW scores, (c) ScoreBuffer::topNSE candidate order / kept / MQ,
-(d) DecodeRefSequenceExact windows. Inputs are regenerated from the seeds by
+(d) DecodeRefSequenceExact windows, (e) corridor builders. Inputs are regenerated from the seeds by
 tests/cases.py, so only outputs are stored (plus an input checksum to detect generator drift)."""
 import hashlib
 import json
@@ -103,6 +103,31 @@ def main():
         json.dump({"windows_sha": digest(np.array(wins, dtype=np.int64)), "n": len(wins),
                    "text_sha": [digest(d) for d in dec],
                    "samples": [[wins[i][0], wins[i][1], dec[i].decode()] for i in range(0, len(wins), 37) if wins[i][1] <= 64]}, f)
+    # (e) corridor builders of the caller (getCorridorLinear/Full/Endpoints/EndpointsWithAnchors)
+    import ctypes as C
+    lib = C.CDLL(CsReference.PATH)
+
+    def ref_corridor(kind, c, arg, realign=0):
+        an = c["anchors"] if kind == 3 else []
+        n = len(an)
+        a0 = (C.c_int * max(n, 1))(*[a[0] for a in an])
+        a1 = (C.c_ulonglong * max(n, 1))(*[a[1] for a in an])
+        a2 = (C.c_int * max(n, 1))(*[a[2] for a in an])
+        off = np.zeros(c["q"], dtype=np.int32)
+        ln = np.zeros(c["q"], dtype=np.int32)
+        h = lib.ref_corridor(kind, c["q"], c["r"], arg, realign, n, a0, a1, a2, C.c_ulonglong(c["on_ref_start"]),
+                             c["ext_qstart"], 256, c["full_len"], off.ctypes.data_as(C.c_void_p),
+                             ln.ctypes.data_as(C.c_void_p))
+        assert h == c["q"]
+        return digest(off, ln)
+
+    cor = []
+    for c in cases.corridor_cases():
+        cor.append({"linear": ref_corridor(0, c, c["corridor"]), "full": ref_corridor(1, c, c["r"]),
+                    "endpoints": ref_corridor(2, c, c["corridor"], c["realign"]),
+                    "anchors": ref_corridor(3, c, c["multiplier"])})
+    with open(os.path.join(HERE, "corridor_golden.json"), "w") as f:
+        json.dump(cor, f)
     print("wrote golden vectors:", {k: len(v["records"]) for k, v in out.items()}, len(sw["scores"]))
 
 
