@@ -17,7 +17,7 @@
 
 #define private public
 #define protected public
-#include "AlignmentBuffer.h"
+#include "AlignmentBuffer.h"  // (pulls in ConvexAlignFast.h, whose closing brace sits outside its include guard)
 #include "CS.h"
 #include "IConfig.h"
 #include "Log.h"
@@ -314,6 +314,59 @@ int ref_estimate_corridor(int on_read_start, int on_read_stop, long long on_ref_
   iv.onRefStart = (loc)on_ref_start;
   iv.onRefStop = (loc)on_ref_stop;
   return fake_alignment_buffer()->estimateCorridor(&iv);
+}
+
+// AlignmentBuffer::computeAlignment (src/AlignmentBuffer.cpp:226-465): reference window extraction,
+// corridor choice per attempt, SingleAlign, retry with a wider corridor. Needs ref_cs_init (the encoded
+// genome). Outputs like ref_convex_single_align of oracle/ref_shim.cpp; returns 1 if an Align came
+// back, 0 if the reference gave up (returned 0).
+int ref_compute_alignment(unsigned long long on_ref_start, unsigned long long on_ref_stop, int n_anchors,
+                          const int* a_on_read, const unsigned long long* a_on_ref, const int* a_rev,
+                          int corridor, const char* read_seq, int ext_qstart, int ext_qend, int full_read_len,
+                          int realign, int full_alignment, int short_read, int* ints, float* floats,
+                          char* cigar_out, int cigar_cap, char* md_out, int md_cap, int* nm_out, int nm_cap) {
+  ensure_config();
+  AlignmentBuffer* ab = fake_alignment_buffer();
+  if (!ab->aligner) {
+    ab->aligner = new Convex::ConvexAlignFast(0, Config.getScoreMatch(), Config.getScoreMismatch(),
+                                              Config.getScoreGapOpen(), Config.getScoreExtendMax(),
+                                              Config.getScoreExtendMin(), Config.getScoreGapDecay());
+    *const_cast<int*>(&ab->readPartLength) = Config.getReadPartLength();
+  }
+  Interval iv;
+  std::vector<Anchor> anchors((size_t)(n_anchors > 0 ? n_anchors : 1));
+  for (int i = 0; i < n_anchors; ++i) {
+    anchors[i].onRead = a_on_read[i];
+    anchors[i].onRef = (loc)a_on_ref[i];
+    anchors[i].isReverse = a_rev[i] != 0;
+  }
+  iv.anchors = anchors.data();
+  iv.anchorLength = n_anchors;
+  iv.onRefStart = (loc)on_ref_start;
+  iv.onRefStop = (loc)on_ref_stop;
+  MappedRead* read = new MappedRead(0, 16);
+  read->name = new char[8];
+  strcpy(read->name, "r");
+  Align* a = ab->computeAlignment(&iv, corridor, read_seq, strlen(read_seq), ext_qstart, ext_qend, full_read_len,
+                                  read, realign != 0, full_alignment != 0, short_read != 0);
+  iv.anchors = 0;
+  iv.anchorLength = 0;
+  delete read;
+  if (!a) return 0;
+  int n = 0;
+  const int v[12] = {0, a->QStart, a->QEnd, a->NM, a->alignmentLength, a->cigarOpCount, a->svType,
+                     a->firstPosition.refPosition, a->firstPosition.readPosition, a->lastPosition.refPosition,
+                     a->lastPosition.readPosition, (int)a->PositionOffset};
+  memcpy(ints, v, sizeof(v));
+  floats[0] = a->Score;
+  floats[1] = a->Identity;
+  snprintf(cigar_out, (size_t)cigar_cap, "%s", a->pBuffer1);
+  snprintf(md_out, (size_t)md_cap, "%s", a->pBuffer2);
+  (void)nm_out; (void)nm_cap; (void)n;
+  a->clearBuffer();
+  a->clearNmPerPosition();
+  delete a;
+  return 1;
 }
 
 // Stage 0/2 of one read entirely inside the reference's code (used by bench.py's CPU arm so that no

@@ -50,13 +50,20 @@ def test_oracle_search_basic_properties(contigs, cs_oracle):
     assert cs_oracle.search(b"")[0] == [] and cs_oracle.search(b"ACGTACGTACGT")[0] == []
 
 
-@pytest.mark.skipif(not CsReference.available(), reason="oracle/_ref/libngmlr_full.so not built")
-def test_oracle_equals_whole_reference(contigs, cs_oracle, tmp_path_factory):
+@pytest.fixture(scope="module")
+def whole_ref(contigs, tmp_path_factory):
+    """The unmodified reference initialised on the test genome (its singletons: once per process)."""
+    if not CsReference.available():
+        pytest.skip("oracle/_ref/libngmlr_full.so not built")
     path = str(tmp_path_factory.mktemp("cs") / "ref.fa")
     with open(path, "w") as f:
         for i, c in enumerate(contigs):
             f.write(f">c{i}\n{c.tobytes().decode()}\n")
-    ref = CsReference(path)
+    return CsReference(path)
+
+
+def test_oracle_equals_whole_reference(contigs, cs_oracle, whole_ref):
+    ref = whole_ref
     assert ref.concat_len == cs_oracle.concat_len and ref.ref_starts() == cs_oracle.ref_starts()
     a, b = ref.index(), cs_oracle.index()
     for x, y in zip(a, b):
@@ -147,3 +154,99 @@ def test_cache_files_are_byte_compatible_with_the_reference(contigs, tmp_path, b
     mine, theirs = open(tmp_path / "mine-enc.ngm", "rb").read(), open(enc_path, "rb").read()
     defined = 24 + 128 * len(ref.ref_start) + int(ref.enc.size)
     assert len(mine) == len(theirs) and mine[:defined] == theirs[:defined]
+
+
+class _OracleBackend:
+    """The two backend operations of ngmlr_b200.intervals on the CPU oracle."""
+
+    def __init__(self, cs_oracle, oracle):
+        self.cs, self.o = cs_oracle, oracle
+
+    def decode(self, starts, seq_lens):
+        return [self.cs.decode_exact(int(s), int(n)) for s, n in zip(starts, seq_lens)]
+
+    def align(self, tasks, refs, offsets, lengths):
+        return [self.o.single_align(r, t.read_seq, o, l, t.ext_qstart, t.ext_qend)
+                for t, r, o, l in zip(tasks, refs, offsets, lengths)]
+
+
+def _interval_tasks(contigs, enc):
+    """Intervals as processLongReadLIS would hand them to computeAlignment: read part, reference span
+    (with some slack or some shortfall), 256-bp anchors (some reverse-coded), corridor estimate; plus
+    realign / short-read / full-matrix variants and corridors that are too narrow at first."""
+    from ngmlr_b200 import corridor, synth
+    from ngmlr_b200.intervals import IntervalTask
+    rng = np.random.default_rng(77)
+    tasks = []
+    for k in range(36):
+        c = int(rng.integers(0, 2))
+        L = int(rng.integers(300, 3000))
+        s0 = int(rng.integers(200, contigs[c].size - L - 200))
+        big_del = k % 5 == 0          # a long deletion in the read: the first corridor may be too narrow
+        src = contigs[c][s0:s0 + L]
+        if big_del:
+            cut = int(rng.integers(40, 120))
+            mid = L // 2
+            src = np.concatenate([src[:mid], src[mid + cut:]])
+        read, _ = synth.mutate(src, rng, err=0.10)
+        ext_qs, ext_qe = (int(rng.integers(0, 30)), int(rng.integers(0, 30))) if k % 3 == 0 else (0, 0)
+        on_start = enc.ref_start[c] + s0 - int(rng.integers(0, 40))
+        on_stop = enc.ref_start[c] + s0 + L + int(rng.integers(0, 40))
+        full_len = len(read) + ext_qs + ext_qe
+        anchors = []
+        for y in range(0, len(read) - 256, 256):
+            x = int(y * (on_stop - on_start) / max(len(read), 1)) + int(rng.integers(-20, 21))
+            rev = int(rng.integers(0, 2))
+            on_read = (full_len - (y + ext_qs) - 256) if rev else (y + ext_qs)
+            anchors.append((on_read, on_start + max(x, 0), rev))
+        kind = k % 6
+        t = IntervalTask(on_ref_start=on_start, on_ref_stop=on_stop, read_seq=read.tobytes(),
+                         corridor=corridor.estimate_corridor(len(read), on_stop - on_start),
+                         ext_qstart=ext_qs, ext_qend=ext_qe, full_read_length=full_len,
+                         anchors=anchors if kind != 1 else [], realign=kind == 2,
+                         full_alignment=kind == 3 and L < 900, short_read=kind == 4)
+        if kind == 5:
+            t.corridor = 40       # far too narrow: forces retries with wider corridors
+            t.anchors = []
+        tasks.append(t)
+    return tasks
+
+
+def test_batched_compute_alignment_equals_the_reference(contigs, cs_oracle, whole_ref, oracle):
+    """ngmlr_b200.intervals.compute_alignments (window extraction, corridor per attempt, retry policy)
+    with the oracle as its backend == AlignmentBuffer::computeAlignment of the unmodified reference."""
+    import ctypes as C
+    from ngmlr_b200 import refindex
+    from ngmlr_b200.intervals import compute_alignments
+    lib = whole_ref.lib
+    if not hasattr(lib, "ref_compute_alignment"):
+        pytest.skip("libngmlr_full.so predates ref_compute_alignment")
+    enc = refindex.encode_reference(contigs)
+    tasks = _interval_tasks(contigs, enc)
+    got, calls = compute_alignments(_OracleBackend(cs_oracle, oracle), tasks)
+    n_valid = n_retry = 0
+    for t, g, nc in zip(tasks, got, calls):
+        n = len(t.anchors)
+        a0 = (C.c_int * max(n, 1))(*[a[0] for a in t.anchors])
+        a1 = (C.c_ulonglong * max(n, 1))(*[a[1] for a in t.anchors])
+        a2 = (C.c_int * max(n, 1))(*[a[2] for a in t.anchors])
+        ints = (C.c_int * 12)()
+        fl = (C.c_float * 2)()
+        cap = 8 * len(t.read_seq) + 64
+        cig, md = C.create_string_buffer(cap), C.create_string_buffer(cap)
+        ok = lib.ref_compute_alignment(C.c_ulonglong(t.on_ref_start), C.c_ulonglong(t.on_ref_stop), n, a0, a1, a2,
+                                       t.corridor, t.read_seq, t.ext_qstart, t.ext_qend, t.full_read_length,
+                                       int(t.realign), int(t.full_alignment), int(t.short_read), ints, fl,
+                                       cig, cap, md, cap, None, 0)
+        assert bool(ok) == (g is not None), (t.corridor, nc)
+        if g is None:
+            continue
+        n_valid += 1
+        n_retry += nc > 1
+        assert cig.value.decode() == g["cigar"] and md.value.decode() == g["md"]
+        assert (ints[1], ints[2], ints[3], ints[4], ints[5]) == (g["qstart"], g["qend"], g["nm"],
+                                                                  g["alignment_length"], g["cigar_op_count"])
+        assert ints[11] == g["position_offset"]
+        assert np.float32(fl[0]).view(np.uint32) == np.uint32(g["score_bits"])
+        assert np.float32(fl[1]).view(np.uint32) == np.uint32(g["identity_bits"])
+    assert n_valid >= 24 and n_retry >= 3, (n_valid, n_retry)

@@ -146,3 +146,25 @@ def test_align_from_reference_windows_equals_text_upload(aligner):
         assert same_alignment(a, b) == []
     assert sum(1 for r in want if r["ret"] > 0) >= 20
     orc.close()
+
+
+def test_batched_compute_alignment_on_the_device(aligner, oracle):
+    """ngmlr_b200.intervals.compute_alignments through the GPU backend (decode_windows +
+    convex_upload_windows + run + fetch, retries as further batches) == the same host logic over the
+    CPU oracle (which tests/test_cs_oracle.py pins against AlignmentBuffer::computeAlignment)."""
+    from ngmlr_b200 import refindex
+    from ngmlr_b200.intervals import B200Backend, compute_alignments
+    from oracle_lib import same_alignment
+    from test_cs_oracle import _OracleBackend, _interval_tasks
+    contigs = cs_cases.genome_contigs()
+    orc = CsOracle([c.tobytes() for c in contigs])
+    enc = refindex.encode_reference(contigs)
+    aligner.set_reference(enc)
+    want, want_calls = compute_alignments(_OracleBackend(orc, oracle), _interval_tasks(contigs, enc))
+    got, got_calls = compute_alignments(B200Backend(aligner), _interval_tasks(contigs, enc))
+    assert got_calls == want_calls
+    for w, g in zip(want, got):
+        assert (w is None) == (g is None)
+        if w is not None:
+            assert same_alignment(w, g.as_dict()) == []
+    orc.close()
