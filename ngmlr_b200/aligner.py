@@ -106,8 +106,11 @@ class PackedReads:
 
 def split_read(seq, part_length=256):
     """ReadProvider::splitRead's sub-reads (src/ReadProvider.cpp:57-134): floor(len / part_length)
-    consecutive pieces of part_length bases."""
+    consecutive pieces of part_length bases (the tail shorter than a part is not searched); a read
+    shorter than one part is its own single sub-read (:76-104)."""
     n = len(seq) // part_length
+    if n == 0:
+        return [seq]
     return [seq[i * part_length:(i + 1) * part_length] for i in range(n)]
 
 

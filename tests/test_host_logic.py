@@ -256,3 +256,12 @@ def test_corridor_builders_match_golden():
         ax = [a[1] - c["on_ref_start"] for a in c["anchors"]]
         ay = [c["full_len"] - a[0] - 256 - c["ext_qstart"] if a[2] else a[0] - c["ext_qstart"] for a in c["anchors"]]
         assert gu.digest(*corridor.corridor_endpoints_with_anchors(c["q"], c["r"], ax, ay, c["multiplier"])) == g["anchors"]
+
+
+def test_split_read_follows_splitRead():
+    from ngmlr_b200 import split_read
+    s = bytes(range(256)) * 3 + b"ACGT" * 10
+    parts = split_read(s)
+    assert len(parts) == 3 and all(len(p) == 256 for p in parts) and b"".join(parts) == s[:768]
+    assert split_read(b"ACGT" * 10) == [b"ACGT" * 10]          # shorter than one part: one sub-read
+    assert split_read(b"A" * 256) == [b"A" * 256] and len(split_read(b"A" * 511)) == 1
