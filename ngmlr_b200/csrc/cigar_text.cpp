@@ -30,21 +30,24 @@ inline void put_op(std::string& s, int len, char op, int& count) {
 // mismatch density (inversion detection input, src/ConvexAlignFast.cpp:117-119, 193-269).
 struct ErrorWindow {
   uint32_t bits = 0;
-  int level = 0;
+  int ones = 0;   // popcount(bits), kept incrementally (one bit leaves, one enters per event)
+  int level = 0;  // what the reference records: NumberOfSetBits after a match/mismatch, but only
+                  // "previous + 1" after the first base of an indel (it does not recount there)
+  void shift(uint32_t in) {
+    ones += (int)in - (int)(bits >> 31);
+    bits = (bits << 1) | in;
+  }
   void match() {
-    bits <<= 1;
-    level = __builtin_popcount(bits);
+    shift(0u);
+    level = ones;
   }
   void mismatch() {
-    bits = (bits << 1) | 1u;
-    level = __builtin_popcount(bits);
+    shift(1u);
+    level = ones;
   }
   void gap_base(bool first) {  // only the first base of an indel run counts (maxIndelLength = 1)
-    bits <<= 1;
-    if (first) {
-      bits |= 1u;
-      level = level + 1 > 0 ? level + 1 : 0;
-    }
+    shift(first ? 1u : 0u);
+    if (first) level = level + 1 > 0 ? level + 1 : 0;
   }
 };
 
