@@ -265,3 +265,78 @@ def test_split_read_follows_splitRead():
     assert len(parts) == 3 and all(len(p) == 256 for p in parts) and b"".join(parts) == s[:768]
     assert split_read(b"ACGT" * 10) == [b"ACGT" * 10]          # shorter than one part: one sub-read
     assert split_read(b"A" * 256) == [b"A" * 256] and len(split_read(b"A" * 511)) == 1
+
+
+def _binary_runs_from_text(cigar, md, ext_qs, ext_qe):
+    """Rebuild the reference's binary CIGAR (len << 4 | op; EQ 7, X 8, I 1, D 2, S 4; leading and
+    trailing clip entries always present) from CIGAR + MD text."""
+    import re
+    ops = [(int(n), o) for n, o in re.findall(r"(\d+)([MIDS])", cigar)]
+    lead = ops.pop(0)[0] - ext_qs if ops and ops[0][1] == "S" else -ext_qs
+    trail = ops.pop()[0] - ext_qe if ops and ops[-1][1] == "S" else -ext_qe
+    # MD: numbers = matches, letters = mismatches, ^letters = deletions
+    md_items = re.findall(r"(\d+)|(\^[A-Za-z]+)|([A-Za-z])", md)
+    seq = []          # per aligned reference base of M/D: 'E' match, 'X' mismatch, 'D' deleted
+    for num, dele, mis in md_items:
+        if num:
+            seq.extend("E" * int(num))
+        elif dele:
+            seq.extend("D" * (len(dele) - 1))
+        else:
+            seq.append("X")
+    runs, si = [max(lead, 0) << 4 | 4], 0
+    for n, o in ops:
+        if o == "M":
+            k = 0
+            while k < n:
+                kind = seq[si + k]
+                j = k
+                while j < n and seq[si + j] == kind:
+                    j += 1
+                runs.append((j - k) << 4 | (7 if kind == "E" else 8))
+                k = j
+            si += n
+        elif o == "D":
+            assert all(c == "D" for c in seq[si:si + n])
+            runs.append(n << 4 | 2)
+            si += n
+        else:
+            runs.append(n << 4 | 1)
+    runs.append(max(trail, 0) << 4 | 4)
+    return runs
+
+
+def test_text_stage_equals_oracle_on_real_alignments(oracle):
+    """The product's CIGAR/MD/NM/nmPerPosition stage (binary_cigar_to_text, via its host-only debug
+    hook) on the alignments the oracle finds: same text and same nmPerPosition triples as the oracle's
+    convertCigar restatement (which is pinned against the reference)."""
+    import ctypes as C
+    import cases
+    from ngmlr_b200 import _lib
+    lib = _lib.load()
+    n_checked = 0
+    for p in cases.random_problems(40, 515, max_len=1500):
+        w = oracle.single_align(p.ref, p.qry, p.offsets, p.lengths, p.ext_qstart, p.ext_qend)
+        if w["ret"] < 0 or w["status"]:
+            continue
+        runs = _binary_runs_from_text(w["cigar"], w["md"], p.ext_qstart, p.ext_qend)
+        arr = np.array(runs, dtype=np.int32)
+        ints = (C.c_int32 * 12)()
+        ident = C.c_float()
+        cap = 8 * (len(p.qry) + len(p.ref)) + 64
+        cig, md = C.create_string_buffer(cap), C.create_string_buffer(cap)
+        nm = np.zeros(3 * (2 * (len(p.qry) + 1) + len(p.ref)), dtype=np.int32)
+        ref = bytes(p.ref)
+        ok = lib.ngmlr_b200_debug_cigar_text(arr.ctypes.data_as(C.c_void_p), len(runs), ref, len(ref),
+                                             w["position_offset"], p.ext_qstart, p.ext_qend, ints, C.byref(ident),
+                                             cig, cap, md, cap, nm.ctypes.data_as(C.c_void_p), int(nm.size))
+        assert ok == 1
+        assert cig.value.decode() == w["cigar"] and md.value.decode() == w["md"]
+        assert (ints[0], ints[1], ints[2], ints[3], ints[4], ints[5]) == (
+            w["ret"], w["qstart"], w["qend"], w["nm"], w["alignment_length"], w["cigar_op_count"])
+        assert (ints[7], ints[8], ints[9], ints[10]) == (w["first_ref"], w["first_read"], w["last_ref"], w["last_read"])
+        assert np.float32(ident.value).view(np.uint32) == np.uint32(w["identity_bits"])
+        assert ints[11] == w["nm_count"]
+        assert np.array_equal(nm[:3 * ints[11]].reshape(-1, 3), w["nm_positions"])
+        n_checked += 1
+    assert n_checked >= 15
