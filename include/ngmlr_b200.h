@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define NGMLR_B200_ABI_VERSION 1
+#define NGMLR_B200_ABI_VERSION 2
 
 /* Convex scoring parameters = ConvexAlignFast's constructor arguments
  * (src/ConvexAlignFast.h:20-27, src/ConvexAlignFast.cpp:29-43; CLI defaults src/IConfig.h:23-71):
@@ -60,8 +60,16 @@ typedef struct {
   int32_t cigar_len, md_len;
   const char* cigar;        /* Align::pBuffer1, NUL-terminated */
   const char* md;           /* Align::pBuffer2, NUL-terminated */
-  const int32_t* nm_positions; /* nm_count x {refPosition, readPosition, nm} */
+  const int32_t* nm_positions; /* nm_count x {refPosition, readPosition, nm}; NULL in the device text
+                               * stage unless requested (ngmlr_b200_set_text_stage) */
   int64_t cells;            /* DP cells evaluated (SURVEY.md section 8d unit of work) */
+  /* The peak scan of AlignmentBuffer::detectMisalignment over nmPerPosition
+   * (src/AlignmentBuffer.cpp:1319-1388): closed low-identity regions, each {startInv, stopInv,
+   * startInvRead, stopInvRead} = the arguments from which the reference calls checkForSV.
+   * n_sv_regions counts all of them (the reference's checkCount), the first n_sv_regions_stored
+   * (at most 32) are listed. */
+  int32_t n_sv_regions, n_sv_regions_stored;
+  const int32_t* sv_regions;
 } ngmlr_b200_align_result;
 
 /* Aggregate device-side statistics of the last convex batch (for roofline accounting). */
@@ -78,6 +86,10 @@ typedef struct {
   /* host wall-clock of the last upload / run / fetch phases (ms) */
   float host_pack_ms, host_h2d_ms, host_run_ms, host_d2h_ms, host_text_ms;
   int32_t host_threads;
+  /* device text stage (convex_text.cu): kernel time, launches, bytes of CIGAR + MD text produced */
+  float text_ms;
+  int32_t text_launches;
+  int64_t text_bytes;
 } ngmlr_b200_batch_stats;
 
 int ngmlr_b200_abi_version(void);
@@ -126,6 +138,17 @@ int ngmlr_b200_convex_upload(ngmlr_b200_ctx* ctx, int n, const char* const* refs
 int ngmlr_b200_convex_run(ngmlr_b200_ctx* ctx);
 int ngmlr_b200_convex_fetch(ngmlr_b200_ctx* ctx, ngmlr_b200_align_result* results);
 int ngmlr_b200_convex_stats(ngmlr_b200_ctx* ctx, ngmlr_b200_batch_stats* out);
+
+/* Where ConvexAlignFast::convertCigar (src/ConvexAlignFast.cpp:112-333) and the peak scan of its
+ * consumer AlignmentBuffer::detectMisalignment (src/AlignmentBuffer.cpp:1319-1388) run:
+ *   on_device = 0 (default)  host threads; results carry the full nmPerPosition array -- what the
+ *                            IAlignment plugin object needs to fill the caller's `Align`;
+ *   on_device = 1            one more kernel after the traceback: CIGAR / MD text, NM, identity,
+ *                            positions and the low-identity regions are produced on the GPU; only
+ *                            strings and 96 bytes per alignment cross PCIe. nmPerPosition (12 bytes
+ *                            per alignment column) is materialised only if want_nm_positions != 0.
+ * Results are identical either way (tests/test_gpu_text.py). Takes effect at the next upload. */
+int ngmlr_b200_set_text_stage(ngmlr_b200_ctx* ctx, int on_device, int want_nm_positions);
 
 /* Debug/parity aid: after convex_run, decode problem i's direction matrix into the reference's
  * row-major layout (AlignmentMatrixFast::directionMatrix, src/AlignmentMatrixFast.h:261): one
@@ -222,6 +245,61 @@ int ngmlr_b200_convex_upload_windows(ngmlr_b200_ctx* ctx, int n, const uint64_t*
                                      const int32_t* qry_lens, const int32_t* corridor_offsets,
                                      const int32_t* corridor_lengths, const int64_t* row_start,
                                      const int32_t* ext_qstart, const int32_t* ext_qend);
+
+/* ---- the read set resident in HBM + AlignmentBuffer::computeAlignment for a batch of intervals -----
+ * ngmlr_b200_reads_upload: the reads of a batch cross PCIe once. Stage 0/2 then runs on their
+ * sub-reads -- ReadProvider::splitRead (src/ReadProvider.cpp:57-134): floor(len / read_part_length)
+ * consecutive pieces, a read shorter than one piece is its own sub-read -- through
+ * ngmlr_b200_cs_run / ngmlr_b200_cs_fetch (sub-reads in read order), and stage 4 names read parts by
+ * index. Returns the number of sub-reads, or < 0. */
+int ngmlr_b200_reads_upload(ngmlr_b200_ctx* ctx, int n_reads, const char* const* seqs, const int32_t* lens,
+                            int read_part_length);
+int64_t ngmlr_b200_reads_h2d_bytes(const ngmlr_b200_ctx* ctx);
+
+/* Anchor (src/Types.h: Anchor::onRead / onRef / isReverse) of an interval. */
+typedef struct {
+  int32_t on_read;
+  int32_t is_reverse;
+  int64_t on_ref;
+} ngmlr_b200_anchor;
+
+/* One call of AlignmentBuffer::computeAlignment(interval, corridor, readSeq, readLength,
+ * externalQStart, externalQEnd, fullReadLength, read, realign, fullAlignment, shortRead)
+ * (src/AlignmentBuffer.cpp:226-465). readSeq is named, not shipped: the part
+ * [on_read_start, on_read_start + read_seq_len) of resident read `read_index`, reverse-complemented
+ * when `reverse` (AlignmentBuffer::extractReadSeq, :1514-1545) -- or, with read_index < 0, the text
+ * read_seq of read_seq_len characters (all intervals of a call must use the same form). */
+typedef struct {
+  int32_t read_index;
+  int32_t on_read_start;
+  int32_t read_seq_len;      /* readLength = strlen(readSeq) */
+  int32_t reverse;
+  uint64_t on_ref_start, on_ref_stop;   /* Interval::onRefStart / onRefStop */
+  int32_t corridor;          /* the corridor argument (estimateCorridor(interval), :1454-1467) */
+  int32_t ext_qstart, ext_qend;
+  int32_t full_read_length;
+  int32_t realign, full_alignment, short_read;
+  int32_t anchor_begin, n_anchors;      /* Interval::anchors as a range of the anchors array */
+  const char* read_seq;      /* only with read_index < 0 */
+} ngmlr_b200_interval;
+
+/* computeAlignment for n intervals: reference windows are decoded on the device
+ * (extractReferenceSequenceForAlignment), the corridor of every attempt -- getCorridorFull /
+ * getCorridorLinear / getCorridorEndpointsWithAnchors (multiplier < 3, not realigning, anchors
+ * present) / getCorridorEndpoints, :333-352 -- is sent in closed form and its rows are generated on
+ * the device, and while an alignment does not cover the read (cigarLength != fullReadLength) it is
+ * repeated with corridorMultiplier + 1, at most 5 times and while corridor * multiplier <=
+ * 2 * refSeqLen (:303-305). Attempt k of all intervals that are still invalid is ONE device batch.
+ * results[i].ret == full_read_length for a valid alignment; ret = -1 where computeAlignment returns 0
+ * (no reference window, every attempt invalid, or SingleAlign threw). attempts[i] (optional) = number
+ * of SingleAlign calls the reference would have made. Uses the device text stage; result strings stay
+ * valid until the next fetch / compute call on the context. Needs ngmlr_b200_cs_set_reference and
+ * ngmlr_b200_set_ref_starts. read_part_length = Config.getReadPartLength() (256). Returns n or < 0. */
+int ngmlr_b200_compute_alignments(ngmlr_b200_ctx* ctx, int n, const ngmlr_b200_interval* intervals,
+                                  const ngmlr_b200_anchor* anchors, int read_part_length,
+                                  ngmlr_b200_align_result* results, int32_t* attempts);
+/* Totals over the device batches of the last ngmlr_b200_compute_alignments call. */
+int ngmlr_b200_compute_alignments_stats(ngmlr_b200_ctx* ctx, ngmlr_b200_batch_stats* out);
 
 /* Candidate selection once a (sub-)read's candidates are scored. Replaces ScoreBuffer::topNSE and
  * ScoreBuffer::computeMQ (src/ScoreBuffer.cpp:170-192, 33-45). Host code (the reference's is too): for

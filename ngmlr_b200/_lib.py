@@ -23,7 +23,8 @@ class AlignResult(C.Structure):
                 ("first_read", C.c_int32), ("last_ref", C.c_int32), ("last_read", C.c_int32),
                 ("nm_count", C.c_int32), ("cigar_len", C.c_int32), ("md_len", C.c_int32),
                 ("cigar", C.c_char_p), ("md", C.c_char_p), ("nm_positions", C.POINTER(C.c_int32)),
-                ("cells", C.c_int64)]
+                ("cells", C.c_int64), ("n_sv_regions", C.c_int32), ("n_sv_regions_stored", C.c_int32),
+                ("sv_regions", C.POINTER(C.c_int32))]
 
 
 class BatchStats(C.Structure):
@@ -33,7 +34,21 @@ class BatchStats(C.Structure):
                 ("fill_launches", C.c_int32), ("traceback_launches", C.c_int32),
                 ("compact_launches", C.c_int32), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
                 ("host_pack_ms", C.c_float), ("host_h2d_ms", C.c_float), ("host_run_ms", C.c_float),
-                ("host_d2h_ms", C.c_float), ("host_text_ms", C.c_float), ("host_threads", C.c_int32)]
+                ("host_d2h_ms", C.c_float), ("host_text_ms", C.c_float), ("host_threads", C.c_int32),
+                ("text_ms", C.c_float), ("text_launches", C.c_int32), ("text_bytes", C.c_int64)]
+
+
+class Anchor(C.Structure):
+    _fields_ = [("on_read", C.c_int32), ("is_reverse", C.c_int32), ("on_ref", C.c_int64)]
+
+
+class Interval(C.Structure):
+    _fields_ = [("read_index", C.c_int32), ("on_read_start", C.c_int32), ("read_seq_len", C.c_int32),
+                ("reverse", C.c_int32), ("on_ref_start", C.c_uint64), ("on_ref_stop", C.c_uint64),
+                ("corridor", C.c_int32), ("ext_qstart", C.c_int32), ("ext_qend", C.c_int32),
+                ("full_read_length", C.c_int32), ("realign", C.c_int32), ("full_alignment", C.c_int32),
+                ("short_read", C.c_int32), ("anchor_begin", C.c_int32), ("n_anchors", C.c_int32),
+                ("read_seq", C.c_char_p)]
 
 
 # every symbol include/ngmlr_b200.h declares (tests/test_abi.py checks the list against the header)
@@ -47,6 +62,8 @@ C_API_SYMBOLS = (
     "ngmlr_b200_cs_set_reference", "ngmlr_b200_cs_score_batch", "ngmlr_b200_cs_upload",
     "ngmlr_b200_cs_run", "ngmlr_b200_cs_fetch", "ngmlr_b200_select_candidates",
     "ngmlr_b200_set_ref_starts", "ngmlr_b200_decode_windows", "ngmlr_b200_convex_upload_windows",
+    "ngmlr_b200_set_text_stage", "ngmlr_b200_reads_upload", "ngmlr_b200_reads_h2d_bytes",
+    "ngmlr_b200_compute_alignments", "ngmlr_b200_compute_alignments_stats",
 )
 PLUGIN_SYMBOLS = ("CreateAlignment", "DeleteAlignment", "SetAlignmentScoring")
 
@@ -106,6 +123,13 @@ def load():
     lib.ngmlr_b200_decode_windows.argtypes = [vp, C.c_int, u64p, i32p, C.c_char_p, i64p]
     lib.ngmlr_b200_convex_upload_windows.argtypes = [vp, C.c_int, u64p, u64p, cpp, i32p, i32p, i32p, i64p, i32p, i32p]
     lib.ngmlr_b200_select_candidates.argtypes = [C.c_int, i64p, C.POINTER(C.c_float), i32p, i32p, i32p]
+    lib.ngmlr_b200_set_text_stage.argtypes = [vp, C.c_int, C.c_int]
+    lib.ngmlr_b200_reads_upload.argtypes = [vp, C.c_int, cpp, i32p, C.c_int]
+    lib.ngmlr_b200_reads_h2d_bytes.argtypes = [vp]
+    lib.ngmlr_b200_reads_h2d_bytes.restype = C.c_int64
+    lib.ngmlr_b200_compute_alignments.argtypes = [vp, C.c_int, C.POINTER(Interval), C.POINTER(Anchor), C.c_int,
+                                                  C.POINTER(AlignResult), i32p]
+    lib.ngmlr_b200_compute_alignments_stats.argtypes = [vp, C.POINTER(BatchStats)]
     lib.ngmlr_b200_sw_last_kernel_ms.argtypes = [vp]
     lib.ngmlr_b200_sw_last_kernel_ms.restype = C.c_float
     _lib = lib

@@ -40,6 +40,9 @@ class Align:
     pBuffer2: str = ""   # MD
     nmPerPosition: np.ndarray = field(default_factory=lambda: np.zeros((0, 3), np.int32))
     cells: int = 0
+    nmCount: int = 0          # entries convertCigar records (nmPerPosition may be absent: device text stage)
+    nSvRegions: int = 0       # low-identity regions the peak scan of detectMisalignment closes
+    svRegions: np.ndarray = field(default_factory=lambda: np.zeros((0, 4), np.int32))
 
     def as_dict(self):
         """Same keys as tests/oracle_lib.py results, for bit-exact comparison."""
@@ -51,7 +54,7 @@ class Align:
                     cigar_op_count=self.cigarOpCount, sv_type=self.svType,
                     first_ref=self.firstPosition[0], first_read=self.firstPosition[1],
                     last_ref=self.lastPosition[0], last_read=self.lastPosition[1],
-                    nm_count=len(self.nmPerPosition), cigar=self.pBuffer1, md=self.pBuffer2,
+                    nm_count=self.nmCount, cigar=self.pBuffer1, md=self.pBuffer2,
                     nm_positions=self.nmPerPosition, score=self.Score)
 
 
@@ -135,6 +138,54 @@ def select_candidates(cand_start, sw_scores):
     if rc != n:
         raise RuntimeError("ngmlr_b200_select_candidates failed")
     return order[:sw_scores.size], kept[:n], mq[:n]
+
+
+class IntervalBatch:
+    """computeAlignment calls laid out for the C ABI (ngmlr_b200_interval / ngmlr_b200_anchor arrays),
+    built once from IntervalTask-like objects: attributes on_ref_start, on_ref_stop, corridor, ext_qstart,
+    ext_qend, full_read_length, anchors [(onRead, onRef, isReverse)], realign, full_alignment, short_read,
+    and either read_index / on_read_start / read_seq_len / reverse (resident read set) or read_seq (text)."""
+
+    def __init__(self, tasks):
+        n = len(tasks)
+        self.n = n
+        self.intervals = (_lib.Interval * max(n, 1))()
+        n_anchor = sum(len(t.anchors) for t in tasks)
+        self.anchors = (_lib.Anchor * max(n_anchor, 1))()
+        self._keep = []
+        a = 0
+        for i, t in enumerate(tasks):
+            iv = self.intervals[i]
+            ridx = getattr(t, "read_index", -1)
+            iv.read_index = ridx
+            if ridx >= 0:
+                iv.on_read_start = t.on_read_start
+                iv.read_seq_len = t.read_seq_len
+                iv.reverse = int(bool(t.reverse))
+                iv.read_seq = None
+            else:
+                seq = None if t.read_seq is None else bytes(t.read_seq)
+                self._keep.append(seq)
+                iv.on_read_start = 0
+                iv.read_seq_len = 0 if seq is None else len(seq)
+                iv.reverse = 0
+                iv.read_seq = seq
+            iv.on_ref_start = t.on_ref_start
+            iv.on_ref_stop = t.on_ref_stop
+            iv.corridor = t.corridor
+            iv.ext_qstart = t.ext_qstart
+            iv.ext_qend = t.ext_qend
+            iv.full_read_length = t.full_read_length
+            iv.realign = int(bool(t.realign))
+            iv.full_alignment = int(bool(t.full_alignment))
+            iv.short_read = int(bool(t.short_read))
+            iv.anchor_begin = a
+            iv.n_anchors = len(t.anchors)
+            for (on_read, on_ref, is_rev) in t.anchors:
+                self.anchors[a].on_read = int(on_read)
+                self.anchors[a].on_ref = int(on_ref)
+                self.anchors[a].is_reverse = int(bool(is_rev))
+                a += 1
 
 
 class B200Aligner:
@@ -302,6 +353,41 @@ class B200Aligner:
         as_np = lambda p, dt: (np.ctypeslib.as_array(p, shape=(m,)).copy() if m else np.zeros(0, dt))
         return start, as_np(sc, np.float32), as_np(lo, np.uint64), as_np(rv, np.uint8), as_np(sw, np.float32), mx[:n]
 
+    # ---- resident read set + computeAlignment for a batch of intervals -------------------------
+    def set_text_stage(self, on_device, want_nm_positions=False):
+        """Where convertCigar + the peak scan of detectMisalignment run (see ngmlr_b200_set_text_stage)."""
+        self._check(self.lib.ngmlr_b200_set_text_stage(self.h, int(bool(on_device)), int(bool(want_nm_positions))))
+
+    def reads_upload(self, reads, read_part_length=256):
+        """The reads of a batch -> HBM, once. Stage 0/2 (cs_run / cs_fetch) then runs on their sub-reads
+        (ReadProvider::splitRead, in read order), compute_alignments names read parts by index.
+        Returns the number of sub-reads."""
+        reads = reads if isinstance(reads, PackedReads) else PackedReads(reads)
+        n_sub = self._check(self.lib.ngmlr_b200_reads_upload(
+            self.h, reads.n, reads.arr, reads.lens.ctypes.data_as(C.POINTER(C.c_int32)), int(read_part_length)))
+        self._cs_n = n_sub
+        return n_sub
+
+    def reads_h2d_bytes(self):
+        return int(self.lib.ngmlr_b200_reads_h2d_bytes(self.h))
+
+    def compute_alignments(self, tasks, read_part_length=256):
+        """AlignmentBuffer::computeAlignment for every task (ngmlr_b200.intervals.IntervalTask or a
+        prepared IntervalBatch): -> (AlignBatchResult, attempts int32[n]); a record with ret < 0 means the
+        reference's computeAlignment returns 0."""
+        ib = tasks if isinstance(tasks, IntervalBatch) else IntervalBatch(tasks)
+        res = (_lib.AlignResult * max(ib.n, 1))()
+        attempts = np.zeros(max(ib.n, 1), dtype=np.int32)
+        self._check(self.lib.ngmlr_b200_compute_alignments(
+            self.h, ib.n, ib.intervals, ib.anchors, int(read_part_length), res,
+            attempts.ctypes.data_as(C.POINTER(C.c_int32))))
+        return AlignBatchResult(res, ib.n), attempts[:ib.n]
+
+    def compute_alignments_stats(self):
+        s = _lib.BatchStats()
+        self._check(self.lib.ngmlr_b200_compute_alignments_stats(self.h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in s._fields_}
+
     # ---- phased interface (bench: inputs resident in HBM) ---------------------------------
     def upload(self, batch):
         self._n = batch.n
@@ -381,7 +467,9 @@ class AlignBatchResult:
             raise IndexError(i)
         r = self._res[i]
         nm = (np.ctypeslib.as_array(r.nm_positions, shape=(r.nm_count * 3,)).reshape(-1, 3).copy()
-              if r.nm_count > 0 else np.zeros((0, 3), np.int32))
+              if r.nm_count > 0 and r.nm_positions else np.zeros((0, 3), np.int32))
+        sv = (np.ctypeslib.as_array(r.sv_regions, shape=(r.n_sv_regions_stored * 4,)).reshape(-1, 4).copy()
+              if r.n_sv_regions_stored > 0 and r.sv_regions else np.zeros((0, 4), np.int32))
         return Align(ret=r.ret, threw=bool(r.threw), Score=float(r.score),
                      Identity=float(r.identity), PositionOffset=r.position_offset,
                      QStart=r.qstart, QEnd=r.qend, NM=r.nm,
@@ -389,4 +477,5 @@ class AlignBatchResult:
                      svType=r.sv_type, firstPosition=(r.first_ref, r.first_read),
                      lastPosition=(r.last_ref, r.last_read),
                      pBuffer1=(r.cigar or b"").decode(), pBuffer2=(r.md or b"").decode(),
-                     nmPerPosition=nm, cells=r.cells)
+                     nmPerPosition=nm, cells=r.cells, nmCount=r.nm_count, nSvRegions=r.n_sv_regions,
+                     svRegions=sv)

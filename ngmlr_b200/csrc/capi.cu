@@ -4,88 +4,10 @@
 // strips), the pinned staging buffers and the stream; packs a batch of SingleAlign problems,
 // launches fill -> traceback (which also compacts the binary CIGARs), and turns the binary CIGARs into the reference's `Align`
 // fields. There is no CPU compute path: every entry point needs a CUDA device.
-#include <cuda_runtime.h>
-#include <math.h>
-#include <stdarg.h>
-#include <stdio.h>
-#include <string.h>
+#include "runtime.h"
 
-#include <algorithm>
-#include <atomic>
-#include <chrono>
-#include <numeric>
-#include <stdlib.h>
-#include <mutex>
-#include <thread>
-#include <string>
-#include <vector>
+namespace nb {
 
-#include "../../include/ngmlr_b200.h"
-#include "cigar_text.h"
-#include "device_types.h"
-#include "kernels.h"
-
-namespace {
-
-using namespace nb;
-
-std::string g_create_error;
-
-template <typename T>
-struct DevBuf {
-  T* p = nullptr;
-  size_t cap = 0;  // elements
-  cudaError_t reserve(size_t n, bool keep = false, cudaStream_t st = 0) {
-    if (n <= cap) return cudaSuccess;
-    size_t want = std::max(n, cap + cap / 2);
-    T* q = nullptr;
-    cudaError_t e = cudaMalloc(&q, want * sizeof(T));
-    if (e != cudaSuccess) return e;
-    if (keep && p && cap) cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, st);
-    if (p) {
-      cudaStreamSynchronize(st);
-      cudaFree(p);
-    }
-    p = q;
-    cap = want;
-    return cudaSuccess;
-  }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-  }
-};
-
-template <typename T>
-struct PinBuf {
-  T* p = nullptr;
-  size_t cap = 0;
-  cudaError_t reserve(size_t n) {
-    if (n <= cap) return cudaSuccess;
-    size_t want = std::max(n, cap + cap / 2);
-    T* q = nullptr;
-    cudaError_t e = cudaMallocHost(&q, want * sizeof(T));
-    if (e != cudaSuccess) return e;
-    if (p) cudaFreeHost(p);
-    p = q;
-    cap = want;
-    return cudaSuccess;
-  }
-  void release() {
-    if (p) cudaFreeHost(p);
-    p = nullptr;
-    cap = 0;
-  }
-};
-
-inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-
-inline double now_ms() {
-  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
-}
-
-// Host worker threads for packing and CIGAR/MD text (NGMLR_B200_HOST_THREADS overrides).
 int host_threads() {
   static int n = [] {
     const char* e = getenv("NGMLR_B200_HOST_THREADS");
@@ -96,34 +18,13 @@ int host_threads() {
   return n;
 }
 
-// fn(i) for i in [0, n), dynamically scheduled in chunks over host_threads() threads.
-template <typename F>
-void parallel_for(int n, int chunk, F fn) {
-  const int threads = std::min(host_threads(), (n + chunk - 1) / chunk);
-  if (threads <= 1) {
-    for (int i = 0; i < n; ++i) fn(i);
-    return;
-  }
-  std::atomic<int> next(0);
-  auto work = [&]() {
-    for (;;) {
-      const int b = next.fetch_add(chunk);
-      if (b >= n) break;
-      const int e = std::min(n, b + chunk);
-      for (int i = b; i < e; ++i) fn(i);
-    }
-  };
-  std::vector<std::thread> pool;
-  pool.reserve(threads - 1);
-  for (int t = 1; t < threads; ++t) pool.emplace_back(work);
-  work();
-  for (auto& t : pool) t.join();
-}
+}  // namespace nb
 
-// bytes readable past the end of every staged sequence (the fill kernel stages whole 64-column
-// chunks, see convex_fill.cu) and slack of the per-warp boundary strip
-constexpr size_t SEQ_PAD = 192;
-constexpr size_t STRIP_SLACK = 192;
+namespace {
+
+using namespace nb;
+
+std::string g_create_error;
 
 // Scorings for which the as-coded SSE fill (raw indelRun in the run tests) can differ from the
 // scalar rule: a gap-open out of a cell that was itself reached through the *other* gap type
@@ -142,89 +43,6 @@ bool scoring_needs_raw(const Scoring& s) {
 }  // namespace
 
 void nb_cs_release(ngmlr_b200_ctx* ctx);  // candidate-search state lives in a side table (below)
-
-struct ngmlr_b200_ctx {
-  int device = 0;
-  int num_sms = 0;
-  cudaStream_t stream = nullptr;
-  bool own_stream = true;
-  cudaEvent_t ev[6] = {};
-  Scoring sc{};
-  bool raw = false;
-  int force_raw = -1;
-  std::string error;
-
-  // ---- convex batch state ----
-  int n = 0;
-  size_t seq_bytes = 0, rows = 0, nblocks = 0, tb_ints = 0;
-  int max_len = 0;
-  int max_ref_len = 0;
-  int wide_problems = 0;  // problems whose corridor is >= 352 columns wide
-  int force_team = -1;
-  int fill_ctas_cap = 0;  // 0 = full occupancy
-  PinBuf<unsigned long long> h_win;   // windows mode: start | arena offset | (sequenceLength, span) pairs
-  DevBuf<unsigned long long> d_win;
-  int64_t upload_d2h_bytes = 0;
-  int ctas_per_sm[4] = {0, 0, 0, 0};  // occupancy of the four fill-kernel variants
-  long long debug_arena_words = -1;    // test hook: initial direction-arena size
-  PinBuf<uint8_t> h_seq;
-  PinBuf<int32_t> h_coff, h_clen, h_order, h_blkbase;
-  PinBuf<int8_t> h_delta;
-  std::vector<uint8_t> is_packed;
-  int no_corridor_packing = 0;  // NGMLR_B200_NO_CORRIDOR_PACKING=1: always ship raw CorridorLines
-  PinBuf<AlnDesc> h_desc;
-  PinBuf<FillOut> h_fill;
-  PinBuf<TraceOut> h_trace;
-  PinBuf<int32_t> h_runs;
-  PinBuf<unsigned long long> h_counters;
-  std::vector<int32_t> ext_qs, ext_qe;
-  DevBuf<uint8_t> d_seq;
-  DevBuf<int32_t> d_coff, d_clen, d_order, d_blkbase;
-  DevBuf<int8_t> d_delta;
-  DevBuf<AlnDesc> d_desc;
-  DevBuf<BlockRec> d_blocks;
-  DevBuf<uint32_t> d_dir;
-  DevBuf<BndEntry> d_bnd;
-  DevBuf<FillOut> d_fill;
-  DevBuf<int32_t> d_scratch;
-  DevBuf<TraceOut> d_trace;
-  DevBuf<int32_t> d_runs;
-  DevBuf<unsigned long long> d_counters;  // [0] dir_alloc, [1] runs_alloc, [2] work counter (as int)
-  size_t dir_words_needed = 0;
-  bool ran = false;
-  unsigned long long runs_used = 0, dir_used = 0;
-  int fill_grid = 0;
-  ngmlr_b200_batch_stats stats{};
-  std::vector<AlignText> texts;
-
-  // ---- sw state ----
-  PinBuf<uint8_t> h_sw_seq;
-  PinBuf<uint64_t> h_sw_off;
-  PinBuf<int32_t> h_sw_len;
-  PinBuf<float> h_sw_out;
-  DevBuf<uint8_t> d_sw_seq;
-  DevBuf<uint64_t> d_sw_off;
-  DevBuf<int32_t> d_sw_len;
-  DevBuf<float> d_sw_out;
-  DevBuf<int32_t> d_sw_scratch;
-
-  int fail(const char* fmt, ...) {
-    char buf[512];
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(buf, sizeof(buf), fmt, ap);
-    va_end(ap);
-    error = buf;
-    return -1;
-  }
-};
-
-#define CU(call)                                                                          \
-  do {                                                                                    \
-    cudaError_t e__ = (call);                                                             \
-    if (e__ != cudaSuccess)                                                               \
-      return ctx->fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
-  } while (0)
 
 extern "C" {
 
@@ -264,7 +82,7 @@ int ngmlr_b200_create(int gpu_id, const ngmlr_b200_scoring* s, ngmlr_b200_ctx** 
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, gpu_id);
   ctx->num_sms = prop.multiProcessorCount;
-  if (prop.major < 10) {
+  if (prop.major != 10 || prop.minor != 0) {  // only sm_100a SASS is embedded (no PTX for other architectures)
     g_create_error = "ngmlr_b200: kernels are built for sm_100a only; device is sm_" +
                      std::to_string(prop.major) + std::to_string(prop.minor);
     delete ctx;
@@ -297,7 +115,7 @@ void ngmlr_b200_destroy(ngmlr_b200_ctx* ctx) {
   ctx->h_seq.release(); ctx->h_coff.release(); ctx->h_clen.release(); ctx->h_order.release(); ctx->h_blkbase.release(); ctx->h_delta.release();
   ctx->h_desc.release(); ctx->h_fill.release(); ctx->h_trace.release(); ctx->h_runs.release();
   ctx->h_counters.release();
-  ctx->d_seq.release(); ctx->d_coff.release(); ctx->d_clen.release(); ctx->d_order.release(); ctx->d_blkbase.release(); ctx->d_delta.release(); ctx->d_win.release(); ctx->h_win.release();
+  ctx->d_seq.release(); ctx->d_coff.release(); ctx->d_clen.release(); ctx->d_order.release(); ctx->d_blkbase.release(); ctx->d_delta.release();
   ctx->d_desc.release(); ctx->d_blocks.release(); ctx->d_dir.release(); ctx->d_bnd.release();
   ctx->d_fill.release(); ctx->d_scratch.release(); ctx->d_trace.release(); ctx->d_runs.release();
   ctx->d_counters.release();
@@ -380,478 +198,7 @@ int ngmlr_b200_set_force_raw(ngmlr_b200_ctx* ctx, int v) {
 
 }  // extern "C"
 
-namespace {
-
-// Reference windows decoded on the device instead of shipped as text (convex_upload_windows).
-struct RefWindows {
-  const uint8_t* d_enc;
-  const unsigned long long* d_ref_starts;
-  int n_starts;
-  const uint64_t* win_start;  // host, n entries
-};
-
-// refs == nullptr <=> windows mode: the sequence arena then holds all reference windows first (filled
-// by decode_windows_kernel and copied back for the host CIGAR/MD stage), then all reads.
-int convex_upload_impl(ngmlr_b200_ctx* ctx, int n, const char* const* refs, const RefWindows* win,
-                       const int32_t* ref_lens, const char* const* qrys, const int32_t* qry_lens,
-                       const int32_t* corridor_offsets, const int32_t* corridor_lengths,
-                       const int64_t* row_start, const int32_t* ext_qstart, const int32_t* ext_qend) {
-  if (!ctx) return -1;
-  if (n < 0) return ctx->fail("convex_upload: n < 0");
-  CU(cudaSetDevice(ctx->device));
-  ctx->ran = false;
-  ctx->n = n;
-  if (n == 0) return 0;
-  // ---- sizes ----
-  size_t seq_bytes = 0, rows = 0, nblocks = 0, tb_ints = 0;
-  for (int i = 0; i < n; ++i) {
-    if (ref_lens[i] < 0 || qry_lens[i] < 0) return ctx->fail("convex_upload: negative length at %d", i);
-    if (row_start[i + 1] - row_start[i] != (int64_t)qry_lens[i])
-      return ctx->fail("convex_upload: problem %d has %lld corridor rows for a %d-base read "
-                       "(corridorHeight must equal qryLen)", i,
-                       (long long)(row_start[i + 1] - row_start[i]), qry_lens[i]);
-    seq_bytes += align_up((size_t)ref_lens[i] + SEQ_PAD, 16) + align_up((size_t)qry_lens[i] + SEQ_PAD, 16);
-    rows += (size_t)qry_lens[i];
-    nblocks += ((size_t)qry_lens[i] + 31) / 32;
-  }
-  CU(ctx->h_seq.reserve(seq_bytes + 64));
-  CU(ctx->h_coff.reserve(rows + 32));
-  CU(ctx->h_clen.reserve(rows + 32));
-  CU(ctx->h_delta.reserve(rows + 32));
-  CU(ctx->h_blkbase.reserve(nblocks + 1));
-  ctx->is_packed.assign(n, 0);
-  CU(ctx->h_desc.reserve(n));
-  CU(ctx->h_order.reserve(n));
-  ctx->ext_qs.assign(n, 0);
-  ctx->ext_qe.assign(n, 0);
-  // ---- pack (parallel over problems) ----
-  const double t_pack0 = now_ms();
-  const int64_t r0 = row_start[0];
-  std::vector<size_t> ref_at(n), qry_at(n), blk_at(n), tb_at(n);
-  size_t ref_region = 0;  // windows mode: bytes of the leading reference region
-  if (!refs)
-    for (int i = 0; i < n; ++i) ref_region += align_up((size_t)ref_lens[i] + SEQ_PAD, 16);
-  {
-    size_t so_ = 0, ro_ = 0, qo_ = ref_region, bo_ = 0, tb_ = 0;
-    for (int i = 0; i < n; ++i) {
-      const int rl = ref_lens[i], ql = qry_lens[i];
-      const size_t rspan = align_up((size_t)rl + SEQ_PAD, 16), qspan = align_up((size_t)ql + SEQ_PAD, 16);
-      if (refs) {
-        ref_at[i] = so_;
-        qry_at[i] = so_ + rspan;
-        so_ += rspan + qspan;
-      } else {
-        ref_at[i] = ro_;
-        qry_at[i] = qo_;
-        ro_ += rspan;
-        qo_ += qspan;
-      }
-      blk_at[i] = bo_;
-      bo_ += ((size_t)ql + 31) / 32;
-      tb_at[i] = tb_;
-      const long long ref_cap = ql > 200000 ? (long long)ql + 1 : 200000;  // maxBinaryCigarLength (:480-485)
-      tb_ += (size_t)std::min<long long>((long long)ql + rl + 4, ref_cap);
-    }
-    tb_ints = tb_;
-  }
-  std::vector<unsigned long long> est(n);
-  std::vector<size_t> dirw(n);
-  std::vector<int> maxlen(n);
-  parallel_for(n, 16, [&](int i) {
-    AlnDesc& d = ctx->h_desc.p[i];
-    memset(&d, 0, sizeof(d));
-    const int rl = ref_lens[i], ql = qry_lens[i];
-    size_t so = ref_at[i];
-    d.ref_off = so;
-    if (refs) {
-      memcpy(ctx->h_seq.p + so, refs[i], rl);
-      memset(ctx->h_seq.p + so + rl, 0, align_up((size_t)rl + SEQ_PAD, 16) - rl);
-    }
-    so = qry_at[i];
-    d.qry_off = so;
-    memcpy(ctx->h_seq.p + so, qrys[i], ql);
-    memset(ctx->h_seq.p + so + ql, 0, align_up((size_t)ql + SEQ_PAD, 16) - ql);
-    d.row_off = (uint64_t)(row_start[i] - r0);
-    d.blk_off = blk_at[i];
-    d.ref_len = rl;
-    d.height = ql;
-    d.ref_cap = ql > 200000 ? ql + 1 : 200000;
-    d.tb_cap = (int)std::min<long long>((long long)ql + rl + 4, d.ref_cap);
-    d.tb_off = tb_at[i];
-    // Corridor rows: one pass that writes the packed form (int8 offset deltas + one base per 32-row
-    // block) and finds out whether it is exact for this problem (constant length, |delta| < 128);
-    // only problems that fail ship their raw CorridorLines.
-    const int32_t* src_off = corridor_offsets + row_start[i];
-    const int32_t* src_len = corridor_lengths + row_start[i];
-    int8_t* delta = ctx->h_delta.p + d.row_off;
-    int32_t* blkbase = ctx->h_blkbase.p + d.blk_off;
-    int ml = 0;
-    unsigned long long sum = 0;
-    bool packable = !ctx->no_corridor_packing && ql > 0;
-    const int len0 = ql ? src_len[0] : 0;
-    for (int y = 0; y < ql; ++y) {
-      const int ln = src_len[y];
-      ml = std::max(ml, ln);
-      sum += (unsigned long long)std::max(ln, 0);
-      const long long dl = y ? (long long)src_off[y] - (long long)src_off[y - 1] : 0;
-      packable = packable && ln == len0 && dl >= -128 && dl <= 127;
-      delta[y] = (int8_t)dl;
-      if ((y & 31) == 0) blkbase[y >> 5] = src_off[y];
-    }
-    int32_t* lens = ctx->h_clen.p + d.row_off;
-    int32_t* offs = ctx->h_coff.p + d.row_off;
-    if (!packable && ql) {
-      memcpy(offs, src_off, (size_t)ql * sizeof(int32_t));
-      memcpy(lens, src_len, (size_t)ql * sizeof(int32_t));
-    }
-    d.packed = packable ? 1 : 0;
-    d.const_len = len0;
-    ctx->is_packed[i] = packable ? 1 : 0;
-    offs = const_cast<int32_t*>(src_off);  // the arena estimate below only needs the end points
-    d.max_len = ml;
-    maxlen[i] = std::min(ml, rl);
-    est[i] = sum;
-    // direction arena estimate: per 32-row block, steps = row width + 31 (stagger) + corridor
-    // advance over the block; the exact figure is computed by the kernel (bump allocation) and an
-    // overflow triggers a re-run with a larger arena.
-    dirw[i] = 0;
-    if (ql > 0) {
-      const long long adv_total = std::max<long long>(0, (long long)offs[ql - 1] - offs[0]);
-      const long long adv = (adv_total * 32 + std::max(ql - 1, 1) - 1) / std::max(ql - 1, 1) + 2;
-      const long long w = std::min<long long>(ml, (long long)rl);
-      const long long steps = w + 31 + adv;
-      dirw[i] = (size_t)(((size_t)ql + 31) / 32) * (size_t)((steps + 15) / 16 + 1) * 32;
-    }
-  });
-  size_t so = 0, bo = 0;
-  int max_len_all = 0;
-  size_t dir_words = 0;
-  ctx->max_ref_len = 0;
-  ctx->wide_problems = 0;
-  for (int i = 0; i < n; ++i) {
-    if (maxlen[i] >= 352) ctx->wide_problems++;
-    max_len_all = std::max(max_len_all, maxlen[i]);
-    ctx->max_ref_len = std::max(ctx->max_ref_len, ref_lens[i]);
-    dir_words += dirw[i];
-    if (ext_qstart) ctx->ext_qs[i] = ext_qstart[i];
-    if (ext_qend) ctx->ext_qe[i] = ext_qend[i];
-  }
-  so = seq_bytes;
-  bo = nblocks;
-  std::iota(ctx->h_order.p, ctx->h_order.p + n, 0);
-  std::stable_sort(ctx->h_order.p, ctx->h_order.p + n,
-                   [&](int a, int b) { return est[a] > est[b]; });
-  ctx->seq_bytes = so;
-  ctx->rows = rows;
-  ctx->nblocks = bo;
-  ctx->tb_ints = tb_ints;
-  ctx->max_len = max_len_all;
-  ctx->dir_words_needed = dir_words + dir_words / 16 + 1024;
-  const double t_pack1 = now_ms();
-  // ---- device arenas + H2D ----
-  cudaStream_t st = ctx->stream;
-  CU(ctx->d_seq.reserve(so + 64));
-  CU(ctx->d_coff.reserve(rows + 32));
-  CU(ctx->d_clen.reserve(rows + 32));
-  CU(ctx->d_desc.reserve(n));
-  CU(ctx->d_order.reserve(n));
-  CU(ctx->d_blocks.reserve(bo + 1));
-  CU(ctx->d_fill.reserve(n));
-  CU(ctx->d_trace.reserve(n));
-  CU(ctx->d_scratch.reserve(tb_ints + 32));
-  CU(ctx->d_runs.reserve(tb_ints / 4 + 4096));
-  CU(ctx->d_counters.reserve(4));
-  CU(ctx->h_counters.reserve(4));
-  CU(ctx->h_fill.reserve(n));
-  CU(ctx->h_trace.reserve(n));
-  CU(cudaMemcpyAsync(ctx->d_seq.p + ref_region, ctx->h_seq.p + ref_region, so - ref_region,
-                     cudaMemcpyHostToDevice, st));
-  if (!refs) {
-    // window descriptors -> device, decode into the reference region, bring the text back for fetch()
-    CU(ctx->h_win.reserve((size_t)n * 3 + 2));
-    CU(ctx->d_win.reserve((size_t)n * 3 + 2));
-    unsigned long long* hw = ctx->h_win.p;
-    int32_t* hl = reinterpret_cast<int32_t*>(hw + 2 * (size_t)n);
-    for (int i = 0; i < n; ++i) {
-      hw[i] = win->win_start[i];
-      hw[n + i] = ctx->h_desc.p[i].ref_off;
-      hl[i] = ref_lens[i] + 1;                                               // sequenceLength incl. NUL
-      hl[n + i] = (int32_t)align_up((size_t)ref_lens[i] + SEQ_PAD, 16);     // text + zero padding
-    }
-    CU(cudaMemcpyAsync(ctx->d_win.p, hw, (size_t)n * 24, cudaMemcpyHostToDevice, st));
-    RefDecodeParams rp;
-    rp.enc = win->d_enc;
-    rp.ref_starts = win->d_ref_starts;
-    rp.n_starts = win->n_starts;
-    rp.n = n;
-    rp.win_start = ctx->d_win.p;
-    rp.out_off = reinterpret_cast<const uint64_t*>(ctx->d_win.p + n);
-    rp.win_len = reinterpret_cast<const int32_t*>(ctx->d_win.p + 2 * (size_t)n);
-    rp.out_span = rp.win_len + n;
-    rp.out = ctx->d_seq.p;
-    CU(launch_decode_windows(rp, st));
-    CU(cudaMemcpyAsync(ctx->h_seq.p, ctx->d_seq.p, ref_region, cudaMemcpyDeviceToHost, st));
-  }
-  size_t raw_rows = 0;
-  int raw_problems = 0;
-  for (int i = 0; i < n; ++i)
-    if (!ctx->is_packed[i]) {
-      raw_rows += (size_t)qry_lens[i];
-      ++raw_problems;
-    }
-  CU(ctx->d_delta.reserve(rows + 32));
-  CU(ctx->d_blkbase.reserve(bo + 1));
-  if (rows) {
-    CU(cudaMemcpyAsync(ctx->d_delta.p, ctx->h_delta.p, rows, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ctx->d_blkbase.p, ctx->h_blkbase.p, bo * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    if (raw_problems > 64 || raw_rows * 2 > rows) {  // many raw problems: ship the arrays whole
-      CU(cudaMemcpyAsync(ctx->d_coff.p, ctx->h_coff.p, rows * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-      CU(cudaMemcpyAsync(ctx->d_clen.p, ctx->h_clen.p, rows * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-      raw_rows = rows;
-    } else {
-      for (int i = 0; i < n; ++i) {
-        if (ctx->is_packed[i] || !qry_lens[i]) continue;
-        const size_t ro = (size_t)ctx->h_desc.p[i].row_off, nb = (size_t)qry_lens[i] * sizeof(int32_t);
-        CU(cudaMemcpyAsync(ctx->d_coff.p + ro, ctx->h_coff.p + ro, nb, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(ctx->d_clen.p + ro, ctx->h_clen.p + ro, nb, cudaMemcpyHostToDevice, st));
-      }
-    }
-  }
-  CU(cudaMemcpyAsync(ctx->d_desc.p, ctx->h_desc.p, (size_t)n * sizeof(AlnDesc), cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(ctx->d_order.p, ctx->h_order.p, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-  CU(cudaStreamSynchronize(st));
-  ctx->stats = ngmlr_b200_batch_stats();
-  ctx->stats.host_pack_ms = (float)(t_pack1 - t_pack0);
-  ctx->stats.host_h2d_ms = (float)(now_ms() - t_pack1);
-  ctx->stats.host_threads = host_threads();
-  ctx->stats.h2d_bytes = (int64_t)(so - ref_region + (refs ? 0 : (size_t)n * 24) + rows + bo * 4 + raw_rows * 8 +
-                                   (size_t)n * (sizeof(AlnDesc) + 4));
-  ctx->upload_d2h_bytes = (int64_t)ref_region;
-  ctx->stats.seq_bytes = (int64_t)so;
-  return 0;
-}
-
-}  // namespace
-
 extern "C" {
-
-int ngmlr_b200_convex_upload(ngmlr_b200_ctx* ctx, int n, const char* const* refs,
-                             const int32_t* ref_lens, const char* const* qrys,
-                             const int32_t* qry_lens, const int32_t* corridor_offsets,
-                             const int32_t* corridor_lengths, const int64_t* row_start,
-                             const int32_t* ext_qstart, const int32_t* ext_qend) {
-  if (ctx && n > 0 && !refs) return ctx->fail("convex_upload: refs is NULL");
-  return convex_upload_impl(ctx, n, refs, nullptr, ref_lens, qrys, qry_lens, corridor_offsets, corridor_lengths,
-                            row_start, ext_qstart, ext_qend);
-}
-
-int ngmlr_b200_convex_run(ngmlr_b200_ctx* ctx) {
-  if (!ctx) return -1;
-  if (ctx->n == 0) {
-    ctx->ran = true;
-    return 0;
-  }
-  CU(cudaSetDevice(ctx->device));
-  cudaStream_t st = ctx->stream;
-  const int n = ctx->n;
-  const double t_run0 = now_ms();
-  const bool raw = ctx->force_raw < 0 ? (ctx->raw || ctx->max_len > 32767) : (ctx->force_raw != 0);
-  // Team mode (4 warps pipeline one problem) when the corridors are wide enough for the pipeline to
-  // stay full (a warp must still be busy with its block when the fourth warp behind it has produced
-  // the first chunk of the next one: ~4 x 100 columns); NGMLR_B200_FILL_TEAM=0/1 overrides.
-  bool team = ctx->wide_problems * 2 > n;
-  if (ctx->force_team >= 0) team = ctx->force_team != 0;
-  const int variant = (raw ? 1 : 0) | (team ? 2 : 0);
-  if (!ctx->ctas_per_sm[variant]) ctx->ctas_per_sm[variant] = std::max(1, fill_max_ctas_per_sm(raw, team));
-  int per_sm = ctx->ctas_per_sm[variant];
-  if (ctx->fill_ctas_cap > 0) per_sm = std::min(per_sm, ctx->fill_ctas_cap);
-  const int max_grid = ctx->num_sms * per_sm;
-  const int want_grid = team ? n : (n + FILL_WARPS_PER_CTA - 1) / FILL_WARPS_PER_CTA;
-  const int grid = std::max(1, std::min(max_grid, want_grid));
-  ctx->fill_grid = grid;
-  const size_t warps = (size_t)grid * FILL_WARPS_PER_CTA;
-  const size_t bnd_stride = align_up((size_t)ctx->max_ref_len + STRIP_SLACK, 8);
-  CU(ctx->d_bnd.reserve(warps * bnd_stride));
-  size_t dir_words = std::max(ctx->dir_words_needed, (size_t)4096);
-  if (ctx->debug_arena_words >= 0) {  // force the overflow -> grow -> re-run path (tests)
-    dir_words = (size_t)ctx->debug_arena_words;
-    ctx->d_dir.release();
-  }
-  size_t runs_cap = ctx->d_runs.cap;
-
-  for (int attempt = 0; attempt < 16; ++attempt) {
-    CU(ctx->d_dir.reserve(dir_words));
-    CU(ctx->d_runs.reserve(runs_cap));
-    CU(cudaMemsetAsync(ctx->d_counters.p, 0, 4 * sizeof(unsigned long long), st));
-    FillParams fp;
-    fp.seq = ctx->d_seq.p;
-    fp.c_off = ctx->d_coff.p;
-    fp.c_len = ctx->d_clen.p;
-    fp.c_blkbase = ctx->d_blkbase.p;
-    fp.c_delta = ctx->d_delta.p;
-    fp.desc = ctx->d_desc.p;
-    fp.order = ctx->d_order.p;
-    fp.n = n;
-    fp.blocks = ctx->d_blocks.p;
-    fp.dir = ctx->d_dir.p;
-    fp.dir_capacity = ctx->d_dir.cap;
-    fp.dir_alloc = ctx->d_counters.p + 0;
-    fp.work_counter = reinterpret_cast<int*>(ctx->d_counters.p + 2);
-    fp.bnd = ctx->d_bnd.p;
-    fp.bnd_stride = bnd_stride;
-    fp.out = ctx->d_fill.p;
-    fp.sc = ctx->sc;
-    TraceParams tp;
-    tp.seq = ctx->d_seq.p;
-    tp.c_off = ctx->d_coff.p;
-    tp.c_len = ctx->d_clen.p;
-    tp.c_blkbase = ctx->d_blkbase.p;
-    tp.c_delta = ctx->d_delta.p;
-    tp.desc = ctx->d_desc.p;
-    tp.order = ctx->d_order.p;
-    tp.n = n;
-    tp.blocks = ctx->d_blocks.p;
-    tp.dir = ctx->d_dir.p;
-    tp.fill = ctx->d_fill.p;
-    tp.scratch = ctx->d_scratch.p;
-    tp.out = ctx->d_trace.p;
-    tp.runs = ctx->d_runs.p;
-    tp.runs_capacity = ctx->d_runs.cap;
-    tp.runs_alloc = ctx->d_counters.p + 1;
-
-    CU(cudaEventRecord(ctx->ev[0], st));
-    CU(launch_convex_fill(fp, raw, team, grid, st));
-    CU(cudaEventRecord(ctx->ev[1], st));
-    CU(launch_convex_traceback(tp, st));
-    CU(cudaEventRecord(ctx->ev[2], st));
-    CU(cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, 4 * sizeof(unsigned long long),
-                       cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    ctx->stats.fill_launches++;
-    ctx->stats.traceback_launches++;
-    const unsigned long long dir_used = ctx->h_counters.p[0], runs_used = ctx->h_counters.p[1];
-    bool again = false;
-    if (dir_used > ctx->d_dir.cap) {
-      // the counter under-reports after an overflow (warps stop allocating), so also double and
-      // fall back to the host's estimate
-      dir_words = std::max({(size_t)dir_used + (size_t)dir_used / 8 + 4096, (size_t)ctx->d_dir.cap * 2,
-                            ctx->dir_words_needed});
-      again = true;
-    }
-    if (runs_used > ctx->d_runs.cap) {
-      runs_cap = (size_t)runs_used + 4096;
-      again = true;
-    }
-    ctx->dir_used = dir_used;
-    ctx->runs_used = runs_used;
-    if (!again) break;
-    if (attempt == 15) return ctx->fail("convex_run: arena sizing did not converge");
-  }
-  ctx->dir_words_needed = std::max(ctx->dir_words_needed, (size_t)ctx->dir_used);
-  float ms = 0;
-  cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
-  ctx->stats.fill_ms = ms;
-  cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]);
-  ctx->stats.traceback_ms = ms;
-  ctx->stats.compact_ms = 0.0f;  // compaction is fused into the traceback kernel (fields kept for ABI stability)
-  ctx->stats.dir_bytes = (int64_t)ctx->dir_used * 4;
-  ctx->stats.cigar_runs = (int64_t)ctx->runs_used;
-  ctx->stats.host_run_ms = (float)(now_ms() - t_run0);
-  ctx->ran = true;
-  return 0;
-}
-
-int ngmlr_b200_convex_fetch(ngmlr_b200_ctx* ctx, ngmlr_b200_align_result* results) {
-  if (!ctx) return -1;
-  if (!ctx->ran) return ctx->fail("convex_fetch: call convex_run first");
-  const int n = ctx->n;
-  if (n == 0) return 0;
-  CU(cudaSetDevice(ctx->device));
-  cudaStream_t st = ctx->stream;
-  const double t_f0 = now_ms();
-  CU(ctx->h_runs.reserve((size_t)ctx->runs_used + 16));
-  CU(cudaMemcpyAsync(ctx->h_fill.p, ctx->d_fill.p, (size_t)n * sizeof(FillOut), cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(ctx->h_trace.p, ctx->d_trace.p, (size_t)n * sizeof(TraceOut), cudaMemcpyDeviceToHost, st));
-  if (ctx->runs_used)
-    CU(cudaMemcpyAsync(ctx->h_runs.p, ctx->d_runs.p, (size_t)ctx->runs_used * sizeof(int32_t),
-                       cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
-  const double t_f1 = now_ms();
-  ctx->stats.d2h_bytes = (int64_t)((size_t)n * (sizeof(FillOut) + sizeof(TraceOut)) + ctx->runs_used * 4) +
-                         ctx->upload_d2h_bytes;
-  if ((int)ctx->texts.size() < n) ctx->texts.resize(n);
-  for (int i = 0; i < n; ++i)
-    if (ctx->h_trace.p[i].status == ST_DIR_OVERFLOW)
-      return ctx->fail("convex_fetch: internal arena overflow survived run()");
-  parallel_for(n, 8, [&](int i) {
-    const AlnDesc& d = ctx->h_desc.p[i];
-    const FillOut& f = ctx->h_fill.p[i];
-    const TraceOut& t = ctx->h_trace.p[i];
-    ngmlr_b200_align_result& r = results[i];
-    memset(&r, 0, sizeof(r));
-    r.ret = -1;
-    r.score = -1.0f;  // align.Score = -1.0f on entry and on failure (:457, :537)
-    r.cigar = "";
-    r.md = "";
-    r.cells = (int64_t)f.cells;
-    if (t.status == ST_THROW) {
-      r.threw = 1;
-      return;
-    }
-    if (t.status != ST_OK) return;
-    AlignText& tx = ctx->texts[i];
-    const char* ref = reinterpret_cast<const char*>(ctx->h_seq.p + d.ref_off);
-    if (!binary_cigar_to_text(ctx->h_runs.p + t.run_off, t.n_runs, ref, d.ref_len, t.ref_position,
-                              ctx->ext_qs[i], ctx->ext_qe[i], tx)) {
-      r.threw = 1;
-      return;
-    }
-    r.ret = tx.ret;
-    r.score = f.best_score;
-    r.identity = tx.identity;
-    r.position_offset = t.ref_position;
-    r.qstart = tx.qstart;
-    r.qend = tx.qend;
-    r.nm = tx.nm;
-    r.alignment_length = tx.alignment_length;
-    r.cigar_op_count = tx.cigar_op_count;
-    r.sv_type = tx.sv_type;
-    r.first_ref = tx.first_ref;
-    r.first_read = tx.first_read;
-    r.last_ref = tx.last_ref;
-    r.last_read = tx.last_read;
-    r.nm_count = (int32_t)(tx.nm_positions.size() / 3);
-    r.cigar_len = (int32_t)tx.cigar.size();
-    r.md_len = (int32_t)tx.md.size();
-    r.cigar = tx.cigar.c_str();
-    r.md = tx.md.c_str();
-    r.nm_positions = tx.nm_positions.data();
-  });
-  int64_t cells = 0, steps = 0;
-  for (int i = 0; i < n; ++i) {
-    cells += (int64_t)ctx->h_fill.p[i].cells;
-    steps += ctx->h_trace.p[i].steps;
-  }
-  ctx->stats.cells = cells;
-  ctx->stats.path_steps = steps;
-  ctx->stats.host_d2h_ms = (float)(t_f1 - t_f0);
-  ctx->stats.host_text_ms = (float)(now_ms() - t_f1);
-  return 0;
-}
-
-int ngmlr_b200_convex_align_batch(ngmlr_b200_ctx* ctx, int n, const char* const* refs,
-                                  const int32_t* ref_lens, const char* const* qrys,
-                                  const int32_t* qry_lens, const int32_t* corridor_offsets,
-                                  const int32_t* corridor_lengths, const int64_t* row_start,
-                                  const int32_t* ext_qstart, const int32_t* ext_qend,
-                                  ngmlr_b200_align_result* results) {
-  int rc = ngmlr_b200_convex_upload(ctx, n, refs, ref_lens, qrys, qry_lens, corridor_offsets,
-                                    corridor_lengths, row_start, ext_qstart, ext_qend);
-  if (rc) return rc;
-  rc = ngmlr_b200_convex_run(ctx);
-  if (rc) return rc;
-  return ngmlr_b200_convex_fetch(ctx, results);
-}
 
 int ngmlr_b200_convex_stats(ngmlr_b200_ctx* ctx, ngmlr_b200_batch_stats* out) {
   if (!ctx || !out) return -1;
@@ -872,8 +219,12 @@ int ngmlr_b200_convex_debug_directions(ngmlr_b200_ctx* ctx, int i, uint8_t* dirs
   CU(cudaMemcpy(&f, ctx->d_fill.p + i, sizeof(f), cudaMemcpyDeviceToHost));
   if (nblk) CU(cudaMemcpy(blocks.data(), ctx->d_blocks.p + d.blk_off, nblk * sizeof(BlockRec), cudaMemcpyDeviceToHost));
   std::vector<int32_t> offs_v(H), lens_v(H);
+  CorridorForm form = {d.ckind, d.c0, d.cstep, d.const_len, d.cd, d.ck, d.cright};
   for (int y = 0; y < H; ++y) {
-    if (d.packed) {
+    if (d.packed == 2) {
+      offs_v[y] = corridor_form_offset(form, y);
+      lens_v[y] = d.const_len;
+    } else if (d.packed) {
       offs_v[y] = (y & 31) ? offs_v[y - 1] + ctx->h_delta.p[d.row_off + y] : ctx->h_blkbase.p[d.blk_off + (y >> 5)];
       lens_v[y] = d.const_len;
     } else {
@@ -883,8 +234,11 @@ int ngmlr_b200_convex_debug_directions(ngmlr_b200_ctx* ctx, int i, uint8_t* dirs
   }
   const int32_t* offs = offs_v.data();
   const int32_t* lens = lens_v.data();
-  const char* ref = reinterpret_cast<const char*>(ctx->h_seq.p + d.ref_off);
-  const char* qry = reinterpret_cast<const char*>(ctx->h_seq.p + d.qry_off);
+  std::vector<char> ref_v((size_t)d.ref_len + 1), qry_v((size_t)H + 1);  // from the device: works for every input form
+  if (d.ref_len) CU(cudaMemcpy(ref_v.data(), ctx->d_seq.p + d.ref_off, (size_t)d.ref_len, cudaMemcpyDeviceToHost));
+  if (H) CU(cudaMemcpy(qry_v.data(), ctx->d_seq.p + d.qry_off, (size_t)H, cudaMemcpyDeviceToHost));
+  const char* ref = ref_v.data();
+  const char* qry = qry_v.data();
   size_t total = 0;
   for (int y = 0; y < H; ++y) total += (size_t)std::max(lens[y], 0);
   if (total > dirs_cap) return ctx->fail("debug_directions: buffer too small (%zu > %zu)", total, dirs_cap);
@@ -991,54 +345,12 @@ float ngmlr_b200_sw_last_kernel_ms(ngmlr_b200_ctx* ctx) {
 // ============================================================================================
 namespace {
 
-struct CsState {
-  DevBuf<uint8_t> d_packed;
-  DevBuf<uint32_t> d_tab, d_pos, d_order;
-  DevBuf<uint32_t> d_used;  // bitmap
-  DevBuf<uint8_t> d_seq, d_tables;
-  DevBuf<uint64_t> d_off;     // seq_off | table_off | order_off | out_off
-  DevBuf<int32_t> d_len, d_count;
-  DevBuf<uint32_t> d_cap;
-  DevBuf<unsigned long long> d_hits;
-  DevBuf<float> d_max;
-  DevBuf<CsCandidate> d_out;
-  uint32_t index_len = 0, n_pos = 0;
-  uint64_t unit_offset = 0;
-  int k = 0, bin_shift = 0;
-  std::vector<float> scores;
-  std::vector<uint64_t> locs;
-  std::vector<uint8_t> reverse;
-  std::vector<float> sw_scores;
-  float last_ms = 0;
-  // candidate scoring
-  DevBuf<uint8_t> d_enc, d_rev;
-  uint64_t enc_bytes = 0, concat_len = 0;
-  DevBuf<unsigned long long> d_ref_starts;   // refStartPos (set_ref_starts)
-  std::vector<unsigned long long> ref_starts;
-  DevBuf<unsigned long long> d_winpos;
-  DevBuf<uint64_t> d_qoff;
-  DevBuf<int32_t> d_qlen;
-  DevBuf<float> d_sw;
-  DevBuf<int32_t> d_swscratch;
-  std::vector<uint64_t> last_seq_off;  // arena offsets of the reads of the last search
-  // resident pipeline
-  int rn = 0;                       // reads uploaded
-  size_t rbytes = 0;
-  DevBuf<unsigned long long> d_a, d_b, d_c, d_sa, d_sb, d_sc, d_cnt64, d_cstart, d_cloc;
-  DevBuf<uint8_t> d_scan_tmp;
-  DevBuf<float> d_cscore;
-  long long n_cand = 0;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  std::vector<int64_t> h_cstart;
-  // pinned staging for the resident pipeline's upload / fetch
-  PinBuf<uint8_t> p_seq, p_rev;
-  PinBuf<float> p_score, p_sw;
-  PinBuf<uint64_t> p_loc;
-};
-
 std::vector<std::pair<ngmlr_b200_ctx*, CsState*>> g_cs_states;
 std::mutex* g_cs_mutex = new std::mutex();
 
+}  // namespace
+
+namespace nb {
 CsState* cs_state(ngmlr_b200_ctx* ctx, bool create) {
   std::lock_guard<std::mutex> lock(*g_cs_mutex);
   for (auto& kv : g_cs_states)
@@ -1047,8 +359,7 @@ CsState* cs_state(ngmlr_b200_ctx* ctx, bool create) {
   g_cs_states.emplace_back(ctx, new CsState());
   return g_cs_states.back().second;
 }
-
-}  // namespace
+}  // namespace nb
 
 void nb_cs_release(ngmlr_b200_ctx* ctx) {
   std::lock_guard<std::mutex> lock(*g_cs_mutex);
@@ -1123,6 +434,8 @@ int ngmlr_b200_cs_search_batch(ngmlr_b200_ctx* ctx, int n, const char* const* se
     bytes += align_up((size_t)std::max(lens[i], 0) + 1, 16);
   }
   cs->last_seq_off = seq_off;
+  cs->rn = 0;              // d_seq / d_off / d_len are shared with the resident pipeline: invalidate it
+  cs->seq_base = nullptr;
   std::vector<uint8_t> hseq(bytes + 16, 0);
   parallel_for(n, 256, [&](int i) { memcpy(hseq.data() + seq_off[i], seqs[i], (size_t)std::max(lens[i], 0)); });
   CU(cs->d_seq.reserve(bytes + 16));
@@ -1167,8 +480,12 @@ int ngmlr_b200_cs_search_batch(ngmlr_b200_ctx* ctx, int n, const char* const* se
     size_t tent = 0, oent = 0, rent = 0;
     int last = first;
     while (last < n) {
-      uint32_t cap = 16;
-      while ((unsigned long long)cap < 2 * hits[last] + 2) cap <<= 1;
+      unsigned long long cap64 = 16;
+      while (cap64 < 2 * hits[last] + 2) cap64 <<= 1;
+      if (cap64 > (1ull << 31))
+        return ctx->fail("cs_search_batch: (sub-)read %d has %llu k-mer hits; split the read (ReadProvider::splitRead)",
+                         last, hits[last]);
+      const uint32_t cap = (uint32_t)cap64;
       const size_t need = (size_t)cap * 16 + (size_t)hits[last] * 4 + (size_t)hits[last] * 2 * 16;
       if (last > first && (tent * 16 + oent * 4 + rent * 16 + need) > budget) break;
       caps[last] = cap;
@@ -1349,8 +666,19 @@ int ngmlr_b200_convex_upload_windows(ngmlr_b200_ctx* ctx, int n, const uint64_t*
   w.d_ref_starts = cs ? cs->d_ref_starts.p : nullptr;
   w.n_starts = cs ? (int)cs->ref_starts.size() : 0;
   w.win_start = on_ref_start;
-  return convex_upload_impl(ctx, n, nullptr, &w, ref_lens.data(), qrys, qry_lens, corridor_offsets,
-                            corridor_lengths, row_start, ext_qstart, ext_qend);
+  UploadSpec sp;
+  sp.n = n;
+  sp.win = &w;
+  sp.ref_lens = ref_lens.data();
+  sp.qrys = qrys;
+  sp.qry_lens = qry_lens;
+  sp.corridor_offsets = corridor_offsets;
+  sp.corridor_lengths = corridor_lengths;
+  sp.row_start = row_start;
+  sp.ext_qstart = ext_qstart;
+  sp.ext_qend = ext_qend;
+  if (n > 0 && !qrys) return ctx->fail("convex_upload_windows: qrys is NULL");
+  return convex_upload_spec(ctx, sp);
 }
 
 int ngmlr_b200_cs_score_batch(ngmlr_b200_ctx* ctx, int n, const char* const* seqs,
@@ -1368,6 +696,7 @@ int ngmlr_b200_cs_score_batch(ngmlr_b200_ctx* ctx, int n, const char* const* seq
   *sw_scores = cs->sw_scores.data();
   if (n <= 0) return rc;
   const size_t m = (size_t)cand_start[n];
+  if (m > 0x7fffffffull) return ctx->fail("cs_score_batch: %zu candidates in one batch; use smaller batches", m);
   cs->sw_scores.assign(m, -1.0f);
   *sw_scores = cs->sw_scores.data();
   if (!m) return rc;
@@ -1455,6 +784,7 @@ int ngmlr_b200_cs_upload(ngmlr_b200_ctx* ctx, int n, const char* const* seqs, co
   CU(cudaStreamSynchronize(st));
   cs->rn = n;
   cs->rbytes = bytes;
+  cs->seq_base = cs->d_seq.p;
   cs->n_cand = 0;
   return 0;
 }
@@ -1471,6 +801,7 @@ int ngmlr_b200_cs_run(ngmlr_b200_ctx* ctx, float sensitivity, float min_kmer_hit
   if (n_candidates) *n_candidates = 0;
   if (kernel_ms) *kernel_ms = 0.0f;
   if (n <= 0) return 0;
+  if (!cs->seq_base) return ctx->fail("cs_run: the resident (sub-)reads were replaced by cs_search_batch; upload again");
   if (!cs->ev0) {
     CU(cudaEventCreate(&cs->ev0));
     CU(cudaEventCreate(&cs->ev1));
@@ -1496,7 +827,7 @@ int ngmlr_b200_cs_run(ngmlr_b200_ctx* ctx, float sensitivity, float min_kmer_hit
   p.bin_shift = cs->bin_shift;
   p.sensitivity = sensitivity;
   p.min_kmer_hits = min_kmer_hits;
-  p.seq = cs->d_seq.p;
+  p.seq = cs->seq_base;
   p.seq_off = cs->d_off.p;
   p.seq_len = cs->d_len.p;
   p.n = n;
@@ -1539,6 +870,7 @@ int ngmlr_b200_cs_run(ngmlr_b200_ctx* ctx, float sensitivity, float min_kmer_hit
   CU(cudaMemcpyAsync(&m64, cs->d_cstart.p + n, 8, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   const size_t m = (size_t)m64;
+  if (m > 0x7fffffffull) return ctx->fail("cs_run: %zu candidates in one batch; use smaller batches", m);
   cs->n_cand = (long long)m;
   CU(cs->d_cloc.reserve(m + 1));
   CU(cs->d_cscore.reserve(m + 1));
@@ -1558,7 +890,7 @@ int ngmlr_b200_cs_run(ngmlr_b200_ctx* ctx, float sensitivity, float min_kmer_hit
     CU(cs->d_swscratch.reserve((size_t)grid * warps_per_cta * stride * 2));
     SwParams sp;
     memset(&sp, 0, sizeof(sp));
-    sp.seq = cs->d_seq.p;
+    sp.seq = cs->seq_base;
     sp.ref_off = cs->d_qoff.p;
     sp.qry_off = cs->d_qoff.p;
     sp.ref_len = cs->d_qlen.p;

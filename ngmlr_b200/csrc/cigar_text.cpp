@@ -216,4 +216,42 @@ bool binary_cigar_to_text(const int32_t* runs, int n_runs, const char* ref, int 
   return true;
 }
 
+int scan_low_identity_regions(const int32_t* nm_positions, int nm_count, int alignment_length,
+                              std::vector<int32_t>& regions, int cap) {
+  regions.clear();
+  int closed = 0;
+  int start_ref = -1, stop_ref = -1, start_read = -1, stop_read = -1;
+  int distance = 20;  // maxDistance
+  for (int i = 0; i < alignment_length; ++i) {
+    const int nm = i < nm_count ? nm_positions[3 * i + 2] : 0;
+    const int pr = i < nm_count ? nm_positions[3 * i + 0] : 0;
+    const int pq = i < nm_count ? nm_positions[3 * i + 1] : 0;
+    const float id = (float)(32 - nm) / 32.0f;
+    const bool peak = id > 0.0f && id < 0.75f;  // isInversion (:1143-1148)
+    if (start_ref == -1) {
+      if (peak) {
+        start_ref = stop_ref = pr;
+        start_read = stop_read = pq;
+      }
+    } else if (peak) {
+      stop_ref = pr;
+      stop_read = pq;
+      distance = 20;
+    } else if (distance == 0) {
+      if (closed < cap) {
+        regions.push_back(start_ref);
+        regions.push_back(stop_ref);
+        regions.push_back(start_read);
+        regions.push_back(stop_read);
+      }
+      ++closed;
+      start_ref = stop_ref = start_read = stop_read = -1;
+      distance = 20;
+    } else {
+      --distance;
+    }
+  }
+  return closed;
+}
+
 }  // namespace nb

@@ -26,4 +26,13 @@ struct AlignText {
 bool binary_cigar_to_text(const int32_t* runs, int n_runs, const char* ref, int ref_len,
                           int ref_position, int ext_qstart, int ext_qend, AlignText& out);
 
+// The peak scan of AlignmentBuffer::detectMisalignment (src/AlignmentBuffer.cpp:1319-1388) over the
+// recorded columns: columns with 0 < (32 - nm) / 32 < 0.75 open / extend a low-identity region, the
+// 21st column in a row without one closes it. The reference's loop runs to alignment_length although
+// only nm_count entries were written; the entries in between are taken as zero (nm = 0: no peak).
+// Appends {startInv, stopInv, startInvRead, stopInvRead} of the first `cap` closed regions to
+// `regions` (cleared first) and returns how many regions were closed.
+int scan_low_identity_regions(const int32_t* nm_positions, int nm_count, int alignment_length,
+                              std::vector<int32_t>& regions, int cap);
+
 }  // namespace nb

@@ -144,12 +144,8 @@ convex_fill_kernel(const FillParams p) {
     const uint8_t* __restrict__ ref = p.seq + d.ref_off;
     const uint8_t* __restrict__ qry = p.seq + d.qry_off;
     CorridorView cv;
-    cv.off = p.c_off + d.row_off;
-    cv.len = p.c_len + d.row_off;
-    cv.blk_base = p.c_blkbase + d.blk_off;
-    cv.delta = p.c_delta + d.row_off;
-    cv.const_len = d.const_len;
-    cv.packed = d.packed;
+
+    cv.bind(p.c_off, p.c_len, p.c_blkbase, p.c_delta, d);
     const int H = d.height, ref_len = d.ref_len;
     const int nblk = (H + 31) >> 5;
 
@@ -218,9 +214,9 @@ convex_fill_kernel(const FillParams p) {
             const unsigned long long key = prog_key(b - 1, need);
             if (is0) {
               while (s_prog[prev_tw] < key) __nanosleep(64);
+              team_fence();  // acquire on the polling lane, BEFORE the barrier that releases the others
             }
             __syncwarp();
-            team_fence();
           }
         }
       };

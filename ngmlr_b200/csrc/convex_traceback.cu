@@ -58,12 +58,8 @@ __global__ void __launch_bounds__(TB_WARPS_PER_CTA * 32) convex_traceback_kernel
   const uint8_t* __restrict__ ref = p.seq + d.ref_off;
   const uint8_t* __restrict__ qry = p.seq + d.qry_off;
   CorridorView cv;
-  cv.off = p.c_off + d.row_off;
-  cv.len = p.c_len + d.row_off;
-  cv.blk_base = p.c_blkbase + d.blk_off;
-  cv.delta = p.c_delta + d.row_off;
-  cv.const_len = d.const_len;
-  cv.packed = d.packed;
+
+  cv.bind(p.c_off, p.c_len, p.c_blkbase, p.c_delta, d);
   const BlockRec* __restrict__ blocks = p.blocks + d.blk_off;
   int32_t* __restrict__ bc = p.scratch + d.tb_off;
   const int cap = d.tb_cap;        // our strip

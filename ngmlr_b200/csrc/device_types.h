@@ -1,6 +1,7 @@
 // ngmlr_b200/csrc/device_types.h -- records shared between host runtime and sm_100a kernels.
 #pragma once
 #include <stdint.h>
+#include <vector_types.h>  // int4
 
 namespace nb {
 
@@ -35,8 +36,17 @@ struct alignas(16) AlnDesc {
   int32_t tb_cap;     // ints of traceback scratch
   int32_t ref_cap;    // reference's binaryCigar capacity: max(200000, qryLen+1)  (:480-485)
   int32_t max_len;    // max corridor row length
-  int32_t const_len;  // packed corridor: the (constant) row length
-  int32_t packed;     // 1: rows are stored as int8 offset deltas + one int32 base per 32-row block
+  int32_t const_len;  // packed / closed-form corridor: the (constant) row length
+  int32_t packed;     // 0: raw CorridorLines; 1: int8 offset deltas + one int32 base per 32-row block;
+                      // 2: closed form -- no per-row data at all, rows are generated on the device
+  // closed-form corridor (packed == 2), the reference's builders (src/AlignmentBuffer.cpp:68-197):
+  //   ckind 0: offset[y] = c0 + cstep * y                       getCorridorLinear / getCorridorFull
+  //   ckind 1: offset[y] = (int)(((float)y - cd) / ck - cright)  getCorridorEndpoints (cright = 0) /
+  //                                                             getCorridorEndpointsWithAnchors (cd = 0)
+  // float32, one rounding per operation, truncation toward zero -- as the reference computes them.
+  int32_t ckind, c0, cstep;
+  float cd, ck, cright;
+  int32_t ext_qstart, ext_qend;  // externalQStart / externalQEnd of the call (device text stage)
   int32_t pad2;
 };
 
@@ -84,6 +94,21 @@ struct CorridorView {
   const int8_t* delta;
   int const_len;
   int packed;
+  int ckind, c0, cstep;
+  float cd, ck, cright;
+#ifdef __CUDACC__
+  __device__ __forceinline__ void bind(const int32_t* c_off, const int32_t* c_len, const int32_t* c_blkbase,
+                                       const int8_t* c_delta, const AlnDesc& d) {
+    off = c_off + d.row_off;
+    len = c_len + d.row_off;
+    blk_base = c_blkbase + d.blk_off;
+    delta = c_delta + d.row_off;
+    const_len = d.const_len;
+    packed = d.packed;
+    ckind = d.ckind; c0 = d.c0; cstep = d.cstep;
+    cd = d.cd; ck = d.ck; cright = d.cright;
+  }
+#endif
 };
 
 struct FillParams {
@@ -123,6 +148,57 @@ struct TraceParams {
   int32_t* runs;                       // compact arena
   unsigned long long runs_capacity;
   unsigned long long* runs_alloc;
+};
+
+// ---- device text stage (convex_text.cu) ---------------------------------------------------
+enum : int { TX_OK = 0, TX_THROW = 1, TX_OVERFLOW = 2, TX_SKIP = 3 };
+constexpr int TEXT_PEAK_CAP = 32;  // low-identity regions kept per alignment (all are counted)
+
+struct alignas(16) TextOut {
+  int32_t status;
+  int32_t ret;               // SingleAlign's return value: read bases covered by the CIGAR incl. clips
+  int32_t qstart, qend;
+  int32_t nm, alignment_length, cigar_op_count, sv_type;
+  int32_t first_ref, first_read, last_ref, last_read;
+  int32_t nm_count, cigar_len, md_len, n_peaks;
+  float identity;
+  int32_t n_peaks_stored;
+  unsigned long long text_off;  // CIGAR, NUL, MD, NUL
+  unsigned long long peak_off;  // first stored region (int4: startInv, stopInv, startInvRead, stopInvRead)
+  unsigned long long nm_off;    // first int of the nmPerPosition triples (only when requested)
+};
+
+struct TextParams {
+  const uint8_t* seq;
+  const AlnDesc* desc;
+  const int32_t* order;
+  int n;
+  const TraceOut* trace;
+  const int32_t* runs;
+  TextOut* out;
+  char* text;
+  unsigned long long text_capacity;
+  unsigned long long* text_alloc;
+  int4* peaks;
+  unsigned long long peaks_capacity;
+  unsigned long long* peaks_alloc;
+  int32_t* nm;                      // nullptr: nmPerPosition is not materialised
+  unsigned long long nm_capacity;   // ints
+  unsigned long long* nm_alloc;
+};
+
+// ---- read parts gathered from the resident read set (pipeline.cu) ---------------------------
+struct GatherParams {
+  const uint8_t* reads;        // resident read arena
+  const uint64_t* read_off;    // per read: byte offset in the arena
+  int n;
+  const int32_t* read_index;   // per problem
+  const int32_t* part_start;   // extractReadSeq: read->Seq + onReadStart
+  const int32_t* part_len;
+  const uint8_t* revcomp;      // 1: computeReverseSeq of the part (cplBase, src/AlignmentBuffer.cpp:1117-1141)
+  const uint64_t* out_off;     // byte offset of the part in `out`
+  const int32_t* out_span;     // bytes to write: the part + zero padding
+  uint8_t* out;
 };
 
 // ---- reference windows (DecodeRefSequenceExact) -------------------------------------------
@@ -177,6 +253,14 @@ struct CsParams {
 __device__ __forceinline__ void load_corridor_rows(const CorridorView& c, int blk, int lane, int H, int& off,
                                                    int& len) {
   const int y = (blk << 5) + lane;
+  if (c.packed == 2) {  // closed form: the reference's own float32 expression, evaluated per row
+    int o;
+    if (c.ckind == 0) o = c.c0 + c.cstep * y;
+    else o = (int)__fsub_rn(__fdiv_rn(__fsub_rn((float)y, c.cd), c.ck), c.cright);
+    off = y < H ? o : 0;
+    len = y < H ? c.const_len : 0;
+    return;
+  }
   if (!c.packed) {
     off = y < H ? c.off[y] : 0;
     len = y < H ? c.len[y] : 0;

@@ -40,6 +40,12 @@ cudaError_t launch_sw_score_gather(const SwParams& p, int grid, cudaStream_t str
 
 cudaError_t launch_decode_windows(const RefDecodeParams& p, cudaStream_t stream);
 
+// binary CIGAR -> CIGAR/MD text, NM, identity, positions, low-identity regions (convex_text.cu)
+cudaError_t launch_convex_text(const TextParams& p, cudaStream_t stream);
+
+// read parts (optionally reverse-complemented) from the resident read set into the sequence arena
+cudaError_t launch_gather_reads(const GatherParams& p, cudaStream_t stream);
+
 cudaError_t launch_cs_search(const CsParams& p, bool count_only, cudaStream_t stream);
 cudaError_t launch_unpack_index(const uint8_t* packed, uint32_t n, uint32_t* tab, uint32_t* used_bits,
                                 cudaStream_t stream);

@@ -49,14 +49,24 @@ struct AlignRequest {
   NgmlrB200BatchAlignArgs args;
   int ret = -1;
   bool threw = false, done = false;
-  const char* error = nullptr;
+  bool failed = false;
+  std::string error;  // owned by the request: the next batch cannot overwrite what a client is still throwing
 };
 class B200Alignment;
+// what a thrown `const char*` points at must outlive the throw: one string per calling thread
+std::string& thread_error() {
+  static thread_local std::string e;
+  return e;
+}
 bool batcher_submit(int gpu_id, const ngmlr_b200_scoring& scoring, AlignRequest& r);
 
 class B200Alignment : public IAlignment {
  public:
-  explicit B200Alignment(int gpu_id) : gpu_id_(gpu_id), scoring_(g_scoring) {
+  explicit B200Alignment(int gpu_id, const ngmlr_b200_scoring& scoring) : gpu_id_(gpu_id), scoring_(scoring) {
+    if (const char* e = getenv("NGMLR_B200_MAX_MATRIX_MB")) {  // Config.getMaxMatrixSizeMB() (--max-matrix-size)
+      const long v = atol(e);
+      if (v > 0) max_matrix_mb_ = (unsigned long)v;
+    }
     {
       std::lock_guard<std::mutex> lock(g_pool_mutex);
       for (size_t i = 0; i < g_pool.size(); ++i) {
@@ -117,7 +127,10 @@ class B200Alignment : public IAlignment {
       req.result = &result;
       req.args = a;
       if (batcher_submit(gpu_id_, scoring_, req)) {  // false: batching is off -> direct path below
-        if (req.error) throw req.error;
+        if (req.failed) {
+          thread_error() = req.error;
+          throw thread_error().c_str();
+        }
         if (req.threw) throw 1;
         return req.ret;
       }
@@ -150,60 +163,83 @@ class B200Alignment : public IAlignment {
                   NgmlrB200BatchAlignArgs* args, int* rets, bool* threw_out) {
     ref_len_.resize(n);
     qry_len_.resize(n);
-    row_start_.resize(n + 1);
     qs_.resize(n);
     qe_.resize(n);
-    size_t rows = 0;
+    std::vector<char> too_big((size_t)n, 0);  // local: a throw below must not leave state behind
     for (int i = 0; i < n; ++i) {
       ref_len_[i] = (int32_t)strlen(refs[i]);  // lengths by strlen (:463-464)
       qry_len_[i] = (int32_t)strlen(qrys[i]);
-      row_start_[i] = (int64_t)rows;
-      rows += (size_t)qry_len_[i];
       qs_[i] = args[i].externalQStart;
       qe_[i] = args[i].externalQEnd;
+      if (args[i].corridorHeight < qry_len_[i]) throw "corridorHeight < read length";
     }
-    row_start_[n] = (int64_t)rows;
-    off_.resize(rows);
-    len_.resize(rows);
     for (int i = 0; i < n; ++i) {
       // matrix->prepare(): rows = qryLen; also publishes offsetInMatrix to the caller's lines
       // (src/AlignmentMatrixFast.cpp:36-43)
       CorridorLine* c = args[i].corridor;
-      int32_t* o = off_.data() + row_start_[i];
-      int32_t* l = len_.data() + row_start_[i];
       unsigned long at = 0;
       const int h = args[i].corridorHeight;
       for (int y = 0; y < h; ++y) {
         c[y].offsetInMatrix = at;
         at += (unsigned long)c[y].length;
       }
-      if (h < qry_len_[i]) throw "corridorHeight < read length";
+      // prepare() refuses matrices of >= maxMatrixSizeMB MB -> the alignment fails (:45-58); such a
+      // problem never reaches the device
+      too_big[i] = (unsigned long)((float)at / 1000.0f / 1000.0f) >= max_matrix_mb_;
+    }
+    // the problems that go to the device, in order
+    keep_.clear();
+    for (int i = 0; i < n; ++i)
+      if (!too_big[i]) keep_.push_back(i);
+    const int m = (int)keep_.size();
+    row_start_.resize((size_t)m + 1);
+    krefs_.resize(m); kqrys_.resize(m); krl_.resize(m); kql_.resize(m); kqs_.resize(m); kqe_.resize(m);
+    size_t rows = 0;
+    for (int j = 0; j < m; ++j) {
+      const int i = keep_[j];
+      row_start_[j] = (int64_t)rows;
+      rows += (size_t)qry_len_[i];
+      krefs_[j] = refs[i]; kqrys_[j] = qrys[i];
+      krl_[j] = ref_len_[i]; kql_[j] = qry_len_[i]; kqs_[j] = qs_[i]; kqe_[j] = qe_[i];
+    }
+    row_start_[m] = (int64_t)rows;
+    off_.resize(rows);
+    len_.resize(rows);
+    for (int j = 0; j < m; ++j) {
+      const int i = keep_[j];
+      CorridorLine* c = args[i].corridor;
+      int32_t* o = off_.data() + row_start_[j];
+      int32_t* l = len_.data() + row_start_[j];
       for (int y = 0; y < qry_len_[i]; ++y) {
         o[y] = c[y].offset;
         l[y] = c[y].length;
       }
-      // prepare() refuses matrices of >= maxMatrixSizeMB (10000) MB -> alignment fails (:45-58)
-      too_big_.push_back((unsigned long)((float)at / 1000.0f / 1000.0f) >= 10000ul);
     }
-    res_.resize(n);
+    res_.resize((size_t)std::max(m, 1));
     for (int i = 0; i < n; ++i) {
       results[i]->svType = 0;  // (:454-457)
       results[i]->Score = -1.0f;
       rets[i] = -1;
       if (threw_out) threw_out[i] = false;
     }
-    int rc = ngmlr_b200_convex_align_batch(ctx_, n, refs, ref_len_.data(), qrys, qry_len_.data(),
-                                           off_.data(), len_.data(), row_start_.data(), qs_.data(),
-                                           qe_.data(), res_.data());
-    if (rc != 0) {
-      too_big_.clear();
-      throw ngmlr_b200_last_error(ctx_);
+    if (m > 0) {
+      int rc = ngmlr_b200_convex_align_batch(ctx_, m, krefs_.data(), krl_.data(), kqrys_.data(), kql_.data(),
+                                             off_.data(), len_.data(), row_start_.data(), kqs_.data(),
+                                             kqe_.data(), res_.data());
+      if (rc != 0) {
+        // Device memory exhausted by the direction matrix is the reference's "matrix too large": -1
+        // per problem instead of an exception that would end the whole run.
+        const char* e = ngmlr_b200_last_error(ctx_);
+        if (e && strstr(e, "out of memory")) return;
+        error_ = e ? e : "ngmlr_b200: batched alignment failed";
+        throw error_.c_str();
+      }
     }
     bool threw = false;
-    for (int i = 0; i < n; ++i) {
-      const ngmlr_b200_align_result& r = res_[i];
+    for (int j = 0; j < m; ++j) {
+      const int i = keep_[j];
+      const ngmlr_b200_align_result& r = res_[j];
       Align& a = *results[i];
-      if (too_big_[i]) continue;
       if (a.pBuffer2) a.pBuffer2[0] = '\0';  // (:469)
       if (r.threw) {
         threw = true;
@@ -253,7 +289,6 @@ class B200Alignment : public IAlignment {
       a.svType = r.sv_type;
       rets[i] = r.ret;
     }
-    too_big_.clear();
     if (threw && n == 1 && !threw_out) throw 1;  // caller wraps SingleAlign in try/catch(...) -> unmapped
   }
 
@@ -261,10 +296,13 @@ class B200Alignment : public IAlignment {
   int gpu_id_ = 0;
   ngmlr_b200_scoring scoring_;
   ngmlr_b200_ctx* ctx_ = nullptr;
-  std::vector<int32_t> ref_len_, qry_len_, off_, len_, qs_, qe_;
+  unsigned long max_matrix_mb_ = 10000ul;  // Config.getMaxMatrixSizeMB() default (src/IConfig.h)
+  std::vector<int32_t> ref_len_, qry_len_, off_, len_, qs_, qe_, krl_, kql_, kqs_, kqe_;
   std::vector<int64_t> row_start_;
+  std::vector<int> keep_;
+  std::vector<char const*> krefs_, kqrys_;
   std::vector<ngmlr_b200_align_result> res_;
-  std::vector<bool> too_big_;
+  std::string error_;
 };
 
 // ---- cross-thread batcher ("a GPU implementation that batches across threads
@@ -278,10 +316,7 @@ class Batcher {
  public:
   Batcher(int gpu_id, const ngmlr_b200_scoring& sc, int window_us, int max_batch)
       : gpu_id_(gpu_id), scoring_(sc), window_us_(window_us), max_batch_(max_batch) {
-    const ngmlr_b200_scoring saved = g_scoring;
-    g_scoring = sc;  // the server object takes the scoring of its first client
-    server_ = new B200Alignment(gpu_id);
-    g_scoring = saved;
+    server_ = new B200Alignment(gpu_id, sc);  // the server object takes the scoring of its first client
     if (server_->ok()) {
       worker_ = std::thread([this] { loop(); });
       worker_.detach();  // lives for the process: never torn down behind the CUDA runtime's back
@@ -326,22 +361,24 @@ class Batcher {
         results[i] = batch[i]->result;
         args[i] = batch[i]->args;
       }
-      const char* error = nullptr;
+      bool failed = false;
+      std::string error;
       try {
         server_->align_many(n, refs.data(), qrys.data(), results.data(), args.data(), rets.data(),
                             reinterpret_cast<bool*>(threw.data()));
       } catch (const char* e) {
-        error_ = e ? e : "batched alignment failed";
-        error = error_.c_str();
+        failed = true;
+        error = e ? e : "batched alignment failed";
       } catch (...) {
-        error_ = "batched alignment failed";
-        error = error_.c_str();
+        failed = true;
+        error = "batched alignment failed";
       }
       {
         std::lock_guard<std::mutex> lk(m_);
         for (int i = 0; i < n; ++i) {
           batch[i]->ret = rets[i];
           batch[i]->threw = threw[i] != 0;
+          batch[i]->failed = failed;
           batch[i]->error = error;
           batch[i]->done = true;
         }
@@ -358,7 +395,6 @@ class Batcher {
   std::mutex m_;
   std::condition_variable cv_work_, cv_done_;
   std::vector<AlignRequest*> queue_;
-  std::string error_;
 };
 
 bool batcher_submit(int gpu_id, const ngmlr_b200_scoring& scoring, AlignRequest& r) {
@@ -387,7 +423,12 @@ bool batcher_submit(int gpu_id, const ngmlr_b200_scoring& scoring, AlignRequest&
 extern "C" {
 
 IAlignment* CreateAlignment(int const gpu_id) {
-  B200Alignment* a = new B200Alignment(gpu_id);
+  ngmlr_b200_scoring sc;
+  {
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    sc = g_scoring;
+  }
+  B200Alignment* a = new B200Alignment(gpu_id, sc);
   if (!a->ok()) {  // fail loudly: no CPU fallback
     delete a;
     return nullptr;
@@ -399,6 +440,7 @@ void DeleteAlignment(IAlignment* aligner) { delete aligner; }
 
 void SetAlignmentScoring(float match, float mismatch, float gapOpen, float gapExtend,
                          float gapExtendMin, float gapDecay) {
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
   g_scoring.match = match;
   g_scoring.mismatch = mismatch;
   g_scoring.gap_open = gapOpen;

@@ -65,7 +65,37 @@ __global__ void __launch_bounds__(256) decode_windows_kernel(const RefDecodePara
   }
 }
 
+// Read parts for alignment, taken from the read set that is already resident in HBM (uploaded once for
+// stage 0/2): AlignmentBuffer::extractReadSeq (src/AlignmentBuffer.cpp:1514-1545) -- the part
+// read->Seq[onReadStart, +len) as it is, or its reverse complement (computeReverseSeq / cplBase,
+// :1117-1141: only upper-case A C G T are complemented). One CTA per part.
+__global__ void __launch_bounds__(256) gather_reads_kernel(const GatherParams p) {
+  const int w = blockIdx.x;
+  const uint8_t* __restrict__ src = p.reads + p.read_off[p.read_index[w]] + p.part_start[w];
+  const int len = p.part_len[w], span = p.out_span[w];
+  const bool rc = p.revcomp[w] != 0;
+  uint8_t* __restrict__ out = p.out + p.out_off[w];
+  for (int i = threadIdx.x; i < span; i += blockDim.x) {
+    uint8_t c = 0;
+    if (i < len) {
+      if (rc) {
+        const uint8_t b = src[len - 1 - i];
+        c = b == 'A' ? 'T' : (b == 'T' ? 'A' : (b == 'C' ? 'G' : (b == 'G' ? 'C' : b)));
+      } else {
+        c = src[i];
+      }
+    }
+    out[i] = c;
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_gather_reads(const GatherParams& p, cudaStream_t stream) {
+  if (p.n <= 0) return cudaSuccess;
+  gather_reads_kernel<<<p.n, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_decode_windows(const RefDecodeParams& p, cudaStream_t stream) {
   if (p.n <= 0) return cudaSuccess;

@@ -210,7 +210,8 @@ __global__ void __launch_bounds__(SW_WARPS_PER_CTA * 32) sw_score_kernel(const S
           const int L = qlen - 1;
           qc[r] = row < L ? nt_code_cpl(qry[L - 1 - row]) : (row < qlen ? 4 : -1);
         } else {
-          qc[r] = row < qlen ? nt_code(qry[row]) : -1;
+          // the terminator is code 4 by position, not by content: a sub-read may be a view into a longer read
+          qc[r] = row < qlen - 1 ? nt_code(qry[row]) : (row < qlen ? 4 : -1);
         }
         H[r] = 0;
         E[r] = 0;

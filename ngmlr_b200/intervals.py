@@ -37,10 +37,17 @@ class IntervalTask:
     full_alignment: bool = False
     short_read: bool = False
     read_part_length: int = 256
+    # the read part named by index into the resident read set (B200Aligner.reads_upload) instead of as text
+    read_index: int = -1
+    on_read_start: int = 0
+    read_seq_len: int = 0
+    reverse: bool = False
 
     def __post_init__(self):
+        if self.read_seq is not None and not self.read_seq_len:
+            self.read_seq_len = len(self.read_seq)
         if not self.full_read_length:
-            self.full_read_length = len(self.read_seq) + self.ext_qstart + self.ext_qend
+            self.full_read_length = self.read_seq_len + self.ext_qstart + self.ext_qend
 
 
 def _corridor_for(task, ref_len, multiplier):

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.C_API_SYMBOLS), declared ^ set(_lib.C_API_SYMBOLS)
     for s in list(declared) + list(_lib.PLUGIN_SYMBOLS):
         assert hasattr(lib, s), s
-    assert lib.ngmlr_b200_abi_version() == 1
+    assert lib.ngmlr_b200_abi_version() == 2
     assert lib.ngmlr_b200_plugin_cookie() == 0x10201130  # cCookie, src/IAlignment.h:193
 
 
@@ -31,9 +31,13 @@ def test_result_struct_layout_matches_header():
 #include <stddef.h>
 #include "ngmlr_b200.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(ngmlr_b200_align_result), offsetof(ngmlr_b200_align_result, cigar),
+  printf("%zu %zu %zu %zu %zu %zu ", sizeof(ngmlr_b200_align_result), offsetof(ngmlr_b200_align_result, cigar),
          offsetof(ngmlr_b200_align_result, cells), sizeof(ngmlr_b200_batch_stats),
          offsetof(ngmlr_b200_batch_stats, fill_ms), sizeof(ngmlr_b200_scoring));
+  printf("%zu %zu %zu %zu %zu %zu %zu\n", offsetof(ngmlr_b200_align_result, sv_regions),
+         offsetof(ngmlr_b200_batch_stats, text_bytes), sizeof(ngmlr_b200_interval),
+         offsetof(ngmlr_b200_interval, on_ref_stop), offsetof(ngmlr_b200_interval, read_seq),
+         sizeof(ngmlr_b200_anchor), offsetof(ngmlr_b200_anchor, on_ref));
   return 0;
 }'''
     import tempfile
@@ -43,7 +47,10 @@ int main(void) {
                         os.path.join(d, "t.c")], check=True)
         out = subprocess.run([os.path.join(d, "t")], capture_output=True, text=True, check=True).stdout.split()
     got = [C.sizeof(_lib.AlignResult), _lib.AlignResult.cigar.offset, _lib.AlignResult.cells.offset,
-           C.sizeof(_lib.BatchStats), _lib.BatchStats.fill_ms.offset, C.sizeof(_lib.Scoring)]
+           C.sizeof(_lib.BatchStats), _lib.BatchStats.fill_ms.offset, C.sizeof(_lib.Scoring),
+           _lib.AlignResult.sv_regions.offset, _lib.BatchStats.text_bytes.offset, C.sizeof(_lib.Interval),
+           _lib.Interval.on_ref_stop.offset, _lib.Interval.read_seq.offset, C.sizeof(_lib.Anchor),
+           _lib.Anchor.on_ref.offset]
     assert [int(x) for x in out] == got
 
 
