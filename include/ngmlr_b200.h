@@ -298,6 +298,12 @@ typedef struct {
 int ngmlr_b200_compute_alignments(ngmlr_b200_ctx* ctx, int n, const ngmlr_b200_interval* intervals,
                                   const ngmlr_b200_anchor* anchors, int read_part_length,
                                   ngmlr_b200_align_result* results, int32_t* attempts);
+/* The first attempt of ngmlr_b200_compute_alignments only, staged for the phased calls:
+ * ngmlr_b200_convex_run / ngmlr_b200_convex_fetch then operate on it (benchmarks time the kernels with
+ * the batch resident in HBM). Every interval must reach SingleAlign. Switches the context to the device
+ * text stage. */
+int ngmlr_b200_intervals_upload(ngmlr_b200_ctx* ctx, int n, const ngmlr_b200_interval* intervals,
+                                const ngmlr_b200_anchor* anchors, int read_part_length);
 /* Totals over the device batches of the last ngmlr_b200_compute_alignments call. */
 int ngmlr_b200_compute_alignments_stats(ngmlr_b200_ctx* ctx, ngmlr_b200_batch_stats* out);
 

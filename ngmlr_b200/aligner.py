@@ -383,6 +383,12 @@ class B200Aligner:
             attempts.ctypes.data_as(C.POINTER(C.c_int32))))
         return AlignBatchResult(res, ib.n), attempts[:ib.n]
 
+    def intervals_upload(self, tasks, read_part_length=256):
+        """Stage the first attempt of compute_alignments for run() / fetch() (inputs resident in HBM)."""
+        ib = tasks if isinstance(tasks, IntervalBatch) else IntervalBatch(tasks)
+        self._n = ib.n
+        self._check(self.lib.ngmlr_b200_intervals_upload(self.h, ib.n, ib.intervals, ib.anchors, int(read_part_length)))
+
     def compute_alignments_stats(self):
         s = _lib.BatchStats()
         self._check(self.lib.ngmlr_b200_compute_alignments_stats(self.h, C.byref(s)))

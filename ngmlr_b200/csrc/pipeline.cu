@@ -95,6 +95,99 @@ CorridorForm corridor_for(const ngmlr_b200_interval& iv, const ngmlr_b200_anchor
   return f;
 }
 
+// Scratch of one device batch of intervals (attempt k of a compute_alignments call).
+struct IntervalBatchBuf {
+  std::vector<uint64_t> win_start;
+  std::vector<int32_t> ref_lens, qry_lens, ridx, pstart, eqs, eqe;
+  std::vector<uint8_t> rc;
+  std::vector<const char*> qtext;
+  std::vector<CorridorForm> forms;
+};
+
+int upload_interval_batch(ngmlr_b200_ctx* ctx, CsState* cs, const ngmlr_b200_interval* intervals,
+                          const ngmlr_b200_anchor* anchors, const std::vector<int>& batch,
+                          const std::vector<IvState>& st, int read_part_length, bool by_index,
+                          IntervalBatchBuf& b) {
+  const int m = (int)batch.size();
+  b.win_start.resize(m); b.ref_lens.resize(m); b.qry_lens.resize(m); b.ridx.resize(m); b.pstart.resize(m);
+  b.eqs.resize(m); b.eqe.resize(m); b.rc.resize(m); b.forms.resize(m); b.qtext.resize(m);
+  for (int j = 0; j < m; ++j) {
+    const ngmlr_b200_interval& iv = intervals[batch[j]];
+    const IvState& s = st[batch[j]];
+    b.win_start[j] = iv.on_ref_start;
+    b.ref_lens[j] = s.ref_seq_len - 1;
+    b.qry_lens[j] = iv.read_seq_len;
+    b.ridx[j] = iv.read_index;
+    b.pstart[j] = iv.on_read_start;
+    b.rc[j] = iv.reverse ? 1 : 0;
+    b.qtext[j] = iv.read_seq;
+    b.eqs[j] = iv.ext_qstart;
+    b.eqe[j] = iv.ext_qend;
+    b.forms[j] = corridor_for(iv, anchors, s, read_part_length);
+  }
+  RefWindows w;
+  w.d_enc = cs->d_enc.p;
+  w.d_ref_starts = cs->d_ref_starts.p;
+  w.n_starts = (int)cs->ref_starts.size();
+  w.win_start = b.win_start.data();
+  ReadParts rp;
+  rp.d_reads = ctx->d_reads.p;
+  rp.d_read_off = ctx->d_read_off.p;
+  rp.read_index = b.ridx.data();
+  rp.part_start = b.pstart.data();
+  rp.revcomp = b.rc.data();
+  UploadSpec sp;
+  sp.n = m;
+  sp.win = &w;
+  sp.ref_lens = b.ref_lens.data();
+  if (by_index) sp.parts = &rp;
+  else sp.qrys = b.qtext.data();
+  sp.qry_lens = b.qry_lens.data();
+  sp.forms = b.forms.data();
+  sp.ext_qstart = b.eqs.data();
+  sp.ext_qend = b.eqe.data();
+  return convex_upload_spec(ctx, sp);
+}
+
+// Validates the intervals and initialises their retry state. live = intervals that reach SingleAlign.
+int prepare_intervals(ngmlr_b200_ctx* ctx, CsState* cs, int n, const ngmlr_b200_interval* intervals,
+                      std::vector<IvState>& st, std::vector<int>& live, bool& by_index) {
+  if (!cs || !cs->enc_bytes || cs->ref_starts.empty())
+    return ctx->fail("compute_alignments: call cs_set_reference and set_ref_starts first");
+  bool any_text = false, any_index = false;
+  for (int i = 0; i < n; ++i) {
+    if (intervals[i].read_index >= 0) any_index = true;
+    else any_text = true;
+  }
+  if (any_text && any_index)
+    return ctx->fail("compute_alignments: intervals must all name resident reads or all carry read_seq");
+  if (any_index && ctx->n_reads == 0) return ctx->fail("compute_alignments: call reads_upload first");
+  by_index = any_index;
+  st.assign((size_t)n, IvState());
+  live.clear();
+  live.reserve(n);
+  for (int i = 0; i < n; ++i) {
+    const ngmlr_b200_interval& iv = intervals[i];
+    if (iv.read_index < 0 && !iv.read_seq) continue;                       // readSeq == nullptr -> 0 (:237-239)
+    if (iv.on_ref_start >= iv.on_ref_stop) continue;                        // (:204-207)
+    if (iv.on_ref_stop - iv.on_ref_start > 0x7ffffff0ull) continue;
+    if (!window_ok(cs, iv.on_ref_start)) continue;                          // DecodeRefSequenceExact fails
+    if (iv.read_seq_len < 0) return ctx->fail("compute_alignments: negative read length at %d", i);
+    if (iv.read_index >= 0) {
+      if (iv.read_index >= ctx->n_reads) return ctx->fail("compute_alignments: read index out of range at %d", i);
+      if (iv.on_read_start < 0 || (int64_t)iv.on_read_start + iv.read_seq_len > ctx->read_len[iv.read_index])
+        return ctx->fail("compute_alignments: interval %d leaves its read", i);
+    }
+    IvState& s = st[i];
+    s.ref_seq_len = (int)(iv.on_ref_stop - iv.on_ref_start + 1);
+    s.corridor = std::min(iv.corridor, s.ref_seq_len * 2);  // (:266-267)
+    s.retry = iv.full_alignment ? 1 : 5;
+    s.mult = 1;
+    live.push_back(i);
+  }
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -175,21 +268,12 @@ int ngmlr_b200_compute_alignments(ngmlr_b200_ctx* ctx, int n, const ngmlr_b200_i
   if (!ctx) return -1;
   if (n < 0) return ctx->fail("compute_alignments: n < 0");
   CsState* cs = cs_state(ctx, false);
-  if (!cs || !cs->enc_bytes || cs->ref_starts.empty())
-    return ctx->fail("compute_alignments: call cs_set_reference and set_ref_starts first");
-  bool any_text = false, any_index = false;
-  for (int i = 0; i < n; ++i) {
-    if (intervals[i].read_index >= 0) any_index = true;
-    else any_text = true;
-  }
-  if (any_text && any_index)
-    return ctx->fail("compute_alignments: intervals must all name resident reads or all carry read_seq");
-  if (any_index && ctx->n_reads == 0) return ctx->fail("compute_alignments: call reads_upload first");
+  std::vector<IvState> st;
+  std::vector<int> live;
+  bool by_index = false;
+  if (prepare_intervals(ctx, cs, n, intervals, st, live, by_index)) return -1;
   const int saved_mode = ctx->text_mode, saved_slot = ctx->text_slot;
   ctx->text_mode = 1;  // results of every attempt stay valid in their own pinned arena
-  std::vector<IvState> st((size_t)n);
-  std::vector<int> live;
-  live.reserve(n);
   ctx->ca_h2d_bytes = ctx->ca_d2h_bytes = 0;
   ctx->ca_fill_ms = ctx->ca_traceback_ms = ctx->ca_text_ms = 0.0f;
   ctx->ca_cells = 0;
@@ -202,30 +286,9 @@ int ngmlr_b200_compute_alignments(ngmlr_b200_ctx* ctx, int n, const ngmlr_b200_i
     r.cigar = "";
     r.md = "";
     if (attempts) attempts[i] = 0;
-    const ngmlr_b200_interval& iv = intervals[i];
-    if (iv.read_index < 0 && !iv.read_seq) continue;                       // readSeq == nullptr -> 0 (:237-239)
-    if (iv.on_ref_start >= iv.on_ref_stop) continue;                        // (:204-207)
-    if (iv.on_ref_stop - iv.on_ref_start > 0x7ffffff0ull) continue;
-    if (!window_ok(cs, iv.on_ref_start)) continue;                          // DecodeRefSequenceExact fails
-    if (iv.read_seq_len < 0) return ctx->fail("compute_alignments: negative read length at %d", i);
-    if (iv.read_index >= 0) {
-      if (iv.read_index >= ctx->n_reads) return ctx->fail("compute_alignments: read index out of range at %d", i);
-      if (iv.on_read_start < 0 || (int64_t)iv.on_read_start + iv.read_seq_len > ctx->read_len[iv.read_index])
-        return ctx->fail("compute_alignments: interval %d leaves its read", i);
-    }
-    IvState& s = st[i];
-    s.ref_seq_len = (int)(iv.on_ref_stop - iv.on_ref_start + 1);
-    s.corridor = std::min(iv.corridor, s.ref_seq_len * 2);  // (:266-267)
-    s.retry = iv.full_alignment ? 1 : 5;
-    s.mult = 1;
-    live.push_back(i);
   }
   std::vector<int> batch;
-  std::vector<uint64_t> win_start;
-  std::vector<int32_t> ref_lens, qry_lens, ridx, pstart, eqs, eqe;
-  std::vector<uint8_t> rc;
-  std::vector<const char*> qtext;
-  std::vector<CorridorForm> forms;
+  IntervalBatchBuf buf;
   std::vector<ngmlr_b200_align_result> tmp;
   int rcode = 0;
   for (int attempt = 0; !live.empty() && attempt < TEXT_SLOTS; ++attempt) {
@@ -239,46 +302,9 @@ int ngmlr_b200_compute_alignments(ngmlr_b200_ctx* ctx, int n, const ngmlr_b200_i
     }
     if (batch.empty()) break;
     const int m = (int)batch.size();
-    win_start.resize(m); ref_lens.resize(m); qry_lens.resize(m); ridx.resize(m); pstart.resize(m);
-    eqs.resize(m); eqe.resize(m); rc.resize(m); forms.resize(m); qtext.resize(m);
-    for (int j = 0; j < m; ++j) {
-      const ngmlr_b200_interval& iv = intervals[batch[j]];
-      const IvState& s = st[batch[j]];
-      win_start[j] = iv.on_ref_start;
-      ref_lens[j] = s.ref_seq_len - 1;
-      qry_lens[j] = iv.read_seq_len;
-      ridx[j] = iv.read_index;
-      pstart[j] = iv.on_read_start;
-      rc[j] = iv.reverse ? 1 : 0;
-      qtext[j] = iv.read_seq;
-      eqs[j] = iv.ext_qstart;
-      eqe[j] = iv.ext_qend;
-      forms[j] = corridor_for(iv, anchors, s, read_part_length);
-    }
-    RefWindows w;
-    w.d_enc = cs->d_enc.p;
-    w.d_ref_starts = cs->d_ref_starts.p;
-    w.n_starts = (int)cs->ref_starts.size();
-    w.win_start = win_start.data();
-    ReadParts rp;
-    rp.d_reads = ctx->d_reads.p;
-    rp.d_read_off = ctx->d_read_off.p;
-    rp.read_index = ridx.data();
-    rp.part_start = pstart.data();
-    rp.revcomp = rc.data();
-    UploadSpec sp;
-    sp.n = m;
-    sp.win = &w;
-    sp.ref_lens = ref_lens.data();
-    if (any_index) sp.parts = &rp;
-    else sp.qrys = qtext.data();
-    sp.qry_lens = qry_lens.data();
-    sp.forms = forms.data();
-    sp.ext_qstart = eqs.data();
-    sp.ext_qend = eqe.data();
     ctx->text_slot = attempt;
     tmp.resize(m);
-    if ((rcode = convex_upload_spec(ctx, sp)) != 0) break;
+    if ((rcode = upload_interval_batch(ctx, cs, intervals, anchors, batch, st, read_part_length, by_index, buf)) != 0) break;
     if ((rcode = ngmlr_b200_convex_run(ctx)) != 0) break;
     if ((rcode = ngmlr_b200_convex_fetch(ctx, tmp.data())) != 0) break;
     ctx->ca_h2d_bytes += ctx->stats.h2d_bytes;
@@ -304,6 +330,27 @@ int ngmlr_b200_compute_alignments(ngmlr_b200_ctx* ctx, int n, const ngmlr_b200_i
   ctx->text_mode = saved_mode;
   ctx->text_slot = saved_slot;
   return rcode ? rcode : n;
+}
+
+// The first attempt of ngmlr_b200_compute_alignments only, staged for the phased calls: afterwards
+// ngmlr_b200_convex_run / ngmlr_b200_convex_fetch operate on it (benchmarks time the kernels with the
+// batch resident in HBM). Every interval must reach SingleAlign (a window and a read part).
+// Switches the context to the device text stage.
+int ngmlr_b200_intervals_upload(ngmlr_b200_ctx* ctx, int n, const ngmlr_b200_interval* intervals,
+                                const ngmlr_b200_anchor* anchors, int read_part_length) {
+  if (!ctx) return -1;
+  if (n < 0) return ctx->fail("intervals_upload: n < 0");
+  CsState* cs = cs_state(ctx, false);
+  std::vector<IvState> st;
+  std::vector<int> live;
+  bool by_index = false;
+  if (prepare_intervals(ctx, cs, n, intervals, st, live, by_index)) return -1;
+  if ((int)live.size() != n) return ctx->fail("intervals_upload: %d of %d intervals have no reference window or read part",
+                                              n - (int)live.size(), n);
+  ctx->text_mode = 1;
+  ctx->text_slot = 0;
+  IntervalBatchBuf buf;
+  return upload_interval_batch(ctx, cs, intervals, anchors, live, st, read_part_length, by_index, buf);
 }
 
 int ngmlr_b200_compute_alignments_stats(ngmlr_b200_ctx* ctx, ngmlr_b200_batch_stats* out) {

@@ -246,7 +246,7 @@ def test_stage02_on_resident_reads_equals_subread_upload(fresh):
     reads = []
     for k in range(40):
         c = int(rng.integers(0, len(contigs)))
-        L = int(rng.choice([90, 255, 256, 257, 1000, 2600, 5000]))
+        L = min(int(rng.choice([90, 255, 256, 257, 1000, 2600, 5000])), contigs[c].size - 1)
         s0 = int(rng.integers(0, contigs[c].size - L))
         r, _ = synth.mutate(contigs[c][s0:s0 + L], rng, err=0.1)
         if k % 7 == 0:
