@@ -33,13 +33,55 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = "configs[1]: synthetic 50 Mb i.i.d. reference, PacBio-shaped reads (log-normal, median 8 kb, " \
-           "15% errors ins:del:sub 9:4:2, strand 50/50), one interval alignment per read, corridor from 256-bp anchors"
+CONFIGS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on (default)
+    "pacbio50": dict(genome_mb=50.0, contigs=5, median=8000, err=0.15, ratio=(9, 4, 2), sv=False, hi=40000,
+                     what="configs[1]: synthetic 50 Mb i.i.d. reference (5 contigs), PacBio-shaped reads (log-normal, "
+                          "median 8 kb, 15% errors ins:del:sub 9:4:2, strand 50/50), one interval per read, corridor "
+                          "from 256-bp anchors"),
+    # configs[3] shape (reads and error model; reference size as given by --genome-mb)
+    "ont": dict(genome_mb=50.0, contigs=5, median=20000, err=0.12, ratio=(1, 1, 1), sv=False, hi=100000,
+                what="configs[3] shape: ONT-shaped reads (log-normal, median 20 kb, 12% errors 1:1:1), "
+                     "--subread-corridor 40, one interval per read"),
+    # configs[4] shape
+    "sv": dict(genome_mb=50.0, contigs=5, median=8000, err=0.15, ratio=(9, 4, 2), sv=True, hi=40000,
+               what="configs[4] shape: every read carries one insertion / deletion / inversion of 1-50 kb; indels up "
+                    "to 3 kb inside one interval (anchor-widened corridors), longer ones as two intervals, inversions "
+                    "as three (+ a full-matrix alignment of inverted segments up to 2 kb); retries with wider corridors"),
+    # configs[2] shape: human-sized reference
+    "3gb": dict(genome_mb=3000.0, contigs=24, median=8000, err=0.15, ratio=(9, 4, 2), sv=False, hi=40000,
+                what="configs[2] shape: synthetic 3 Gb i.i.d. reference (24 contigs), PacBio-shaped reads"),
+}
 
 
-def make_pool(genome, n_reads, seed):
-    from ngmlr_b200 import synth
-    return synth.pacbio_problems(n_reads, seed=seed, median=8000, genome=genome)
+class Workload:
+    """Reads as sequenced + the computeAlignment calls ngmlr would issue for them (ngmlr_b200.synth)."""
+
+    def __init__(self, genome, contig_len, enc_ref, n_reads, seed, cfg):
+        from ngmlr_b200 import synth
+        self.genome, self.contig_len, self.enc = genome, contig_len, enc_ref
+        self.reads, self.ivs = synth.simulate_reads(n_reads, genome, contig_len, seed, median=cfg["median"],
+                                                    err=cfg["err"], ratio=cfg["ratio"], sv=cfg["sv"], hi=cfg["hi"])
+        self.bases = sum(len(r) for r in self.reads)
+
+    def g2c(self, pos):
+        c = pos // self.contig_len
+        return self.enc.ref_start[c] + (pos - c * self.contig_len)
+
+    def tasks(self, ivs, read_map=None):
+        from ngmlr_b200 import synth
+        t = synth.interval_tasks(ivs, self.reads, self.g2c)
+        if read_map is not None:
+            for x in t:
+                x.read_index = read_map[x.read_index]
+        return t
+
+    def slice(self, j, S):
+        """Context j of S: reads j, j+S, ... and their intervals, read indices renumbered."""
+        idx = list(range(j, len(self.reads), S))
+        rmap = {r: k for k, r in enumerate(idx)}
+        ivs = [iv for iv in self.ivs if iv.read in rmap]
+        return [self.reads[r] for r in idx], ivs, rmap
 
 
 class ClockSampler:
@@ -91,6 +133,7 @@ class CpuStage02:
     DecodeRefSequence, StrippedSW), or with the oracle port when that library is absent."""
 
     def __init__(self, genome, n_contigs=5):
+        n_contigs = int(n_contigs)
         import ctypes as C
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_lib
@@ -128,6 +171,25 @@ class CpuStage02:
         return None
 
     _CPL = bytes.maketrans(b"ACGT", b"TGCA")
+
+    def candidates(self, st, sub):
+        """One sub-read through the reference's CS vote, DecodeRefSequence and StrippedSW:
+        [(location, reverse, vote score, sw score)] in the reference's emission order."""
+        C = self.C
+        sc = (C.c_float * 512)()
+        lo = (C.c_ulonglong * 512)()
+        rv = (C.c_int * 512)()
+        mh = C.c_float()
+        n = self.lib.ref_cs_search_p(st[0], bytes(sub), len(sub), 16, sc, lo, rv, 512, C.byref(mh))
+        assert n <= 512
+        out = []
+        buf = C.create_string_buffer(312)
+        for j in range(max(0, n)):
+            if not self.lib.ref_cs_decode(C.c_ulonglong(lo[j] - 20), C.c_ulonglong(308), buf):
+                buf.value = b"N" * 308
+            q = bytes(sub).translate(self._CPL)[::-1] if rv[j] else bytes(sub)
+            out.append((int(lo[j]), int(rv[j]), float(sc[j]), float(self.lib.ref_full_ssw_score(st[1], buf.value, q))))
+        return out
 
     def read(self, st, qry):
         """All sub-reads of one read: vote, then score every candidate. Returns #candidates."""
@@ -201,14 +263,15 @@ def tune_malloc_for_threads():
         pass
 
 
-def cpu_reference_run(problems, threads, impl, stage02=None):
-    """Run problems through the CPU implementation on `threads` host threads (ctypes releases the
-    GIL). impl: 'reference' = oracle/_ref (unmodified ConvexAlignFast), 'port' = oracle C port.
-    stage02: CpuStage02 or None (stage 4 only)."""
+def cpu_reference_run(work_items, threads, impl, stage02=None, keep=None):
+    """work_items: [(read bytes as sequenced, [AlignProblem of each interval of the read])]; every read goes
+    through stage 0/2 (when stage02 is given) and every problem through SingleAlign, on `threads` host
+    threads (ctypes releases the GIL). impl: 'reference' = oracle/_ref (unmodified ConvexAlignFast),
+    'port' = oracle C port. keep: dict that receives {(read, k): result dict} (parity check)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
     tune_malloc_for_threads()
-    work = list(range(len(problems)))
+    work = list(range(len(work_items)))
     lock = threading.Lock()
     engines = [(oracle_lib.Reference() if impl == "reference" else oracle_lib.Oracle(),
                 stage02.worker_state() if stage02 else None) for _ in range(threads)]
@@ -220,11 +283,13 @@ def cpu_reference_run(problems, threads, impl, stage02=None):
                 if not work:
                     break
                 i = work.pop()
-            p = problems[i]
+            read, probs = work_items[i]
             if stage02:
-                stage02.read(st, p.qry)
-            r = eng.single_align(p.ref, p.qry, p.offsets, p.lengths)
-            assert r["ret"] == len(p.qry)
+                stage02.read(st, read)
+            for k, p in enumerate(probs):
+                r = eng.single_align(p.ref, p.qry, p.offsets, p.lengths, p.ext_qstart, p.ext_qend)
+                if keep is not None:
+                    keep[(i, k)] = r
 
     ts = [threading.Thread(target=worker, args=(t,)) for t in range(threads)]
     t0 = time.perf_counter()
@@ -252,35 +317,64 @@ def cpu_impl_kind():
     return "port"
 
 
+def cpu_work_items(wl, n_reads):
+    """The first n_reads reads of the workload with the first-attempt SingleAlign problems of their intervals."""
+    by_read = {}
+    for iv in wl.ivs:
+        if iv.read < n_reads:
+            by_read.setdefault(iv.read, []).append(iv)
+    return [(wl.reads[r], [iv.problem(wl.genome, wl.reads) for iv in by_read.get(r, [])]) for r in range(n_reads)]
+
+
+def build_reference(args, cfg, rank, world, dev):
+    """Genome + 4-bit encoding + k-mer index on rank 0, then ONE NCCL broadcast of the packed reference
+    (ngmlr_b200.parallel.broadcast_reference); no collective per step."""
+    from ngmlr_b200 import parallel, refindex, synth
+    n_genome = int(args.genome_mb * 1e6)
+    n_contigs = cfg["contigs"]
+    contig_len = n_genome // n_contigs
+    n_genome = contig_len * n_contigs
+    genome = enc_ref = kidx = None
+    t0 = time.perf_counter()
+    if rank == 0:
+        genome = synth.random_genome(n_genome, 1)
+        enc_ref = refindex.encode_reference([genome[i * contig_len:(i + 1) * contig_len] for i in range(n_contigs)])
+        kidx = refindex.build_index(enc_ref)
+    if world > 1:
+        genome, enc_ref, kidx = parallel.broadcast_reference(genome, enc_ref, kidx, src=0, device=dev)
+    return genome, contig_len, enc_ref, kidx, time.perf_counter() - t0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--reads", type=int, default=8192, help="reads (alignment problems) per step per GPU")
-    ap.add_argument("--genome-mb", type=float, default=50.0)
+    ap.add_argument("--config", default="pacbio50", choices=sorted(CONFIGS))
+    ap.add_argument("--reads", type=int, default=8192, help="reads per step per GPU")
+    ap.add_argument("--genome-mb", type=float, default=0.0, help="reference size (0 = the config's)")
     ap.add_argument("--dp-only", action="store_true", help="time stage 4 (convex alignment) alone")
     ap.add_argument("--contexts", type=int, default=4, help="aligner contexts (host threads/streams) per GPU")
     ap.add_argument("--fill-ctas", type=int, default=4,
                     help="fill CTAs per SM per launch in the concurrent phases (0 = full occupancy; the solo "
                          "roofline phase always runs at full occupancy)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--parity-reads", type=int, default=0, help="reads compared CPU vs GPU (0 = the CPU sample)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
+    cfg = CONFIGS[args.config]
+    if args.genome_mb <= 0:
+        args.genome_mb = cfg["genome_mb"]
+    workload_name = cfg["what"] + f"; reference {args.genome_mb:g} Mb"
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cores = effective_cpus()
-
-    # host worker threads of the library (packing / CIGAR text): share the logical CPUs among ranks x
-    # contexts. Deliberately not limited to the container's CPU quota: the host phases are short bursts
-    # and measured faster with 32 threads per context than with 8 (0.90 vs 0.84 Gbp/s end to end under a
-    # 16-CPU quota), whereas the CPU reference arm, which is busy all the time, is fastest at 2 x quota.
     os.environ.setdefault("NGMLR_B200_HOST_THREADS",
-                          str(max(4, min(32, (os.cpu_count() or 1) // max(1, world * max(1, args.contexts))))))
+                          str(max(2, min(16, (os.cpu_count() or 1) // max(1, world * max(1, args.contexts))))))
 
     from ngmlr_b200 import synth
 
@@ -288,26 +382,29 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
+        from ngmlr_b200 import refindex
         kind = cpu_impl_kind()
-        genome = synth.random_genome(int(args.genome_mb * 1e6), 1)
+        n_genome = int(args.genome_mb * 1e6)
+        contig_len = n_genome // cfg["contigs"]
+        genome = synth.random_genome(contig_len * cfg["contigs"], 1)
         threads = cores
-        # bounded sample: ~8 reads per thread per step (dynamic scheduling evens out the read lengths) keeps a
-        # K+W run within minutes
+        # bounded sample: ~8 reads per thread per step (dynamic scheduling evens out the read lengths)
         n = args.cpu_sample or max(threads, min(args.reads, 8 * threads))
-        pool = make_pool(genome, n, seed=2)
-        bases = sum(len(p.qry) for p in pool)
-        cells = sum(p.cells for p in pool)
-        st02 = None if args.dp_only else CpuStage02(genome)
+        wl = Workload(genome, contig_len, None, n, 2, cfg)
+        items = cpu_work_items(wl, n)
+        bases = wl.bases
+        cells = sum(p.cells for _r, ps in items for p in ps)
+        st02 = None if args.dp_only else CpuStage02(genome, cfg["contigs"])
         for _ in range(max(1, min(args.warmup, 1))):   # grows the per-thread malloc arenas, warms the caches
-            cpu_reference_run(pool, threads, kind, st02)
-        times = [cpu_reference_run(pool, threads, kind, st02) for _ in range(args.steps)]
+            cpu_reference_run(items, threads, kind, st02)
+        times = [cpu_reference_run(items, threads, kind, st02) for _ in range(args.steps)]
         t = float(np.sum(times))
         val = bases * args.steps / t / 1e9
         line = {"metric": "aligned_gbp_per_s", "value": val, "unit": "Gbp/s", "impl": "reference",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": val / 5.56e-4, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "reads_per_step": n, "read_bases_per_step": bases,
+                "config": {"workload": workload_name, "reads_per_step": n, "read_bases_per_step": bases,
                            "dp_cells_per_step": cells},
                 "cpu_baseline": {"value": val, "unit": "Gbp/s", "cores": threads, "kind": kind,
                                  "sample": f"{n} reads ({bases} bases, {cells} DP cells) per step, {threads} threads "
@@ -330,52 +427,18 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    # reference: genome + 4-bit encoding + k-mer index built on rank 0, then ONE NCCL broadcast of
-    # the packed reference at start-up; no collective per step
-    from ngmlr_b200 import refindex
-    n_genome = int(args.genome_mb * 1e6)
-    n_contigs = 5
-    t_ref0 = time.perf_counter()
-    if rank == 0:
-        genome = synth.random_genome(n_genome, 1)
-        step_c = n_genome // n_contigs
-        enc_ref = refindex.encode_reference([genome[i * step_c:(i + 1) * step_c] for i in range(n_contigs)])
-        kidx = refindex.build_index(enc_ref)
-        meta = [enc_ref.enc.size, enc_ref.concat_len, kidx.tab.size, kidx.pos.size] + enc_ref.ref_start + enc_ref.ref_len
-    if world > 1:
-        mt = torch.zeros(4 + 2 * n_contigs, dtype=torch.int64, device=dev)
-        if rank == 0:
-            mt.copy_(torch.tensor(meta, dtype=torch.int64))
-        dist.broadcast(mt, src=0)
-        m = [int(x) for x in mt.cpu()]
-        bufs = {"genome": (n_genome, torch.uint8), "enc": (m[0], torch.uint8), "tab": (m[2], torch.int32),
-                "rci": (m[2], torch.int8), "pos": (m[3], torch.int32)}
-        got = {}
-        for name, (sz, dt) in bufs.items():
-            t = torch.empty(sz, dtype=dt, device=dev)
-            if rank == 0:
-                src = {"genome": genome, "enc": enc_ref.enc, "tab": kidx.tab.view(np.int32),
-                       "rci": kidx.rci, "pos": kidx.pos.view(np.int32)}[name]
-                t.copy_(torch.from_numpy(np.ascontiguousarray(src)))
-            dist.broadcast(t, src=0)
-            got[name] = t.cpu().numpy()
-            del t
-        if rank != 0:
-            genome = got["genome"]
-            enc_ref = refindex.EncodedReference(got["enc"], m[1], m[4:4 + n_contigs], m[4 + n_contigs:4 + 2 * n_contigs])
-            kidx = refindex.KmerIndex(13, 4, got["tab"].view(np.uint32), got["rci"], got["pos"].view(np.uint32))
-    t_ref = time.perf_counter() - t_ref0
+    genome, contig_len, enc_ref, kidx, t_ref = build_reference(args, cfg, rank, world, dev)
 
-    from ngmlr_b200 import B200Aligner, PackedBatch, PackedReads, split_read
-    pool = make_pool(genome, args.reads, seed=2 + rank)   # reads sharded by rank: own reads per rank
-    batch = PackedBatch.from_problems(pool)
-    bases = batch.read_bases
-    subreads = PackedReads([s for p in pool for s in split_read(p.qry)])   # ReadProvider::splitRead
+    from ngmlr_b200 import B200Aligner, IntervalBatch, PackedReads
+    wl = Workload(genome, contig_len, enc_ref, args.reads, 2 + rank, cfg)   # reads sharded by rank: own reads per rank
+    bases = wl.bases
+    all_reads = PackedReads(wl.reads)
+    all_ivs = IntervalBatch(wl.tasks(wl.ivs))
     # S independent aligner contexts (own stream, own device arenas), driven by S host threads --
     # the reference's model of one aligner object per worker thread. The step's batch is dealt to the
-    # contexts read by read (context j aligns reads j, j+S, ...); their work overlaps on the GPU, which
+    # contexts read by read (context j takes reads j, j+S, ...); their work overlaps on the GPU, which
     # hides the tail of each fill launch and the traceback behind another context's fill, and (end to
-    # end) packing/H2D/D2H/text of one slice behind the kernels of the others.
+    # end) the host side of one slice behind the kernels of the others.
     S = max(1, args.contexts)
     streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
     als = [B200Aligner(local_rank, stream=st_.cuda_stream) for st_ in streams]
@@ -383,9 +446,12 @@ def main():
     for a_ in als:
         a_.set_index(kidx)
         a_.set_reference(enc_ref)
-    slices = [pool[j::S] for j in range(S)]
-    sl_batch = [PackedBatch.from_problems(sl) for sl in slices]
-    sl_reads = [PackedReads([s for p in sl for s in split_read(p.qry)]) for sl in slices]
+    sl_reads, sl_ivs, sl_bases = [], [], []
+    for j in range(S):
+        r_, iv_, rmap = wl.slice(j, S)
+        sl_reads.append(PackedReads(r_))
+        sl_ivs.append(IntervalBatch(wl.tasks(iv_, rmap)))
+        sl_bases.append(sum(len(x) for x in r_))
 
     def barrier():
         if world > 1:
@@ -401,14 +467,14 @@ def main():
 
     # ---- (a) one context alone on the whole batch: per-kernel durations for the roofline (the fill
     # kernel timed in isolation, inputs resident) ----
-    al.upload(batch)
-    al.cs_upload(subreads)
+    n_sub = al.reads_upload(all_reads)
+    al.intervals_upload(all_ivs)
     for _ in range(args.warmup):
         if not args.dp_only:
             al.cs_run()
         al.run()
     barrier()
-    fill_ms, tb_ms, cs_ms = [], [], []
+    fill_ms, tb_ms, tx_ms, cs_ms = [], [], [], []
     n_cand = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(streams[0])
@@ -419,24 +485,26 @@ def main():
         st = al.stats()
         fill_ms.append(st["fill_ms"])
         tb_ms.append(st["traceback_ms"])
+        tx_ms.append(st["text_ms"])
     e1.record(streams[0])
     torch.cuda.synchronize(dev)
     solo_ms = e0.elapsed_time(e1)
-    res = al.fetch()
+    gpu_first = al.fetch()                 # first-attempt alignments of every interval (parity check below)
     st = al.stats()
-    assert all(res.ret(i) == len(p.qry) for i, p in enumerate(pool)), "bench: invalid alignment in the timed batch"
     cells = st["cells"]
-    del res
+    gpu_first = [gpu_first[i] for i in range(len(gpu_first))]
+    gpu_cs = None if args.dp_only else al.cs_fetch()
+    n_first_valid = sum(1 for r, iv in zip(gpu_first, wl.ivs) if r.ret == len(wl.reads[iv.read]))
 
     # ---- (b) device-resident timed region: every context keeps its slice in HBM, exactly K steps ----
     # Smaller persistent fill grids per launch so that the launches of the S contexts (and their
-    # memory-bound candidate-search / traceback kernels) share the SMs instead of queueing.
+    # memory-bound candidate-search / traceback / text kernels) share the SMs instead of queueing.
     for a_ in als:
         a_.set_fill_ctas_per_sm(args.fill_ctas if S > 1 else 0)
 
     def resident_warm(j):
-        als[j].upload(sl_batch[j])
-        als[j].cs_upload(sl_reads[j])
+        als[j].reads_upload(sl_reads[j])
+        als[j].intervals_upload(sl_ivs[j])
         for _ in range(args.warmup):
             if not args.dp_only:
                 als[j].cs_run()
@@ -467,33 +535,33 @@ def main():
     barrier()
     clocks = sampler.stop()
     dev_ms = e0.elapsed_time(e1)
-    for j in range(S):
-        r_ = als[j].fetch()
-        assert all(r_.ret(i) == len(p.qry) for i, p in enumerate(slices[j])), "bench: invalid alignment in a slice"
-        del r_
 
-    # ---- (c) end to end from host buffers through the public calls: per step every context takes its
-    # slice from host memory (pack + H2D), runs all kernels, and brings candidates, scores and
-    # alignments (binary CIGAR -> CIGAR/MD text) back to the host. Uploads are issued before the
-    # kernels and fetches after them so that a context's host work overlaps other contexts' kernels. ----
-    io = [dict() for _ in range(S)]
+    # ---- (c) end to end from host buffers through the public calls: per step every context uploads its
+    # reads ONCE (reads_upload), runs stage 0/2 on their sub-reads and brings candidates + scores back
+    # (cs_run, cs_fetch), then computeAlignment for its intervals (compute_alignments: windows by position,
+    # corridors in closed form, read parts by index; retries inside the call) -> CIGAR / MD / NM / regions on
+    # the host. ----
+    io = [dict(h2d=0, d2h=0, attempts=0, invalid=0) for _ in range(S)]
 
     def e2e_steps(j, k):
         a_ = als[j]
         for _ in range(k):
-            if not args.dp_only:
-                a_.cs_upload(sl_reads[j])            # host buffers -> device
-            a_.upload(sl_batch[j])
+            a_.reads_upload(sl_reads[j])
+            h2d = a_.reads_h2d_bytes()
+            d2h = 0
             if not args.dp_only:
                 m_, _ms = a_.cs_run()
-            a_.run()
-            if not args.dp_only:
                 cstart, _sc, _lo, _rv, sw_, _mx = a_.cs_fetch()   # candidates + scores -> host
                 assert m_ == cstart[-1] and sw_.size == m_
-                io[j]["h2d"] = sl_reads[j].bases + 12 * sl_reads[j].n
-                io[j]["d2h"] = 17 * int(m_) + 12 * sl_reads[j].n
-            out = a_.fetch()
-            assert len(out) == sl_batch[j].n and out.ret(0) == len(slices[j][0].qry)
+                d2h += 17 * int(m_) + 12 * (len(cstart) - 1)
+            out, att = a_.compute_alignments(sl_ivs[j])
+            cst = a_.compute_alignments_stats()
+            h2d += cst["h2d_bytes"]
+            d2h += cst["d2h_bytes"]
+            bad = sum(1 for i in range(len(out)) if out.ret(i) < 0)
+            io[j].update(h2d=h2d, d2h=d2h, attempts=int(att.sum()), invalid=bad, n=len(out),
+                         host_ms={k_: cst[k_] for k_ in ("host_pack_ms", "host_h2d_ms", "host_run_ms", "host_d2h_ms",
+                                                         "host_text_ms")})
             del out
 
     run_threads(lambda j: e2e_steps(j, 1))
@@ -502,9 +570,10 @@ def main():
     run_threads(lambda j: e2e_steps(j, args.steps))
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
-    st_e2e = [a_.stats() for a_ in als]
-    e2e_h2d = sum(x["h2d_bytes"] for x in st_e2e) + sum(x.get("h2d", 0) for x in io)
-    e2e_d2h = sum(x["d2h_bytes"] for x in st_e2e) + sum(x.get("d2h", 0) for x in io)
+    e2e_h2d = sum(x["h2d"] for x in io)
+    e2e_d2h = sum(x["d2h"] for x in io)
+    n_invalid = sum(x["invalid"] for x in io)
+    assert n_invalid <= max(2, len(wl.ivs) // 200), f"bench: {n_invalid} of {len(wl.ivs)} intervals without an alignment"
 
     t_dev = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     tot = torch.tensor([float(bases), float(cells)], dtype=torch.float64, device=dev)
@@ -524,34 +593,37 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, burst)" if peaks else "fallback 6650 GB/s"
-        # algorithmic bytes of ONE fill launch: 0.25 B per DP cell (2-bit
-        # direction) + sequences read once + corridor rows (8 B/row) read once
-        rows = int(batch.row_start[-1])
-        seq_b = int(batch.ref_lens.sum() + batch.qry_lens.sum())
-        algo_bytes = cells * 0.25 + seq_b + rows * 8
+        # algorithmic bytes of ONE fill launch: 0.25 B per DP cell (2-bit direction) +
+        # sequences read once; corridor rows are generated on the device from 28-byte closed forms
+        seq_b = sum(iv.ref_len + iv.read_len for iv in wl.ivs)
+        algo_bytes = cells * 0.25 + seq_b + 112 * len(wl.ivs)
         fill_s = float(np.mean(fill_ms)) * 1e-3
         achieved = algo_bytes / fill_s / 1e9
-        issue_bound_cells = 148 * 4 * 32 * float(clocks.get("sm_mhz") or 1965.0) * 1e6 / (27.0 * 2.0)
+        sm_mhz = float(clocks.get("sm_mhz") or 1965.0)
+        # 148 SMs x 128 lanes x clock / >= 25 instructions per cell
+        issue_bound = 148 * 128 * sm_mhz * 1e6 / 25.0
         traffic = None
-        try:  # DRAM bytes of one fill launch from the committed ncu capture (same reads/step only)
+        try:  # DRAM bytes of one fill launch from the committed ncu capture (same workload only)
             tr = json.load(open(os.path.join(ROOT, "profiles", "fill_traffic.json")))
-            if tr.get("reads_per_step") == args.reads:
+            if tr.get("reads_per_step") == args.reads and tr.get("config", "pacbio50") == args.config:
                 traffic = tr["dram_bytes_per_launch"]
         except Exception:
             pass
         line = {
             "metric": "aligned_gbp_per_s", "value": value, "unit": "Gbp/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": value / 5.56e-4,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": e2e_val / 5.56e-4,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "reads_per_step_per_gpu": args.reads,
+            "config": {"workload": workload_name, "config": args.config, "reads_per_step_per_gpu": args.reads,
+                       "intervals_per_step_per_gpu": len(wl.ivs),
                        "read_bases_per_step": tot_bases, "dp_cells_per_step": tot_cells,
                        "parallelism": f"read-sharded x{world}, no per-step collective; {S} aligner contexts/GPU, "
                                       f"fill grid {args.fill_ctas or 'full'} CTAs/SM per launch",
                        "l2": "inputs+direction arena per step exceed L2 (direction writes alone "
                              f"{st['dir_bytes'] / 1e6:.0f} MB/step/GPU)",
-                       "vs_baseline_note": "README.md:25 end-to-end 5.56e-4 Gbp/s on 10 Opteron cores (whole "
-                                           "pipeline); this path is the 91 % stage"},
+                       "vs_baseline_note": "e2e (host buffers in, CIGAR/MD text out) / README.md:25 whole-pipeline "
+                                           "5.56e-4 Gbp/s on 10 Opteron cores; the same-box CPU arm is cpu_baseline / "
+                                           "--impl reference"},
             "reads_per_s": args.reads * world * args.steps / (dev_ms * 1e-3),
             "gcells_per_s": tot_cells * args.steps / (dev_ms * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -559,46 +631,54 @@ def main():
                          "kernel": "convex_fill_kernel", "launch_ms": fill_s * 1e3,
                          "algorithmic_bytes_per_launch": algo_bytes,
                          "gcells_per_s_kernel": cells / fill_s / 1e9,
-                         "alu_pipe_bound_gcells_per_s": issue_bound_cells / 1e9,
-                         "frac_of_alu_pipe_bound": cells / fill_s / issue_bound_cells,
-                         "note": "ALU-pipe-bound kernel (~27 ALU-pipe SASS instr per 32-cell step, 2 cycles each "
-                                 "per SMSP, DESIGN.md 4.1); HBM frac is structurally ~0.02"},
+                         "issue_bound_gcells_per_s": issue_bound / 1e9,
+                         "frac_of_issue_bound": cells / fill_s / issue_bound,
+                         "note": "integer/float DP: instruction-issue bound (SURVEY 8(d): 148 SMs x 128 lanes x clock / "
+                                 "25 instructions per cell), not HBM bound; the HBM fraction is structurally ~0.02"},
             "kernel_ms_per_step": {"fill": float(np.mean(fill_ms)), "traceback": float(np.mean(tb_ms)),
+                                   "text": float(np.mean(tx_ms)),
                                    "stage02_cs_vote_decode_score": float(np.mean(cs_ms))},
-            "stage02": {"subreads_per_step_per_gpu": subreads.n, "candidates_per_step_per_gpu": int(n_cand),
+            "stage02": {"subreads_per_step_per_gpu": n_sub, "candidates_per_step_per_gpu": int(n_cand),
                         "sw_cell_updates_per_step_per_gpu": int(n_cand) * 257 * 307,
-                        "reference_setup_s": t_ref,
-                        "note": "k-mer vote of every 256-bp sub-read + device decode + StrippedSW score of every candidate"},
+                        "reference_setup_s": t_ref},
             "e2e": {"value": e2e_val, "unit": "Gbp/s", "h2d_bytes_per_step": e2e_h2d,
                     "d2h_bytes_per_step": e2e_d2h, "ms_per_step": e2e_ms / args.steps,
-                    "host_ms_per_slice": {k: float(np.mean([x[k] for x in st_e2e]))
-                                          for k in ("host_pack_ms", "host_h2d_ms", "host_run_ms",
-                                                    "host_d2h_ms", "host_text_ms")},
-                    "host_threads_per_context": st_e2e[0]["host_threads"],
-                    "note": f"each of the {S} contexts takes every {S}-th read of the batch per step"},
+                    "host_ms_per_slice_first_attempt": {k: float(np.mean([x["host_ms"][k] for x in io]))
+                                                        for k in io[0].get("host_ms", {})},
+                    "singlealign_calls_per_step": sum(x["attempts"] for x in io),
+                    "intervals_without_alignment": n_invalid,
+                    "note": f"reads_upload -> cs_run -> cs_fetch -> compute_alignments per context and step; each of the "
+                            f"{S} contexts takes every {S}-th read"},
             "solo": {"gbp_per_s": bases * args.steps / (solo_ms * 1e-3) / 1e9, "ms_per_step": solo_ms / args.steps,
+                     "first_attempt_valid": n_first_valid, "intervals": len(wl.ivs),
                      "note": "one context alone on the whole batch, same K steps (kernels not overlapped)"},
             # per context and step: cs count, sizes, 4 x (scan init + scan), vote, count widening, compaction,
-            # window decode + score, fill, traceback = 16 kernels (2 with --dp-only); profiles/launches_r01_fullpath.csv
-            "gpu_launches": (2 if args.dp_only else 16) * S * args.steps,
+            # window decode + score (14) + fill, traceback, text (3)
+            "gpu_launches": (3 if args.dp_only else 17) * S * args.steps,
             "clocks": clocks,
         }
-        # CPU baseline on this box's host cores, bounded sample of the same workload
+        # CPU baseline on this box's host cores, bounded sample of the same workload -- and the parity check:
+        # the CPU arm's alignments, candidates and scores against what the GPU produced for the same reads
         try:
             kind = cpu_impl_kind()
             threads = cores
-            n = args.cpu_sample or max(threads, min(len(pool), 8 * threads))
-            sample = pool[:n]
-            st02 = None if args.dp_only else CpuStage02(genome)
-            cpu_reference_run(sample, threads, kind, st02)   # warm-up: per-thread malloc arenas, caches
-            t = cpu_reference_run(sample, threads, kind, st02)
-            sb = sum(len(p.qry) for p in sample)
-            sc = sum(p.cells for p in sample)
+            n = args.cpu_sample or max(threads, min(len(wl.reads), 8 * threads))
+            items = cpu_work_items(wl, n)
+            st02 = None if args.dp_only else CpuStage02(genome, cfg["contigs"])
+            cpu_reference_run(items, threads, kind, st02)   # warm-up: per-thread malloc arenas, caches
+            keep = {}
+            t = cpu_reference_run(items, threads, kind, st02, keep=keep)
+            sb = sum(len(r) for r, _ in items)
+            sc = sum(p.cells for _r, ps in items for p in ps)
             line["cpu_baseline"] = {"value": sb / t / 1e9, "unit": "Gbp/s", "cores": threads, "kind": kind,
                                     "sample": f"first {n} reads of the batch ({sb} bases, {sc} DP cells), "
                                               f"{threads} threads, {t:.1f} s, stages: "
                                               + ("4 only" if st02 is None else f"0/2 ({st02.kind}) + 4"),
                                     "mcells_per_s_per_core": sc / t / threads / 1e6}
+            line["parity_checked"] = parity_check(wl, keep, gpu_first, gpu_cs, st02,
+                                                  args.parity_reads or min(n, 64))
+        except AssertionError:
+            raise
         except Exception as ex:  # the baseline is reported, never required for the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "Gbp/s", "cores": 0, "kind": "unavailable",
                                     "sample": repr(ex)}
@@ -608,6 +688,47 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def parity_check(wl, cpu_aligned, gpu_first, gpu_cs, st02, n_stage02_reads):
+    """The CPU arm's outputs (the reference's own code where oracle/_ref exists) against the GPU's for the
+    same reads, outside every timed region. Stage 4: every interval of the CPU sample -- score bits, CIGAR,
+    MD, NM, positions. Stage 0/2: the candidate lists (order, location, strand, vote score) and StrippedSW
+    scores of every sub-read of the first reads. A mismatch fails the run."""
+    by_read = {}
+    for gi, iv in enumerate(wl.ivs):
+        by_read.setdefault(iv.read, []).append(gi)
+    n_al = 0
+    for (r, k), want in cpu_aligned.items():
+        g = gpu_first[by_read[r][k]].as_dict()
+        if want["ret"] < 0 or g["ret"] < 0:   # no alignment: the reference leaves the other fields undefined
+            assert want["ret"] < 0 and g["ret"] < 0, f"parity: read {r} interval {k}: ret cpu {want['ret']} gpu {g['ret']}"
+            n_al += 1
+            continue
+        for key in ("ret", "score_bits", "cigar", "md", "nm", "position_offset", "qstart", "qend", "alignment_length"):
+            assert want[key] == g[key], f"parity: read {r} interval {k}: {key} differs (cpu {want[key]!r:.80} gpu {g[key]!r:.80})"
+        n_al += 1
+    out = {"alignments": n_al, "fields": "ret, score bits, CIGAR, MD, NM, PositionOffset, QStart, QEnd, alignmentLength"}
+    if gpu_cs is not None and st02 is not None and st02.kind == "reference":
+        cstart, cs_sc, cs_lo, cs_rv, cs_sw, _mx = gpu_cs
+        s = 0   # global sub-read index
+        n_sub = n_c = 0
+        wstate = st02.worker_state()
+        for r in range(len(wl.reads)):
+            read = wl.reads[r]
+            parts = max(1, len(read) // 256)
+            if r < n_stage02_reads and len(read) >= 256:
+                for k in range(parts):
+                    want = st02.candidates(wstate, read[k * 256:(k + 1) * 256])
+                    a, b = int(cstart[s + k]), int(cstart[s + k + 1])
+                    got = [(int(cs_lo[j]), int(cs_rv[j]), float(cs_sc[j]), float(cs_sw[j])) for j in range(a, b)]
+                    assert want == got, f"parity: read {r} sub-read {k}: candidates differ (cpu {want[:3]} gpu {got[:3]})"
+                    n_sub += 1
+                    n_c += len(want)
+            s += parts
+        out.update(subreads=n_sub, candidates=n_c,
+                   stage02_fields="candidate order, location, strand, vote score, StrippedSW score")
+    return out
 
 
 if __name__ == "__main__":

@@ -148,7 +148,10 @@ class SimInterval:
         else:
             c = self.corridor or _corr.estimate_corridor(self.read_len, self.ref_len)
             offs, lens = _corr.corridor_endpoints(self.read_len, self.ref_len, min(c, 2 * (self.ref_len + 1)))
-        return AlignProblem(window.tobytes(), part.tobytes(), offs, lens)
+        # externalQStart / externalQEnd of alignInterval (src/AlignmentBuffer.cpp:1488-1499)
+        full = len(reads[self.read])
+        lo_aligned = (full - self.on_read_start - self.read_len) if self.reverse else self.on_read_start
+        return AlignProblem(window.tobytes(), part.tobytes(), offs, lens, lo_aligned, full - lo_aligned - self.read_len)
 
 
 def revcomp_upper(seq):

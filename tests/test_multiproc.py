@@ -1,6 +1,8 @@
 """world_size-2 CPU (gloo) test of the multi-rank host logic bench.py uses: the reference is
-broadcast once from rank 0, reads are sharded by rank (rank-seeded pools, no overlap, no per-step
-collective), timings are max-reduced and totals sum-reduced."""
+broadcast once from rank 0 as one packed buffer (ngmlr_b200.parallel.broadcast_reference: flat genome,
+4-bit encoding, k-mer index arrays -- every rank ends up with identical arrays), reads are sharded by
+rank (rank-seeded pools, no overlap, no per-step collective), timings are max-reduced and totals
+sum-reduced."""
 import os
 import subprocess
 import sys
@@ -12,24 +14,32 @@ WORKER = textwrap.dedent('''
     import os, sys, json, hashlib
     sys.path.insert(0, os.environ["REPO_ROOT"])
     import numpy as np, torch, torch.distributed as dist
-    from ngmlr_b200 import synth, PackedBatch
+    from ngmlr_b200 import parallel, refindex, synth
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
-    n = 200_000
-    g = torch.zeros(n, dtype=torch.uint8)
+    n, n_contigs = 200_000, 2
+    genome = enc = idx = None
     if rank == 0:
-        g.copy_(torch.from_numpy(synth.random_genome(n, 1)))
-    dist.broadcast(g, src=0)                      # the one start-up collective
-    genome = g.numpy()
-    pool = synth.pacbio_problems(6, seed=2 + rank, median=1500, genome=genome)   # read sharding
-    batch = PackedBatch.from_problems(pool)
-    sig = hashlib.sha256(b"".join(p.qry for p in pool)).hexdigest()
+        genome = synth.random_genome(n, 1)
+        enc = refindex.encode_reference([genome[:n // 2], genome[n // 2:]])
+        idx = refindex.build_index(enc)
+    # the one start-up collective (+ its 64-byte header): the packed reference
+    genome, enc, idx = parallel.broadcast_reference(genome, enc, idx, src=0)
+    reads, ivs = synth.simulate_reads(6, genome, n // 2, 2 + rank, median=1500)   # read sharding: own reads per rank
+    tasks = synth.interval_tasks(ivs, reads, lambda pos: enc.ref_start[pos // (n // 2)] + pos % (n // 2))
+    assert all(t.read_index == k for k, t in enumerate(tasks))
+    bases = sum(len(r) for r in reads)
+    sig = hashlib.sha256(b"".join(reads)).hexdigest()
     t = torch.tensor([10.0 + rank, 5.0 - rank], dtype=torch.float64)   # fake per-rank timings
-    tot = torch.tensor([float(batch.read_bases)], dtype=torch.float64)
+    tot = torch.tensor([float(bases)], dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ref_sig = hashlib.sha256(genome.tobytes() + enc.enc.tobytes() + idx.tab.tobytes() + idx.rci.tobytes()
+                             + idx.pos.tobytes() + repr((enc.concat_len, enc.ref_start, enc.ref_len, idx.k,
+                                                         idx.bin_shift)).encode()).hexdigest()
     sigs = [None] * world
-    dist.all_gather_object(sigs, (sig, batch.read_bases, hashlib.sha256(genome.tobytes()).hexdigest()))
+    dist.all_gather_object(sigs, (sig, bases, ref_sig))
+    assert list(parallel.shard(10, rank, world)) == list(range(rank, 10, world))
     if rank == 0:
         print(json.dumps({"tmax": t.tolist(), "tot": tot.item(), "sigs": sigs}))
     dist.destroy_process_group()
