@@ -107,8 +107,9 @@ convex_fill_kernel(const FillParams p) {
   constexpr int CHUNK = NW == 1 ? 64 : FILL_TEAM_CHUNK;  // steps staged through shared memory at a time
   constexpr int GPC = CHUNK / 16;           // 16-step groups per chunk
   static_assert(NW == 1 || NW == FILL_WARPS_PER_CTA, "a team is one warp or the whole CTA");
-  __shared__ uint4 s_in[FILL_WARPS_PER_CTA][CHUNK + 1];  // +1: lane 31 reads one record ahead
-  __shared__ uint4 s_out[FILL_WARPS_PER_CTA][CHUNK];
+  // staging records of a chunk, interleaved: s_io[w][2 * j] = what lane 0 consumes at step j of the chunk,
+  // s_io[w][2 * j + 1] = what lane 31 produced at step j (one base register + immediates serve both)
+  __shared__ uint4 s_io[FILL_WARPS_PER_CTA][2 * (CHUNK + 1)];  // +1: lane 31 reads one record ahead
   __shared__ volatile unsigned long long s_prog[FILL_WARPS_PER_CTA];
   __shared__ int s_work;
   __shared__ TeamBest s_best[FILL_WARPS_PER_CTA];
@@ -116,8 +117,7 @@ convex_fill_kernel(const FillParams p) {
   const int wib = threadIdx.x >> 5;
   const int tw = NW == 1 ? 0 : wib;  // warp index within the team
   const int team_global = NW == 1 ? blockIdx.x * FILL_WARPS_PER_CTA + wib : blockIdx.x;
-  uint4* const in_s = s_in[wib];
-  uint4* const out_s = s_out[wib];
+  uint4* const io_s = s_io[wib];
   // strip[x + STRIP_PAD] = {S, U, run, ref byte} of column x of the most recently finished bottom row
   uint4* const strip = reinterpret_cast<uint4*>(p.bnd) + (size_t)team_global * p.bnd_stride + STRIP_PAD;
   const Scoring sc = p.sc;
@@ -275,11 +275,11 @@ convex_fill_kernel(const FillParams p) {
       for (int c = 0; c < nchunks; ++c) {
         pa.w = ra;  // the reference byte of the column rides in the record
         pb.w = rb;
-        if (lane < CHUNK) in_s[lane] = pa;
-        if (CHUNK > 32) in_s[lane + 32] = pb;
+        if (lane < CHUNK) io_s[2 * lane] = pa;
+        if (CHUNK > 32) io_s[2 * (lane + 32)] = pb;
         __syncwarp();
         if (is31) {  // lane 31's shuffle sources carry the strip record lane 0 needs next
-          const uint4 t = in_s[0];
+          const uint4 t = io_s[0];
           oS = __uint_as_float(t.x);
           oU = __uint_as_float(t.y);
           oP = t.z;
@@ -302,8 +302,7 @@ convex_fill_kernel(const FillParams p) {
         // (the common case away from the block's leading and trailing wavefront).
         auto do_group = [&](auto all_active_tag, int g) {
           constexpr bool ALL_ACTIVE = decltype(all_active_tag)::value;
-          const uint4* in_g = in_s + ((g % GPC) << 4);
-          uint4* out_g = out_s + ((g % GPC) << 4);
+          uint4* io_g = io_s + ((g % GPC) << 5);
           uint32_t dw = 0;
           {
 #pragma unroll 2  // 2 keeps the per-step predicates in registers; 4 makes ptxas spill them to a bit mask
@@ -391,8 +390,9 @@ convex_fill_kernel(const FillParams p) {
               }
               dw = __funnelshift_r(dw, code, 2);
               if (is31) {
-                out_g[k] = make_uint4(__float_as_uint(S), __float_as_uint(U), oP, 0u);
-                const uint4 t = in_g[k + 1];
+                // the record is exactly the four shuffle sources (w is rewritten when the chunk is staged)
+                io_g[2 * k + 1] = make_uint4(__float_as_uint(oS), __float_as_uint(oU), oP, oC);
+                const uint4 t = io_g[2 * k + 2];
                 oS = __uint_as_float(t.x);
                 oU = __uint_as_float(t.y);
                 oP = t.z;
@@ -414,8 +414,8 @@ convex_fill_kernel(const FillParams p) {
         {
           const int done = (g_end - c * GPC) << 4;  // steps executed in this chunk
           const int xo = base - 31 + c * CHUNK;
-          if (lane < done) st_strip(strip + xo + lane, out_s[lane]);
-          if (CHUNK > 32 && lane + 32 < done) st_strip(strip + xo + lane + 32, out_s[lane + 32]);
+          if (lane < done) st_strip(strip + xo + lane, io_s[2 * lane + 1]);
+          if (CHUNK > 32 && lane + 32 < done) st_strip(strip + xo + lane + 32, io_s[2 * (lane + 32) + 1]);
           if (NW > 1) {
             team_fence();
             __syncwarp();
