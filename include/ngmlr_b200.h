@@ -175,6 +175,22 @@ int ngmlr_b200_cs_set_index(ngmlr_b200_ctx* ctx, const void* packed_index, uint3
                             const uint32_t* positions, uint32_t n_positions, uint64_t unit_offset,
                             int k, int bin_shift);
 
+/* The same index BUILT ON THE DEVICE from the encoded reference that ngmlr_b200_cs_set_reference made
+ * resident: replaces CompactPrefixTable::CreateTable for one table unit (src/PrefixTable.cpp:323-370:
+ * CountKmerFreq + createRefTableIndex + Generate/BuildPrefixTable, driven by CS::PrefixIteration with
+ * prefixskip = kmer_skip) and installs the result as the context's index. contig_start / contig_len =
+ * SequenceProvider.GetRefStart / GetRefLen of the forward-strand entries (sorted); k = --kmer-length (13),
+ * kmer_skip = --kmer-skip (2), bin_shift = --bin-size (4), max_prefix_freq = 1000
+ * (src/PrefixTable.cpp:28). Bit-identical to the reference's arrays (tests/test_gpu_index.py). */
+int ngmlr_b200_cs_build_index(ngmlr_b200_ctx* ctx, const uint64_t* contig_start, const uint64_t* contig_len,
+                              int n_contigs, int k, int kmer_skip, int bin_shift, int max_prefix_freq,
+                              uint32_t* n_positions);
+/* The context's index back in the reference's in-memory format (for the byte-compatible
+ * -ht-<k>-<skip>.2.ngm writer): sizes, and -- where the pointers are not NULL -- index_len x 5 packed
+ * Index bytes and n_positions Location words. */
+int ngmlr_b200_cs_get_index(ngmlr_b200_ctx* ctx, uint32_t* index_len, uint32_t* n_positions, void* packed_index,
+                            uint32_t* positions);
+
 /* Candidate search for n (sub-)reads: replaces CS::PrefixIteration + PrefixSearch + AddLocationStd +
  * CollectResultsStd (src/CSstatic.cpp:23-73, src/CS.cpp:57-149, 217-269) as driven by
  * CS::RunRead (src/CS.cpp:324-398). sensitivity = Config.getSensitivity() (0.8),

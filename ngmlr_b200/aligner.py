@@ -252,6 +252,35 @@ class B200Aligner:
             self.h, packed.ctypes.data_as(C.c_void_p), index.tab.size, pos.ctypes.data_as(C.c_void_p),
             pos.size, 0, index.k, index.bin_shift))
 
+    def build_index(self, ref, k=13, kmer_skip=2, bin_shift=4, max_prefix_freq=1000, fetch=False):
+        """CompactPrefixTable::CreateTable on the device, from the encoded reference set with set_reference
+        (`ref`: its EncodedReference, for the contig table). Installs the index in this context; with
+        fetch=True also returns it as a refindex.KmerIndex (host arrays in the reference's format)."""
+        starts = np.asarray(ref.ref_start, dtype=np.uint64)
+        lens = np.asarray(ref.ref_len, dtype=np.uint64)
+        npos = C.c_uint32(0)
+        u64p = C.POINTER(C.c_uint64)
+        self._check(self.lib.ngmlr_b200_cs_build_index(self.h, starts.ctypes.data_as(u64p), lens.ctypes.data_as(u64p),
+                                                       int(starts.size), k, kmer_skip, bin_shift, max_prefix_freq,
+                                                       C.byref(npos)))
+        self.index_build_ms = float(self.lib.ngmlr_b200_cs_last_build_ms(self.h))
+        if not fetch:
+            return npos.value
+        return self.get_index(k, bin_shift)
+
+    def get_index(self, k=13, bin_shift=4):
+        from .refindex import KmerIndex
+        n_idx, n_pos = C.c_uint32(0), C.c_uint32(0)
+        self._check(self.lib.ngmlr_b200_cs_get_index(self.h, C.byref(n_idx), C.byref(n_pos), None, None))
+        packed = np.zeros(n_idx.value * 5, dtype=np.uint8)
+        pos = np.zeros(max(n_pos.value, 1), dtype=np.uint32)
+        self._check(self.lib.ngmlr_b200_cs_get_index(self.h, None, None, packed.ctypes.data_as(C.c_void_p),
+                                                     pos.ctypes.data_as(C.c_void_p)))
+        rec = packed.reshape(-1, 5)
+        tab = np.ascontiguousarray(rec[:, :4]).view(np.uint32).reshape(-1)
+        rci = np.ascontiguousarray(rec[:, 4]).view(np.int8)
+        return KmerIndex(k, bin_shift, tab, rci, pos[:n_pos.value])
+
     def cs_search(self, seqs, sensitivity=0.8, min_kmer_hits=0.0):
         """Candidates of each (sub-)read, in the reference's emission order:
         list of [(score, location, reverse)], plus maxHitNumber per read."""

@@ -402,6 +402,14 @@ int ngmlr_b200_cs_set_index(ngmlr_b200_ctx* ctx, const void* packed_index, uint3
   if (n_positions)
     CU(cudaMemcpyAsync(cs->d_pos.p, positions, (size_t)n_positions * 4, cudaMemcpyHostToDevice, st));
   CU(launch_unpack_index(cs->d_packed.p, index_len, cs->d_tab.p, cs->d_used.p, st));
+  {  // m_RevCompIndex, kept for cs_get_index
+    std::vector<int8_t> rci(index_len);
+    const uint8_t* src = static_cast<const uint8_t*>(packed_index);
+    for (size_t i = 0; i < index_len; ++i) rci[i] = (int8_t)src[5 * i + 4];
+    CU(cs->d_rci.reserve((size_t)index_len + 1));
+    CU(cudaMemcpyAsync(cs->d_rci.p, rci.data(), index_len, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+  }
   CU(cudaStreamSynchronize(st));
   cs->d_packed.release();
   cs->index_len = index_len;
@@ -410,6 +418,115 @@ int ngmlr_b200_cs_set_index(ngmlr_b200_ctx* ctx, const void* packed_index, uint3
   cs->k = k;
   cs->bin_shift = bin_shift;
   return 0;
+}
+
+// Builds the k-mer index of the encoded reference that is resident on the device (cs_set_reference) and
+// installs it as the context's index: CompactPrefixTable::CreateTable on the GPU (cs_index_build.cu).
+int ngmlr_b200_cs_build_index(ngmlr_b200_ctx* ctx, const uint64_t* contig_start, const uint64_t* contig_len,
+                              int n_contigs, int k, int kmer_skip, int bin_shift, int max_prefix_freq,
+                              uint32_t* n_positions) {
+  if (!ctx) return -1;
+  CsState* cs = cs_state(ctx, false);
+  if (!cs || !cs->enc_bytes) return ctx->fail("cs_build_index: call cs_set_reference first");
+  if (k < 1 || k > 15) return ctx->fail("cs_build_index: k must be in 1..15");
+  if (n_contigs < 1 || kmer_skip < 0 || max_prefix_freq < 1) return ctx->fail("cs_build_index: bad arguments");
+  if (cs->concat_len >= 0xffff0000ull) return ctx->fail("cs_build_index: one table unit holds < 4 G positions");
+  for (int i = 0; i < n_contigs; ++i) {
+    if (i && contig_start[i] < contig_start[i - 1] + contig_len[i - 1]) return ctx->fail("cs_build_index: contigs must be sorted and disjoint");
+    if (contig_start[i] + contig_len[i] > cs->concat_len) return ctx->fail("cs_build_index: contig %d leaves the reference", i);
+  }
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const unsigned long long cl = cs->concat_len;
+  const uint32_t n_kmers = 1u << (2 * k);
+  const unsigned long long cb_cap = cl / (unsigned long long)(kmer_skip + 1) + (unsigned long long)n_contigs * 64 + 1024;
+  DevBuf<uint32_t> lastn, prefix, pos, key, key_out, pos_out, freq, alloc_cnt, used_cnt, alloc_start, used_start;
+  DevBuf<uint8_t> flag, keep, cub_tmp;
+  DevBuf<unsigned long long> d_contigs;
+  CU(lastn.reserve(cl + 16));
+  CU(flag.reserve(cl + 16));
+  CU(prefix.reserve(cb_cap)); CU(pos.reserve(cb_cap)); CU(key.reserve(cb_cap)); CU(key_out.reserve(cb_cap)); CU(pos_out.reserve(cb_cap));
+  CU(keep.reserve(cb_cap));
+  CU(freq.reserve(n_kmers + 2)); CU(alloc_cnt.reserve(n_kmers + 2)); CU(used_cnt.reserve(n_kmers + 2));
+  CU(alloc_start.reserve(n_kmers + 2)); CU(used_start.reserve(n_kmers + 2));
+  const size_t cub_bytes = index_build_cub_bytes(cl, cb_cap, k);
+  CU(cub_tmp.reserve(cub_bytes));
+  CU(d_contigs.reserve((size_t)2 * n_contigs));
+  std::vector<unsigned long long> hc((size_t)2 * n_contigs);
+  for (int i = 0; i < n_contigs; ++i) {
+    hc[i] = contig_start[i];
+    hc[n_contigs + i] = contig_len[i];
+  }
+  CU(cudaMemcpyAsync(d_contigs.p, hc.data(), hc.size() * 8, cudaMemcpyHostToDevice, st));
+  CU(cs->d_tab.reserve((size_t)n_kmers + 2));
+  CU(cs->d_rci.reserve((size_t)n_kmers + 2));
+  CU(cs->d_used.reserve(((size_t)n_kmers + 1 + 255) / 256 * 8 + 8));
+  CU(cs->d_pos.reserve(cb_cap + 1));
+  IndexBuildParams p;
+  p.enc = cs->d_enc.p;
+  p.concat_len = cl;
+  p.contig_start = d_contigs.p;
+  p.contig_len = d_contigs.p + n_contigs;
+  p.n_contigs = n_contigs;
+  p.k = k;
+  p.skip = kmer_skip;
+  p.bin_shift = bin_shift;
+  p.max_freq = max_prefix_freq;
+  p.unit_offset = 0;
+  IndexBuildScratch s;
+  memset(&s, 0, sizeof(s));
+  s.lastn = lastn.p; s.slot = lastn.p; s.flag = flag.p;
+  s.cb_capacity = cb_cap;
+  s.prefix = prefix.p; s.pos = pos.p; s.key = key.p; s.key_out = key_out.p; s.pos_out = pos_out.p; s.keep = keep.p;
+  s.freq = freq.p; s.alloc_cnt = alloc_cnt.p; s.used_cnt = used_cnt.p; s.alloc_start = alloc_start.p; s.used_start = used_start.p;
+  s.tab = cs->d_tab.p; s.rci = cs->d_rci.p; s.used_bits = cs->d_used.p; s.out_pos = cs->d_pos.p;
+  s.out_capacity = cs->d_pos.cap;
+  s.cub_tmp = cub_tmp.p; s.cub_bytes = cub_bytes;
+  CU(cudaEventRecord(ctx->ev[4], st));
+  CU(build_kmer_index(p, s, st));
+  CU(cudaEventRecord(ctx->ev[5], st));
+  CU(cudaStreamSynchronize(st));
+  cs->index_len = n_kmers + 1;
+  cs->n_pos = s.n_positions;
+  cs->unit_offset = 0;
+  cs->k = k;
+  cs->bin_shift = bin_shift;
+  cs->rn = 0;
+  if (n_positions) *n_positions = s.n_positions;
+  return 0;
+}
+
+// The context's index in the reference's in-memory format (whatever installed it): packed_index receives
+// index_len x 5 bytes (Index{uint m_TabIndex; char m_RevCompIndex}, #pragma pack(1)), positions n_positions
+// uint32 (either may be NULL to query the sizes only).
+int ngmlr_b200_cs_get_index(ngmlr_b200_ctx* ctx, uint32_t* index_len, uint32_t* n_positions, void* packed_index,
+                            uint32_t* positions) {
+  if (!ctx) return -1;
+  CsState* cs = cs_state(ctx, false);
+  if (!cs || !cs->index_len) return ctx->fail("cs_get_index: no index");
+  if (index_len) *index_len = cs->index_len;
+  if (n_positions) *n_positions = cs->n_pos;
+  CU(cudaSetDevice(ctx->device));
+  if (packed_index) {
+    if (!cs->d_rci.p) return ctx->fail("cs_get_index: index was installed without m_RevCompIndex");
+    std::vector<uint32_t> tab(cs->index_len);
+    std::vector<int8_t> rci(cs->index_len);
+    CU(cudaMemcpy(tab.data(), cs->d_tab.p, (size_t)cs->index_len * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(rci.data(), cs->d_rci.p, (size_t)cs->index_len, cudaMemcpyDeviceToHost));
+    uint8_t* out = static_cast<uint8_t*>(packed_index);
+    for (size_t i = 0; i < cs->index_len; ++i) {
+      memcpy(out + 5 * i, &tab[i], 4);
+      out[5 * i + 4] = (uint8_t)rci[i];
+    }
+  }
+  if (positions && cs->n_pos) CU(cudaMemcpy(positions, cs->d_pos.p, (size_t)cs->n_pos * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+float ngmlr_b200_cs_last_build_ms(ngmlr_b200_ctx* ctx) {
+  float ms = 0;
+  if (ctx) cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]);
+  return ms;
 }
 
 int ngmlr_b200_cs_search_batch(ngmlr_b200_ctx* ctx, int n, const char* const* seqs,

@@ -214,6 +214,38 @@ struct RefDecodeParams {
   uint8_t* out;
 };
 
+// ---- k-mer index construction on the device (cs_index_build.cu) ------------------------------
+struct IndexBuildParams {
+  const uint8_t* enc;                      // binRef: 2 bases per byte, A0 T1 G2 C3 N4, spacer-padded
+  unsigned long long concat_len;
+  const unsigned long long* contig_start;  // device, sorted (SequenceProvider.GetRefStart)
+  const unsigned long long* contig_len;    // device (GetRefLen)
+  int n_contigs;
+  int k, skip, bin_shift, max_freq;        // --kmer-length 13, --kmer-skip 2, --bin-size 4, maxPrefixFreq 1000
+  unsigned long long unit_offset;          // TableUnit::Offset
+};
+
+struct IndexBuildScratch {
+  uint32_t* lastn;      // [concat_len] last N at or before the base; reused as the callback slot index
+  uint32_t* slot;       // (= lastn)
+  uint8_t* flag;        // [concat_len] PrefixIteration calls back here
+  unsigned long long cb_capacity;
+  uint32_t *prefix, *pos, *key, *key_out, *pos_out;  // [cb_capacity]
+  uint8_t* keep;        // [cb_capacity]
+  uint32_t *freq, *alloc_cnt, *used_cnt, *alloc_start, *used_start;  // [4^k + 1]
+  // outputs (the context's index arrays)
+  uint32_t* tab;        // [4^k + 1] Index::m_TabIndex
+  int8_t* rci;          // [4^k + 1] Index::m_RevCompIndex
+  uint32_t* used_bits;
+  uint32_t* out_pos;    // Location lists
+  unsigned long long out_capacity;
+  void* cub_tmp;
+  size_t cub_bytes;
+  // results
+  unsigned long long n_callbacks;
+  uint32_t n_positions, n_used;
+};
+
 // ---- candidate search -------------------------------------------------------------------
 struct alignas(16) CsCandidate {
   unsigned long long loc;  // LocationScore::Location.m_Location = ResolveBin(bin)

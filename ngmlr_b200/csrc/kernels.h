@@ -50,6 +50,10 @@ cudaError_t launch_cs_search(const CsParams& p, bool count_only, cudaStream_t st
 cudaError_t launch_unpack_index(const uint8_t* packed, uint32_t n, uint32_t* tab, uint32_t* used_bits,
                                 cudaStream_t stream);
 
+// k-mer index of the resident encoded reference, built on the device (cs_index_build.cu)
+cudaError_t build_kmer_index(const IndexBuildParams& p, IndexBuildScratch& s, cudaStream_t stream);
+size_t index_build_cub_bytes(unsigned long long concat_len, unsigned long long max_callbacks, int k);
+
 // device-resident candidate pipeline glue (cs_pipeline.cu)
 cudaError_t cs_exclusive_scan(void* temp, size_t& temp_bytes, const unsigned long long* in,
                               unsigned long long* out, int n, cudaStream_t stream);

@@ -291,6 +291,7 @@ struct CsState {
   DevBuf<uint8_t> d_packed;
   DevBuf<uint32_t> d_tab, d_pos, d_order;
   DevBuf<uint32_t> d_used;  // bitmap
+  DevBuf<int8_t> d_rci;     // Index::m_RevCompIndex
   DevBuf<uint8_t> d_seq, d_tables;
   DevBuf<uint64_t> d_off;     // seq_off | table_off | order_off | out_off
   DevBuf<int32_t> d_len, d_count;
