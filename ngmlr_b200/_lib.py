@@ -93,6 +93,7 @@ def load():
     lib.ngmlr_b200_set_force_team.argtypes = [vp, C.c_int]
     lib.ngmlr_b200_set_fill_ctas_per_sm.argtypes = [vp, C.c_int]
     lib.ngmlr_b200_debug_set_arena_words.argtypes = [vp, C.c_longlong]
+    lib.ngmlr_b200_debug_set_big_team.argtypes = [vp, C.c_longlong, C.c_int]
     batch = [vp, C.c_int, cpp, i32p, cpp, i32p, i32p, i32p, i64p, i32p, i32p]
     lib.ngmlr_b200_convex_upload.argtypes = batch
     lib.ngmlr_b200_convex_align_batch.argtypes = batch + [C.POINTER(AlignResult)]

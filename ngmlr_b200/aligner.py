@@ -452,6 +452,10 @@ class B200Aligner:
         """Cap the persistent fill grid (0 = full occupancy); see ngmlr_b200_set_fill_ctas_per_sm."""
         self.lib.ngmlr_b200_set_fill_ctas_per_sm(self.h, int(v))
 
+    def debug_set_big_team(self, cells, width):
+        """Test hook: matrices of at least `cells` cells in corridors at least `width` wide get 16-warp teams."""
+        self.lib.ngmlr_b200_debug_set_big_team(self.h, int(cells), int(width))
+
     def force_team(self, v):
         """-1 auto, 0 one warp per problem, 1 four-warp teams (fill kernel scheduling)."""
         self.lib.ngmlr_b200_set_force_team(self.h, int(v))

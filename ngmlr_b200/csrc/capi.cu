@@ -89,6 +89,8 @@ int ngmlr_b200_create(int gpu_id, const ngmlr_b200_scoring* s, ngmlr_b200_ctx** 
     return -1;
   }
   cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&ctx->ev_big, cudaEventDisableTiming);
   for (auto& ev : ctx->ev) cudaEventCreate(&ev);
   ngmlr_b200_scoring d = {2.0f, -5.0f, -5.0f, -5.0f, -1.0f, 0.15f};
   if (s) d = *s;
@@ -123,6 +125,8 @@ void ngmlr_b200_destroy(ngmlr_b200_ctx* ctx) {
   ctx->d_sw_seq.release(); ctx->d_sw_off.release(); ctx->d_sw_len.release(); ctx->d_sw_out.release();
   ctx->d_sw_scratch.release();
   for (auto& ev : ctx->ev) cudaEventDestroy(ev);
+  if (ctx->ev_big) cudaEventDestroy(ctx->ev_big);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -180,6 +184,15 @@ int ngmlr_b200_debug_cigar_text(const int32_t* runs, int n_runs, const char* ref
   const size_t n = std::min(t.nm_positions.size(), (size_t)std::max(nm_cap, 0));
   if (n) memcpy(nm_out, t.nm_positions.data(), n * sizeof(int32_t));
   return ok ? 1 : 0;
+}
+
+// Test / tuning hook: which problems get FILL_BIG_TEAM-warp teams (cells and corridor width from which a
+// matrix counts as huge; defaults 8 Mi cells, 768 columns).
+int ngmlr_b200_debug_set_big_team(ngmlr_b200_ctx* ctx, long long cells, int width) {
+  if (!ctx) return -1;
+  ctx->big_cells = cells < 0 ? ~0ull : (unsigned long long)cells;
+  ctx->big_width = width;
+  return 0;
 }
 
 // force_team: -1 auto, 0 one warp per problem, 1 four-warp teams. Test / tuning hook.

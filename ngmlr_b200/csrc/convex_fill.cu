@@ -101,22 +101,26 @@ struct TeamBest {
   unsigned long long cells;
 };
 
+// NW = warps that pipeline ONE problem (1: every warp of the CTA has its own problem; otherwise the whole
+// CTA is the team: 4 warps for ordinary corridors, FILL_BIG_TEAM warps for the few huge matrices of a batch
+// -- a 10^8-cell realignment matrix would otherwise keep one 4-warp team busy long after the rest of the
+// grid has drained).
 template <bool RAW, int NW>
-__global__ void __launch_bounds__(FILL_WARPS_PER_CTA * 32, FILL_CTAS_PER_SM)
+__global__ void __launch_bounds__((NW == 1 ? FILL_WARPS_PER_CTA : NW) * 32, NW > FILL_WARPS_PER_CTA ? 1 : FILL_CTAS_PER_SM)
 convex_fill_kernel(const FillParams p) {
+  constexpr int WARPS = NW == 1 ? FILL_WARPS_PER_CTA : NW;  // warps per CTA
   constexpr int CHUNK = NW == 1 ? 64 : FILL_TEAM_CHUNK;  // steps staged through shared memory at a time
   constexpr int GPC = CHUNK / 16;           // 16-step groups per chunk
-  static_assert(NW == 1 || NW == FILL_WARPS_PER_CTA, "a team is one warp or the whole CTA");
   // staging records of a chunk, interleaved: s_io[w][2 * j] = what lane 0 consumes at step j of the chunk,
   // s_io[w][2 * j + 1] = what lane 31 produced at step j (one base register + immediates serve both)
-  __shared__ uint4 s_io[FILL_WARPS_PER_CTA][2 * (CHUNK + 1)];  // +1: lane 31 reads one record ahead
-  __shared__ volatile unsigned long long s_prog[FILL_WARPS_PER_CTA];
+  __shared__ uint4 s_io[WARPS][2 * (CHUNK + 1)];  // +1: lane 31 reads one record ahead
+  __shared__ volatile unsigned long long s_prog[WARPS];
   __shared__ int s_work;
-  __shared__ TeamBest s_best[FILL_WARPS_PER_CTA];
+  __shared__ TeamBest s_best[WARPS];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int tw = NW == 1 ? 0 : wib;  // warp index within the team
-  const int team_global = NW == 1 ? blockIdx.x * FILL_WARPS_PER_CTA + wib : blockIdx.x;
+  const int team_global = NW == 1 ? blockIdx.x * WARPS + wib : blockIdx.x;
   uint4* const io_s = s_io[wib];
   // strip[x + STRIP_PAD] = {S, U, run, ref byte} of column x of the most recently finished bottom row
   uint4* const strip = reinterpret_cast<uint4*>(p.bnd) + (size_t)team_global * p.bnd_stride + STRIP_PAD;
@@ -138,7 +142,8 @@ convex_fill_kernel(const FillParams p) {
       __syncthreads();
       w = s_work;
     }
-    if (w >= p.n) break;
+    w += p.first;  // this launch works on order[first, last)
+    if (w >= p.last) break;
     const int ai = p.order[w];
     const AlnDesc d = p.desc[ai];
     const uint8_t* __restrict__ ref = p.seq + d.ref_off;
@@ -504,6 +509,13 @@ cudaError_t launch_convex_fill(const FillParams& p, bool raw, bool team, int gri
     if (team) convex_fill_kernel<false, FILL_WARPS_PER_CTA><<<grid, threads, 0, stream>>>(p);
     else convex_fill_kernel<false, 1><<<grid, threads, 0, stream>>>(p);
   }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_convex_fill_big(const FillParams& p, bool raw, int grid, cudaStream_t stream) {
+  const int threads = FILL_BIG_TEAM * 32;
+  if (raw) convex_fill_kernel<true, FILL_BIG_TEAM><<<grid, threads, 0, stream>>>(p);
+  else convex_fill_kernel<false, FILL_BIG_TEAM><<<grid, threads, 0, stream>>>(p);
   return cudaGetLastError();
 }
 

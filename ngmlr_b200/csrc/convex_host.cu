@@ -195,8 +195,18 @@ int convex_upload_spec(ngmlr_b200_ctx* ctx, const UploadSpec& sp) {
     ctx->ext_qe[i] = ctx->h_desc.p[i].ext_qend;
   }
   const size_t so = seq_bytes, bo = nblocks;
+  // Largest first (LPT); the few huge and wide matrices of a batch -- realignments, full matrices, corridors
+  // widened by the anchors around a long indel -- lead the order: they get FILL_BIG_TEAM-warp teams.
+  std::vector<uint8_t> big(n);
+  int n_big = 0;
+  for (int i = 0; i < n; ++i) {
+    big[i] = est[i] >= ctx->big_cells && maxlen[i] >= ctx->big_width;
+    n_big += big[i];
+  }
+  ctx->n_big = n_big;
   std::iota(ctx->h_order.p, ctx->h_order.p + n, 0);
-  std::stable_sort(ctx->h_order.p, ctx->h_order.p + n, [&](int a, int b) { return est[a] > est[b]; });
+  std::stable_sort(ctx->h_order.p, ctx->h_order.p + n,
+                   [&](int a, int b) { return big[a] != big[b] ? big[a] > big[b] : est[a] > est[b]; });
   ctx->seq_bytes = so;
   ctx->rows = rows;
   ctx->nblocks = bo;
@@ -419,7 +429,11 @@ int ngmlr_b200_convex_run(ngmlr_b200_ctx* ctx) {
   ctx->fill_grid = grid;
   const size_t warps = (size_t)grid * FILL_WARPS_PER_CTA;
   const size_t bnd_stride = align_up((size_t)ctx->max_ref_len + STRIP_SLACK, 8);
-  CU(ctx->d_bnd.reserve(warps * bnd_stride));
+  // huge matrices: their own launch with FILL_BIG_TEAM-warp teams, concurrent with the rest (second stream)
+  int n_big = (ctx->team_safe && ctx->force_team != 0 && !getenv("NGMLR_B200_NO_BIG_TEAMS")) ? ctx->n_big : 0;
+  if (n_big > 2 * ctx->num_sms && n_big * 2 > n) n_big = 0;  // a batch of huge problems only: 4-warp teams fill the GPU
+  const int big_grid = std::min(n_big, ctx->num_sms);
+  CU(ctx->d_bnd.reserve((warps + (size_t)big_grid) * bnd_stride));
   size_t dir_words = std::max(ctx->dir_words_needed, (size_t)4096);
   if (ctx->debug_arena_words >= 0) {  // force the overflow -> grow -> re-run path (tests)
     dir_words = (size_t)ctx->debug_arena_words;
@@ -452,6 +466,8 @@ int ngmlr_b200_convex_run(ngmlr_b200_ctx* ctx) {
       fp.desc = ctx->d_desc.p;
       fp.order = ctx->d_order.p;
       fp.n = n;
+      fp.first = n_big;
+      fp.last = n;
       fp.blocks = ctx->d_blocks.p;
       fp.dir = ctx->d_dir.p;
       fp.dir_capacity = ctx->d_dir.cap;
@@ -479,7 +495,18 @@ int ngmlr_b200_convex_run(ngmlr_b200_ctx* ctx) {
       tp.runs_capacity = ctx->d_runs.cap;
       tp.runs_alloc = ctx->d_counters.p + 1;
       CU(cudaEventRecord(ctx->ev[0], st));
-      CU(launch_convex_fill(fp, raw, team, grid, st));
+      if (n_big > 0) {
+        FillParams fb = fp;
+        fb.first = 0;
+        fb.last = n_big;
+        fb.work_counter = reinterpret_cast<int*>(ctx->d_counters.p + 3);
+        fb.bnd = ctx->d_bnd.p + warps * bnd_stride;
+        CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev[0], 0));
+        CU(launch_convex_fill_big(fb, raw, big_grid, ctx->stream2));
+        CU(cudaEventRecord(ctx->ev_big, ctx->stream2));
+      }
+      if (n - n_big > 0) CU(launch_convex_fill(fp, raw, team, grid, st));
+      if (n_big > 0) CU(cudaStreamWaitEvent(st, ctx->ev_big, 0));
       CU(cudaEventRecord(ctx->ev[1], st));
       CU(launch_convex_traceback(tp, st));
       CU(cudaEventRecord(ctx->ev[2], st));

@@ -120,6 +120,7 @@ struct FillParams {
   const AlnDesc* desc;
   const int32_t* order;   // problem indices, largest first
   int n;
+  int first, last;        // this launch works on order[first, last)
   BlockRec* blocks;
   uint32_t* dir;                        // direction arena (32-bit words)
   unsigned long long dir_capacity;      // words

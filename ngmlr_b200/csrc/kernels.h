@@ -8,9 +8,12 @@ namespace nb {
 
 constexpr int FILL_WARPS_PER_CTA = 4;
 constexpr int FILL_CTAS_PER_SM = 5;
+constexpr int FILL_BIG_TEAM = 16;  // warps that pipeline one huge matrix (one CTA per SM)
 
 // team = all FILL_WARPS_PER_CTA warps of a CTA pipeline one problem; otherwise one warp per problem
 cudaError_t launch_convex_fill(const FillParams& p, bool raw, bool team, int grid, cudaStream_t stream);
+// the same kernel with a FILL_BIG_TEAM-warp team per problem, for the huge matrices of a batch
+cudaError_t launch_convex_fill_big(const FillParams& p, bool raw, int grid, cudaStream_t stream);
 int fill_max_ctas_per_sm(bool raw, bool team);
 
 cudaError_t launch_convex_traceback(const TraceParams& p, cudaStream_t stream);

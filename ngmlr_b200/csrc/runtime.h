@@ -169,6 +169,11 @@ struct ngmlr_b200_ctx {
   int device = 0;
   int num_sms = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;   // the big-team fill launch runs beside the ordinary one
+  cudaEvent_t ev_big = nullptr;
+  unsigned long long big_cells = 8ull << 20;  // a problem is "big" from this many cells ...
+  int big_width = 768;                        // ... in a corridor at least this wide
+  int n_big = 0;                    // leading problems of the order that get FILL_BIG_TEAM-warp teams
   bool own_stream = true;
   cudaEvent_t ev[8] = {};
   nb::Scoring sc{};

@@ -148,6 +148,22 @@ def test_both_fill_schedules_are_bit_exact(aligner, oracle, team):
         aligner.force_team(-1)
 
 
+def test_big_team_fill_is_bit_exact(aligner, oracle):
+    """The few huge matrices of a batch are filled by 16-warp teams in a launch of their own, beside the
+    ordinary one (thresholds lowered here so that ordinary test problems qualify): same matrices, same
+    alignments -- in a mixed batch, and in a batch that consists of 'huge' problems only."""
+    probs = (cases.random_problems(60, 717, max_len=1800, modes=(0, 2, 3))
+             + synth.pacbio_problems(6, genome_len=300_000, seed=13, median=4000))
+    try:
+        aligner.debug_set_big_team(150_000, 100)
+        _compare_batch(aligner, oracle, probs, check_dirs=True)
+        big_only = [p for p in probs if p.cells >= 150_000 and p.lengths[0] >= 100][:12]
+        assert len(big_only) >= 6
+        _compare_batch(aligner, oracle, big_only, check_dirs=True)
+    finally:
+        aligner.debug_set_big_team(8 << 20, 768)
+
+
 @pytest.mark.parametrize("team", [0, 1])
 def test_fill_grid_cap_does_not_change_results(aligner, oracle, team):
     """ngmlr_b200_set_fill_ctas_per_sm: a persistent grid of 1 CTA per SM (every CTA walks many
