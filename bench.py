@@ -132,8 +132,11 @@ class CpuStage02:
     """Stage 0/2 on the CPU with the reference's own code (oracle/_ref/libngmlr_full.so: CS vote,
     DecodeRefSequence, StrippedSW), or with the oracle port when that library is absent."""
 
-    def __init__(self, genome, n_contigs=5):
+    def __init__(self, genome, n_contigs=5, prefer=None):
         n_contigs = int(n_contigs)
+        if prefer is None and genome.size > 500_000_000:
+            prefer = "port"   # the reference takes tens of minutes to index a human-sized FASTA; the C port builds
+                              # the same index (tests/test_cs_oracle.py) in about a minute
         import ctypes as C
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_lib
@@ -141,7 +144,7 @@ class CpuStage02:
         step_c = genome.size // n_contigs
         contigs = [genome[i * step_c:(i + 1) * step_c] for i in range(n_contigs)]
         self.kind = "port"
-        if oracle_lib.CsReference.available():
+        if prefer != "port" and oracle_lib.CsReference.available():
             try:
                 fasta = f"/tmp/ngmlr_b200_bench_{os.getpid()}.fa"
                 with open(fasta, "w") as f:
@@ -176,6 +179,15 @@ class CpuStage02:
         """One sub-read through the reference's CS vote, DecodeRefSequence and StrippedSW:
         [(location, reverse, vote score, sw score)] in the reference's emission order."""
         C = self.C
+        if self.kind == "port":
+            sub = bytes(sub)
+            cands, _ = self.orc.search(sub)
+            out = []
+            for (s_, loc, rev) in cands:
+                w = self.orc.decode((loc - 20) % (1 << 64), 308) or b"N" * 308
+                out.append((int(loc), int(rev), float(s_),
+                            float(self.ssw.ssw_score(w, sub.translate(self._CPL)[::-1] if rev else sub))))
+            return out
         sc = (C.c_float * 512)()
         lo = (C.c_ulonglong * 512)()
         rv = (C.c_int * 512)()
@@ -327,22 +339,22 @@ def cpu_work_items(wl, n_reads):
 
 
 def build_reference(args, cfg, rank, world, dev):
-    """Genome + 4-bit encoding + k-mer index on rank 0, then ONE NCCL broadcast of the packed reference
-    (ngmlr_b200.parallel.broadcast_reference); no collective per step."""
+    """The synthetic genome is generated and 4-bit encoded on rank 0, then ONE NCCL broadcast of the packed
+    reference (ngmlr_b200.parallel.broadcast_reference); every rank decodes the flat genome it simulates its
+    reads from. The k-mer index is built on each rank's own GPU (main()). No collective per step."""
     from ngmlr_b200 import parallel, refindex, synth
-    n_genome = int(args.genome_mb * 1e6)
     n_contigs = cfg["contigs"]
-    contig_len = n_genome // n_contigs
-    n_genome = contig_len * n_contigs
-    genome = enc_ref = kidx = None
+    contig_len = int(args.genome_mb * 1e6) // n_contigs
+    genome = enc_ref = None
     t0 = time.perf_counter()
     if rank == 0:
-        genome = synth.random_genome(n_genome, 1)
+        genome = synth.random_genome(contig_len * n_contigs, 1)
         enc_ref = refindex.encode_reference([genome[i * contig_len:(i + 1) * contig_len] for i in range(n_contigs)])
-        kidx = refindex.build_index(enc_ref)
     if world > 1:
-        genome, enc_ref, kidx = parallel.broadcast_reference(genome, enc_ref, kidx, src=0, device=dev)
-    return genome, contig_len, enc_ref, kidx, time.perf_counter() - t0
+        enc_ref = parallel.broadcast_reference(enc_ref, src=0, device=dev)
+        if rank != 0:
+            genome = np.concatenate(refindex.decode_contigs(enc_ref))
+    return genome, contig_len, enc_ref, time.perf_counter() - t0
 
 
 def main():
@@ -427,7 +439,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    genome, contig_len, enc_ref, kidx, t_ref = build_reference(args, cfg, rank, world, dev)
+    genome, contig_len, enc_ref, t_ref = build_reference(args, cfg, rank, world, dev)
 
     from ngmlr_b200 import B200Aligner, IntervalBatch, PackedReads
     wl = Workload(genome, contig_len, enc_ref, args.reads, 2 + rank, cfg)   # reads sharded by rank: own reads per rank
@@ -443,9 +455,14 @@ def main():
     streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
     als = [B200Aligner(local_rank, stream=st_.cuda_stream) for st_ in streams]
     al = als[0]
-    for a_ in als:
-        a_.set_index(kidx)
-        a_.set_reference(enc_ref)
+    # one copy of the encoded reference per GPU; the k-mer index is built from it ON the device
+    # (CompactPrefixTable::CreateTable as kernels) and shared by the GPU's contexts
+    al.set_reference(enc_ref)
+    t_idx0 = time.perf_counter()
+    n_positions = al.build_index(enc_ref)
+    t_index = time.perf_counter() - t_idx0
+    for a_ in als[1:]:
+        a_.share_reference(al)
     sl_reads, sl_ivs, sl_bases = [], [], []
     for j in range(S):
         r_, iv_, rmap = wl.slice(j, S)
@@ -640,7 +657,8 @@ def main():
                                    "stage02_cs_vote_decode_score": float(np.mean(cs_ms))},
             "stage02": {"subreads_per_step_per_gpu": n_sub, "candidates_per_step_per_gpu": int(n_cand),
                         "sw_cell_updates_per_step_per_gpu": int(n_cand) * 257 * 307,
-                        "reference_setup_s": t_ref},
+                        "reference_setup_s": t_ref, "index_build_on_device_s": t_index,
+                        "index_build_kernels_ms": al.index_build_ms, "index_positions": int(n_positions)},
             "e2e": {"value": e2e_val, "unit": "Gbp/s", "h2d_bytes_per_step": e2e_h2d,
                     "d2h_bytes_per_step": e2e_d2h, "ms_per_step": e2e_ms / args.steps,
                     "host_ms_per_slice_first_attempt": {k: float(np.mean([x["host_ms"][k] for x in io]))
@@ -709,7 +727,7 @@ def parity_check(wl, cpu_aligned, gpu_first, gpu_cs, st02, n_stage02_reads):
             assert want[key] == g[key], f"parity: read {r} interval {k}: {key} differs (cpu {want[key]!r:.80} gpu {g[key]!r:.80})"
         n_al += 1
     out = {"alignments": n_al, "fields": "ret, score bits, CIGAR, MD, NM, PositionOffset, QStart, QEnd, alignmentLength"}
-    if gpu_cs is not None and st02 is not None and st02.kind == "reference":
+    if gpu_cs is not None and st02 is not None:
         cstart, cs_sc, cs_lo, cs_rv, cs_sw, _mx = gpu_cs
         s = 0   # global sub-read index
         n_sub = n_c = 0

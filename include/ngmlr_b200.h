@@ -185,6 +185,10 @@ int ngmlr_b200_cs_set_index(ngmlr_b200_ctx* ctx, const void* packed_index, uint3
 int ngmlr_b200_cs_build_index(ngmlr_b200_ctx* ctx, const uint64_t* contig_start, const uint64_t* contig_len,
                               int n_contigs, int k, int kmer_skip, int bin_shift, int max_prefix_freq,
                               uint32_t* n_positions);
+/* Several contexts on one GPU (one per host thread -- the reference has one aligner object per worker
+ * thread) share ONE copy of the encoded reference and k-mer index: ctx uses owner's device arrays. owner
+ * must outlive ctx and must not replace its reference / index meanwhile. */
+int ngmlr_b200_cs_share_reference(ngmlr_b200_ctx* ctx, ngmlr_b200_ctx* owner);
 /* The context's index back in the reference's in-memory format (for the byte-compatible
  * -ht-<k>-<skip>.2.ngm writer): sizes, and -- where the pointers are not NULL -- index_len x 5 packed
  * Index bytes and n_positions Location words. */

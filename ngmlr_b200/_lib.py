@@ -62,7 +62,8 @@ C_API_SYMBOLS = (
     "ngmlr_b200_cs_set_reference", "ngmlr_b200_cs_score_batch", "ngmlr_b200_cs_upload",
     "ngmlr_b200_cs_run", "ngmlr_b200_cs_fetch", "ngmlr_b200_select_candidates",
     "ngmlr_b200_set_ref_starts", "ngmlr_b200_decode_windows", "ngmlr_b200_convex_upload_windows",
-    "ngmlr_b200_cs_build_index", "ngmlr_b200_cs_get_index", "ngmlr_b200_set_text_stage", "ngmlr_b200_reads_upload", "ngmlr_b200_reads_h2d_bytes",
+    "ngmlr_b200_cs_build_index", "ngmlr_b200_cs_get_index", "ngmlr_b200_cs_share_reference",
+    "ngmlr_b200_set_text_stage", "ngmlr_b200_reads_upload", "ngmlr_b200_reads_h2d_bytes",
     "ngmlr_b200_compute_alignments", "ngmlr_b200_compute_alignments_stats", "ngmlr_b200_intervals_upload",
 )
 PLUGIN_SYMBOLS = ("CreateAlignment", "DeleteAlignment", "SetAlignmentScoring")
@@ -127,6 +128,7 @@ def load():
     lib.ngmlr_b200_cs_build_index.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int, C.c_int, C.c_int,
                                               C.c_int, C.c_int, C.POINTER(C.c_uint32)]
     lib.ngmlr_b200_cs_get_index.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), vp, vp]
+    lib.ngmlr_b200_cs_share_reference.argtypes = [vp, vp]
     lib.ngmlr_b200_cs_last_build_ms.argtypes = [vp]
     lib.ngmlr_b200_cs_last_build_ms.restype = C.c_float
     lib.ngmlr_b200_set_text_stage.argtypes = [vp, C.c_int, C.c_int]

@@ -268,6 +268,10 @@ class B200Aligner:
             return npos.value
         return self.get_index(k, bin_shift)
 
+    def share_reference(self, owner):
+        """Use the encoded reference and k-mer index resident in `owner` (another B200Aligner on this GPU)."""
+        self._check(self.lib.ngmlr_b200_cs_share_reference(self.h, owner.h))
+
     def get_index(self, k=13, bin_shift=4):
         from .refindex import KmerIndex
         n_idx, n_pos = C.c_uint32(0), C.c_uint32(0)

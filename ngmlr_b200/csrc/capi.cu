@@ -433,6 +433,35 @@ int ngmlr_b200_cs_set_index(ngmlr_b200_ctx* ctx, const void* packed_index, uint3
   return 0;
 }
 
+// Several contexts on one GPU (one per host thread, as the reference has one aligner object per worker
+// thread) need the same encoded reference and k-mer index: `ctx` uses the device arrays of `owner` instead of
+// holding copies. `owner` must outlive `ctx` and must not replace its reference / index meanwhile.
+int ngmlr_b200_cs_share_reference(ngmlr_b200_ctx* ctx, ngmlr_b200_ctx* owner) {
+  if (!ctx || !owner) return -1;
+  if (ctx == owner) return 0;
+  if (ctx->device != owner->device) return ctx->fail("cs_share_reference: contexts live on different devices");
+  CsState* from = cs_state(owner, false);
+  if (!from || !from->enc_bytes) return ctx->fail("cs_share_reference: the owner has no reference");
+  CsState* cs = cs_state(ctx, true);
+  cs->d_enc.borrow(from->d_enc);
+  cs->enc_bytes = from->enc_bytes;
+  cs->concat_len = from->concat_len;
+  cs->d_ref_starts.borrow(from->d_ref_starts);
+  cs->ref_starts = from->ref_starts;
+  if (from->index_len) {
+    cs->d_tab.borrow(from->d_tab);
+    cs->d_used.borrow(from->d_used);
+    cs->d_rci.borrow(from->d_rci);
+    cs->d_pos.borrow(from->d_pos);
+    cs->index_len = from->index_len;
+    cs->n_pos = from->n_pos;
+    cs->unit_offset = from->unit_offset;
+    cs->k = from->k;
+    cs->bin_shift = from->bin_shift;
+  }
+  return 0;
+}
+
 // Builds the k-mer index of the encoded reference that is resident on the device (cs_set_reference) and
 // installs it as the context's index: CompactPrefixTable::CreateTable on the GPU (cs_index_build.cu).
 int ngmlr_b200_cs_build_index(ngmlr_b200_ctx* ctx, const uint64_t* contig_start, const uint64_t* contig_len,

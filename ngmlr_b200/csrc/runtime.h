@@ -30,6 +30,11 @@ struct DevBuf {
   size_t cap = 0;  // elements
   cudaError_t reserve(size_t n, bool keep = false, cudaStream_t st = 0) {
     if (n <= cap) return cudaSuccess;
+    if (borrowed) {  // never grow (or free) somebody else's memory: start an own buffer
+      p = nullptr;
+      cap = 0;
+      borrowed = false;
+    }
     size_t want = std::max(n, cap + cap / 2);
     T* q = nullptr;
     cudaError_t e = cudaMalloc(&q, want * sizeof(T));
@@ -43,10 +48,18 @@ struct DevBuf {
     cap = want;
     return cudaSuccess;
   }
+  bool borrowed = false;  // the memory belongs to another buffer (reference / index shared between contexts)
   void release() {
-    if (p) cudaFree(p);
+    if (p && !borrowed) cudaFree(p);
     p = nullptr;
     cap = 0;
+    borrowed = false;
+  }
+  void borrow(const DevBuf& o) {
+    release();
+    p = o.p;
+    cap = o.cap;
+    borrowed = p != nullptr;
   }
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;

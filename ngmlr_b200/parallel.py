@@ -1,11 +1,13 @@
 """Multi-GPU plumbing of the hot path: one process per GPU, reads sharded by rank, the packed
 reference distributed ONCE at start-up, no per-step collective.
 
-`broadcast_reference` ships what every rank needs to run stage 0/2 and stage 4 -- the 4-bit encoded
-genome (`binRef`), the k-mer index arrays of CompactPrefixTable and, for synthetic benchmarks, the
-flat genome the reads are simulated from -- as ONE packed buffer in ONE NCCL broadcast (plus a
-64-byte header so that the receivers can size it). torch.distributed is the plumbing; the payload
-layout is the reference's own in-memory format (ngmlr_b200.refindex).
+`broadcast_reference` ships the 4-bit encoded, spacer-padded genome (`binRef`, 0.5 byte per base) with its
+contig table as ONE buffer in ONE NCCL broadcast (plus a 64-byte-aligned header so that the receivers
+can size it). Everything else a rank needs is derived locally from it: the k-mer index is built on the
+rank's own GPU (B200Aligner.build_index: CompactPrefixTable::CreateTable as scans + one radix sort, a
+fraction of a second for 50 Mb), and synthetic benchmarks decode the flat genome they simulate reads from
+(refindex.decode_contigs). torch.distributed is the plumbing; the payload layout is the reference's own
+in-memory format (ngmlr_b200.refindex).
 """
 import numpy as np
 
@@ -16,9 +18,9 @@ def shard(n_items, rank, world):
     return range(rank, n_items, world)
 
 
-def broadcast_reference(genome, enc_ref, kidx, src=0, device=None):
-    """-> (genome, EncodedReference, KmerIndex) on every rank. On `src` the arguments are the built
-    reference; elsewhere they are ignored (pass None)."""
+def broadcast_reference(enc_ref, src=0, device=None):
+    """-> EncodedReference on every rank. On `src` the argument is the encoded reference; elsewhere it is
+    ignored (pass None)."""
     import torch
     import torch.distributed as dist
     from . import refindex
@@ -27,32 +29,19 @@ def broadcast_reference(genome, enc_ref, kidx, src=0, device=None):
     if rank == src:
         nc = len(enc_ref.ref_start)
         assert nc <= 64
-        parts = [np.ascontiguousarray(genome).view(np.uint8), np.ascontiguousarray(enc_ref.enc).view(np.uint8),
-                 np.ascontiguousarray(kidx.tab).view(np.uint8), np.ascontiguousarray(kidx.rci).view(np.uint8),
-                 np.ascontiguousarray(kidx.pos).view(np.uint8)]
-        meta = [p.size for p in parts] + [enc_ref.concat_len, nc, (kidx.k << 8) | kidx.bin_shift]
+        payload = np.ascontiguousarray(enc_ref.enc).view(np.uint8)
+        meta = [payload.size, enc_ref.concat_len, nc, 0, 0, 0, 0, 0]
         meta += list(enc_ref.ref_start) + [0] * (64 - nc) + list(enc_ref.ref_len) + [0] * (64 - nc)
         hdr.copy_(torch.tensor(meta, dtype=torch.int64))
     dist.broadcast(hdr, src=src)
     m = [int(x) for x in hdr.cpu()]
-    sizes, concat_len, nc, kb = m[:5], m[5], m[6], m[7]
-    total = sum(sizes)
-    buf = torch.empty(total, dtype=torch.uint8, device=device)
+    size, concat_len, nc = m[0], m[1], m[2]
+    buf = torch.empty(size, dtype=torch.uint8, device=device)
     if rank == src:
-        at = 0
-        for p in parts:
-            buf[at:at + p.size].copy_(torch.from_numpy(p))
-            at += p.size
-    dist.broadcast(buf, src=src)          # the one collective of the run
+        buf.copy_(torch.from_numpy(payload))
+    dist.broadcast(buf, src=src)          # the one collective of the run: the packed reference
     if rank == src:
-        return genome, enc_ref, kidx
+        return enc_ref
     host = buf.cpu().numpy()
     del buf
-    at = 0
-    arrs = []
-    for sz in sizes:
-        arrs.append(host[at:at + sz])
-        at += sz
-    enc = refindex.EncodedReference(arrs[1], concat_len, m[8:8 + nc], m[8 + 64:8 + 64 + nc])
-    idx = refindex.KmerIndex(kb >> 8, kb & 0xff, arrs[2].view(np.uint32), arrs[3].view(np.int8), arrs[4].view(np.uint32))
-    return arrs[0], enc, idx
+    return refindex.EncodedReference(host, concat_len, m[8:8 + nc], m[8 + 64:8 + 64 + nc])

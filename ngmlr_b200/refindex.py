@@ -57,6 +57,12 @@ def encode_reference(contigs):
     return EncodedReference(enc, int(enc.size) * 2 - 1, starts, lens)
 
 
+def decode_contigs(ref: EncodedReference):
+    """The contigs of an encoded reference as characters (A C G T N), e.g. to simulate reads from a
+    reference that arrived packed (parallel.broadcast_reference)."""
+    return [DEC4[np.minimum(ref.base_codes(s, n), 4)] for s, n in zip(ref.ref_start, ref.ref_len)]
+
+
 def _revcomp_codes(prefix, k):
     """revComp of src/PrefixTable.cpp:70-88 for the CS k-mer code (A0 C1 T2 G3)."""
     mask = (1 << (2 * k)) - 1

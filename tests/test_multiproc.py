@@ -1,6 +1,6 @@
 """world_size-2 CPU (gloo) test of the multi-rank host logic bench.py uses: the reference is
-broadcast once from rank 0 as one packed buffer (ngmlr_b200.parallel.broadcast_reference: flat genome,
-4-bit encoding, k-mer index arrays -- every rank ends up with identical arrays), reads are sharded by
+broadcast once from rank 0 as one packed buffer (ngmlr_b200.parallel.broadcast_reference: the 4-bit
+encoding with its contig table; every rank decodes the identical flat genome from it), reads are sharded by
 rank (rank-seeded pools, no overlap, no per-step collective), timings are max-reduced and totals
 sum-reduced."""
 import os
@@ -18,13 +18,15 @@ WORKER = textwrap.dedent('''
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     n, n_contigs = 200_000, 2
-    genome = enc = idx = None
+    genome = enc = None
     if rank == 0:
         genome = synth.random_genome(n, 1)
         enc = refindex.encode_reference([genome[:n // 2], genome[n // 2:]])
-        idx = refindex.build_index(enc)
-    # the one start-up collective (+ its 64-byte header): the packed reference
-    genome, enc, idx = parallel.broadcast_reference(genome, enc, idx, src=0)
+    # the one start-up collective (+ its header): the packed reference; the flat genome is decoded from it
+    enc = parallel.broadcast_reference(enc, src=0)
+    decoded = np.concatenate(refindex.decode_contigs(enc))
+    assert genome is None or np.array_equal(genome, decoded)
+    genome = decoded
     reads, ivs = synth.simulate_reads(6, genome, n // 2, 2 + rank, median=1500)   # read sharding: own reads per rank
     tasks = synth.interval_tasks(ivs, reads, lambda pos: enc.ref_start[pos // (n // 2)] + pos % (n // 2))
     assert all(t.read_index == k for k, t in enumerate(tasks))
@@ -34,9 +36,8 @@ WORKER = textwrap.dedent('''
     tot = torch.tensor([float(bases)], dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    ref_sig = hashlib.sha256(genome.tobytes() + enc.enc.tobytes() + idx.tab.tobytes() + idx.rci.tobytes()
-                             + idx.pos.tobytes() + repr((enc.concat_len, enc.ref_start, enc.ref_len, idx.k,
-                                                         idx.bin_shift)).encode()).hexdigest()
+    ref_sig = hashlib.sha256(genome.tobytes() + enc.enc.tobytes()
+                             + repr((enc.concat_len, list(enc.ref_start), list(enc.ref_len))).encode()).hexdigest()
     sigs = [None] * world
     dist.all_gather_object(sigs, (sig, bases, ref_sig))
     assert list(parallel.shard(10, rank, world)) == list(range(rank, 10, world))
