@@ -357,6 +357,127 @@ def build_reference(args, cfg, rank, world, dev):
     return genome, contig_len, enc_ref, time.perf_counter() - t0
 
 
+def ialignment_batch_align(wl, ivs, gpu_results, steps, gpu_id):
+    """The same problems pushed through the reference's plugin surface itself: CreateAlignment(gpu_id) ->
+    IAlignment::BatchAlign through the vtable with host strings, CorridorLine arrays and caller-allocated
+    `Align` records (ngmlr_b200_plugin_time_batch_align builds them from flat arrays and times only the
+    BatchAlign calls). Full fidelity of the drop-in object: CIGAR / MD text AND the nmPerPosition array (12
+    bytes per alignment column) are written into the caller's buffers by host threads. Results are verified
+    against what the resident pipeline produced for the same intervals."""
+    import ctypes as C
+    from ngmlr_b200 import PackedBatch, _lib
+    lib = _lib.load()
+    lib.CreateAlignment.restype = C.c_void_p
+    lib.CreateAlignment.argtypes = [C.c_int]
+    lib.DeleteAlignment.argtypes = [C.c_void_p]
+    i32p, i64p = C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+    lib.ngmlr_b200_plugin_time_batch_align.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p),
+                                                       i32p, i32p, i64p, i32p, i32p, C.c_int, C.POINTER(C.c_double),
+                                                       i32p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    probs = [iv.problem(wl.genome, wl.reads) for iv in ivs]
+    pb = PackedBatch.from_problems(probs)
+    a = lib.CreateAlignment(gpu_id)
+    assert a, "CreateAlignment failed"
+    n = pb.n
+    rets = np.zeros(n, np.int32)
+    bits = np.zeros(n, np.uint32)
+    crc = np.zeros(n, np.uint32)
+    sec = C.c_double(0)
+    args = pb.c_args()
+    lib.ngmlr_b200_plugin_time_batch_align(a, n, args[1], args[3], args[5], args[6], args[7], args[8], args[9], 1,
+                                           C.byref(sec), rets.ctypes.data_as(i32p), bits.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                           crc.ctypes.data_as(C.POINTER(C.c_uint32)))   # warm-up (arenas, pinned buffers)
+    rc = lib.ngmlr_b200_plugin_time_batch_align(a, n, args[1], args[3], args[5], args[6], args[7], args[8], args[9], steps,
+                                                C.byref(sec), rets.ctypes.data_as(i32p),
+                                                bits.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                crc.ctypes.data_as(C.POINTER(C.c_uint32)))
+    lib.DeleteAlignment(a)
+    assert rc == 0, "IAlignment::BatchAlign threw"
+
+    def fnv(s):
+        c = 2166136261
+        for ch in s.encode():
+            c = ((c ^ ch) * 16777619) & 0xffffffff
+        return c
+
+    checked = 0
+    for i, g in enumerate(gpu_results):
+        d = g.as_dict()
+        if d["ret"] < 0:
+            assert rets[i] < 0
+            continue
+        assert int(bits[i]) == d["score_bits"] and int(crc[i]) == fnv(d["cigar"] + d["md"]), \
+            f"IAlignment::BatchAlign differs from the resident pipeline on interval {i}"
+        checked += 1
+    bases = sum(len(p.qry) for p in probs)
+    return {"value": bases * steps / sec.value / 1e9, "unit": "Gbp/s", "ms_per_batch": 1e3 * sec.value / steps,
+            "problems": n, "read_bases": bases, "verified_against_resident_pipeline": checked,
+            "note": "CreateAlignment -> IAlignment::BatchAlign (vtable), host strings + CorridorLine[] in, caller-owned "
+                    "Align buffers out incl. nmPerPosition; one aligner object, one batch in flight"}
+
+
+def integrated_run(wl_cfg, genome, contig_len, n_contigs, enc_ref, index, n_reads, cpu_threads, gpu_threads=128):
+    """The UNMODIFIED ngmlr end to end, twice on the same FASTQ: the plain binary (oracle/_ref/ngmlr, its own
+    ConvexAlignFast / StrippedSW on `cpu_threads` threads) and the same objects linked with the CUDA plugin
+    behind IAlignment (oracle/_ref/ngmlr_b200; every blocking SingleAlign of its `gpu_threads` worker threads
+    parked in the plugin's cross-thread batcher). Both start from the SAME on-disk caches -- written here from
+    the encoded reference and the k-mer index that was built on the GPU (ngmlr_b200.ngmfiles, byte-compatible
+    with ngmlr's own -enc.2.ngm / -ht-13-2.2.ngm), so neither run builds an index. SAM records must be
+    identical. Everything outside IAlignment (FASTQ parsing, CS vote, chaining, SV logic, SAM writing) is
+    the reference's own CPU code in both runs -- the integrated ratio is bounded by it (Amdahl)."""
+    import shutil
+    import tempfile
+    from ngmlr_b200 import ngmfiles, synth
+    plain = os.path.join(ROOT, "oracle", "_ref", "ngmlr")
+    swapped = os.path.join(ROOT, "oracle", "_ref", "ngmlr_b200")
+    if not (os.path.exists(plain) and os.path.exists(swapped)):
+        return {"unavailable": "oracle/_ref/ngmlr{,_b200} not built"}
+    d = tempfile.mkdtemp(prefix="ngmlr_b200_integrated_")
+    try:
+        ref = os.path.join(d, "ref.fa")
+        with open(ref, "w") as f:
+            for c in range(n_contigs):
+                s = genome[c * contig_len:(c + 1) * contig_len].tobytes().decode()
+                f.write(f">c{c}\n" + "\n".join(s[k:k + 80] for k in range(0, len(s), 80)) + "\n")
+        ngmfiles.write_encoded_reference(ref + "-enc.2.ngm", enc_ref, [f"c{c}" for c in range(n_contigs)])
+        ngmfiles.write_index(ref + "-ht-13-2.2.ngm", index, skip=2)
+        reads, _ = synth.simulate_reads(n_reads, genome, contig_len, 77, median=wl_cfg["median"], err=wl_cfg["err"],
+                                        ratio=wl_cfg["ratio"], sv=wl_cfg["sv"], hi=wl_cfg["hi"])
+        fq = os.path.join(d, "reads.fq")
+        bases = 0
+        with open(fq, "w") as f:
+            for i, r in enumerate(reads):
+                s = r.decode()
+                bases += len(s)
+                f.write(f"@r{i}\n{s}\n+\n{'I' * len(s)}\n")
+        out = {"reads": n_reads, "read_bases": bases}
+        sams = {}
+        for name, exe, t, extra in (("cpu", plain, cpu_threads, {}),
+                                    ("b200", swapped, gpu_threads, {"NGMLR_B200_BATCH_WINDOW_US": "200",
+                                                                     "NGMLR_B200_BATCH_MAX": "512",
+                                                                     "NGMLR_B200_HOST_THREADS": "4"})):
+            sam = os.path.join(d, name + ".sam")
+            env = dict(os.environ, NGMLR_B200_LIB=os.path.join(ROOT, "ngmlr_b200", "libngmlr_b200.so"), **extra)
+            t0 = time.perf_counter()
+            r = subprocess.run([exe, "-r", ref, "-q", fq, "-o", sam, "-t", str(t), "--no-progress"],
+                               capture_output=True, text=True, env=env, timeout=1800)
+            wall = time.perf_counter() - t0
+            if r.returncode != 0:
+                return {"unavailable": f"{name} run failed: {r.stderr[-300:]}"}
+            built = "Building reference index" in r.stderr or "Building reference index" in r.stdout
+            sams[name] = sorted(ln for ln in open(sam) if not ln.startswith("@"))
+            out[name] = {"threads": t, "wall_s": wall, "gbp_per_s": bases / wall / 1e9, "built_its_own_index": built,
+                         "env": extra}
+        out["sam_identical"] = sams["cpu"] == sams["b200"]
+        out["sam_records"] = len(sams["cpu"])
+        out["speedup"] = out["cpu"]["wall_s"] / out["b200"]["wall_s"]
+        out["note"] = ("whole unmodified ngmlr processes incl. start-up and cache loading; caches written from the "
+                       "GPU-built index (ngmfiles), identical for both")
+        return out
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -373,6 +494,9 @@ def main():
                          "roofline phase always runs at full occupancy)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     ap.add_argument("--parity-reads", type=int, default=0, help="reads compared CPU vs GPU (0 = the CPU sample)")
+    ap.add_argument("--integrated-reads", type=int, default=-1,
+                    help="reads of the whole-ngmlr comparison (plain binary vs plugin-linked binary); "
+                         "-1 = 2000 at N=1 on configs up to 100 Mb, else 0 (skipped)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
@@ -700,6 +824,23 @@ def main():
         except Exception as ex:  # the baseline is reported, never required for the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "Gbp/s", "cores": 0, "kind": "unavailable",
                                     "sample": repr(ex)}
+        try:   # the plugin surface itself, on the first context's slice of the batch
+            k_ = len(wl.ivs) if len(wl.ivs) <= 2048 else 2048
+            line["e2e_ialignment"] = ialignment_batch_align(wl, wl.ivs[:k_], gpu_first[:k_], max(2, args.steps // 2),
+                                                            local_rank)
+        except AssertionError:
+            raise
+        except Exception as ex:
+            line["e2e_ialignment"] = {"value": None, "note": repr(ex)}
+        n_int = args.integrated_reads
+        if n_int < 0:
+            n_int = 2000 if (world == 1 and args.genome_mb <= 100 and not args.dp_only) else 0
+        if n_int > 0:
+            try:
+                line["integrated"] = integrated_run(cfg, genome, contig_len, cfg["contigs"], enc_ref, al.get_index(),
+                                                    n_int, cores)
+            except Exception as ex:
+                line["integrated"] = {"unavailable": repr(ex)}
         print(json.dumps(line))
     for a_ in als:
         a_.close()

@@ -106,7 +106,8 @@ struct TeamBest {
 // -- a 10^8-cell realignment matrix would otherwise keep one 4-warp team busy long after the rest of the
 // grid has drained).
 template <bool RAW, int NW>
-__global__ void __launch_bounds__((NW == 1 ? FILL_WARPS_PER_CTA : NW) * 32, NW > FILL_WARPS_PER_CTA ? 1 : FILL_CTAS_PER_SM)
+__global__ void __launch_bounds__((NW == 1 ? FILL_WARPS_PER_CTA : NW) * 32,
+                                  NW > FILL_WARPS_PER_CTA ? 1 : (NW == 1 ? FILL_CTAS_PER_SM : FILL_TEAM_CTAS_PER_SM))
 convex_fill_kernel(const FillParams p) {
   constexpr int WARPS = NW == 1 ? FILL_WARPS_PER_CTA : NW;  // warps per CTA
   constexpr int CHUNK = NW == 1 ? 64 : FILL_TEAM_CHUNK;  // steps staged through shared memory at a time

@@ -8,6 +8,9 @@ namespace nb {
 
 constexpr int FILL_WARPS_PER_CTA = 4;
 constexpr int FILL_CTAS_PER_SM = 5;
+#ifndef FILL_TEAM_CTAS_PER_SM
+#define FILL_TEAM_CTAS_PER_SM 6  // the 4-warp team kernel needs 80 registers: 6 CTAs = 24 warps per SM
+#endif
 constexpr int FILL_BIG_TEAM = 16;  // warps that pipeline one huge matrix (one CTA per SM)
 
 // team = all FILL_WARPS_PER_CTA warps of a CTA pipeline one problem; otherwise one warp per problem

@@ -451,4 +451,75 @@ void SetAlignmentScoring(float match, float mismatch, float gapOpen, float gapEx
 
 int ngmlr_b200_plugin_cookie(void) { return 0x10201130; }  // cCookie, src/IAlignment.h:193
 
+// Benchmark / test aid for FFI callers that cannot build C++ objects (bench.py): n SingleAlign problems
+// given as flat arrays are turned into what ngmlr itself would hold -- caller-allocated `Align` records
+// (buffers sized like AlignmentBuffer::computeAlignment does, src/AlignmentBuffer.cpp:271-278) and
+// CorridorLine arrays -- and pushed `repeats` times through `aligner->BatchAlign(...)`, i.e. through the
+// IAlignment vtable, host buffers in, host buffers out. Only the BatchAlign calls are timed
+// (*seconds). rets[i] / score_bits[i] / cigar_crc[i] of the last repeat let the caller verify the results.
+int ngmlr_b200_plugin_time_batch_align(IAlignment* aligner, int n, char const* const* refs, char const* const* qrys,
+                                       const int32_t* corridor_offsets, const int32_t* corridor_lengths,
+                                       const int64_t* row_start, const int32_t* ext_qstart, const int32_t* ext_qend,
+                                       int repeats, double* seconds, int32_t* rets, uint32_t* score_bits,
+                                       uint32_t* cigar_crc) {
+  if (!aligner || n < 0) return -1;
+  std::vector<Align> aligns((size_t)n);
+  std::vector<std::vector<CorridorLine>> lines((size_t)n);
+  std::vector<NgmlrB200BatchAlignArgs> args((size_t)n);
+  for (int i = 0; i < n; ++i) {
+    const int h = (int)(row_start[i + 1] - row_start[i]);
+    lines[i].resize((size_t)h);
+    for (int y = 0; y < h; ++y) {
+      lines[i][y].offset = corridor_offsets[row_start[i] + y];
+      lines[i][y].length = corridor_lengths[row_start[i] + y];
+      lines[i][y].offsetInMatrix = 0;
+    }
+    args[i].corridor = lines[i].data();
+    args[i].corridorHeight = h;
+    args[i].externalQStart = ext_qstart ? ext_qstart[i] : 0;
+    args[i].externalQEnd = ext_qend ? ext_qend[i] : 0;
+    Align& a = aligns[i];
+    const int read_length = h;
+    a.maxBufferLength = read_length * 4 + 8;
+    a.maxMdBufferLength = read_length * 4 + 8;
+    a.pBuffer1 = new char[a.maxBufferLength];
+    a.pBuffer2 = new char[a.maxMdBufferLength];
+    a.pBuffer1[0] = a.pBuffer2[0] = '\0';
+    a.nmPerPostionLength = (read_length + 1) * 2;
+    a.nmPerPosition = new PositionNM[a.nmPerPostionLength];
+  }
+  double total = 0.0;
+  int rc = 0;
+  try {
+    for (int r = 0; r < repeats; ++r) {
+      const auto t0 = std::chrono::steady_clock::now();
+      aligner->BatchAlign(0, n, refs, qrys, aligns.data(), args.data());
+      total += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+  } catch (...) {
+    rc = -2;
+  }
+  for (int i = 0; i < n; ++i) {
+    Align& a = aligns[i];
+    const bool ok = a.Score != -1.0f;
+    if (rets) rets[i] = ok ? a.QStart + a.QEnd : -1;  // BatchAlign reports failure as Score == -1
+    if (score_bits) memcpy(score_bits + i, &a.Score, 4);
+    if (cigar_crc) {
+      uint32_t c = 2166136261u;  // FNV-1a over CIGAR + MD
+      if (ok) {
+        for (const char* q = a.pBuffer1; *q; ++q) c = (c ^ (uint8_t)*q) * 16777619u;
+        for (const char* q = a.pBuffer2; *q; ++q) c = (c ^ (uint8_t)*q) * 16777619u;
+      }
+      cigar_crc[i] = c;
+    }
+    delete[] a.pBuffer1;
+    delete[] a.pBuffer2;
+    delete[] a.nmPerPosition;
+    a.pBuffer1 = a.pBuffer2 = nullptr;
+    a.nmPerPosition = nullptr;
+  }
+  if (seconds) *seconds = total;
+  return rc;
+}
+
 }  // extern "C"
