@@ -416,7 +416,7 @@ def ialignment_batch_align(wl, ivs, gpu_results, steps, gpu_id):
                     "Align buffers out incl. nmPerPosition; one aligner object, one batch in flight"}
 
 
-def integrated_run(wl_cfg, genome, contig_len, n_contigs, enc_ref, index, n_reads, cpu_threads, gpu_threads=128):
+def integrated_run(wl_cfg, genome, contig_len, n_contigs, enc_ref, index, n_reads, cpu_threads, gpu_threads=96):
     """The UNMODIFIED ngmlr end to end, twice on the same FASTQ: the plain binary (oracle/_ref/ngmlr, its own
     ConvexAlignFast / StrippedSW on `cpu_threads` threads) and the same objects linked with the CUDA plugin
     behind IAlignment (oracle/_ref/ngmlr_b200; every blocking SingleAlign of its `gpu_threads` worker threads
@@ -455,7 +455,9 @@ def integrated_run(wl_cfg, genome, contig_len, n_contigs, enc_ref, index, n_read
         for name, exe, t, extra in (("cpu", plain, cpu_threads, {}),
                                     ("b200", swapped, gpu_threads, {"NGMLR_B200_BATCH_WINDOW_US": "200",
                                                                      "NGMLR_B200_BATCH_MAX": "512",
-                                                                     "NGMLR_B200_HOST_THREADS": "4"})):
+                                                                     "NGMLR_B200_BATCH_SERVERS": "2",
+                                                                     "NGMLR_B200_HOST_THREADS": "4",
+                                                                     "NGMLR_B200_STATS": "1"})):
             sam = os.path.join(d, name + ".sam")
             env = dict(os.environ, NGMLR_B200_LIB=os.path.join(ROOT, "ngmlr_b200", "libngmlr_b200.so"), **extra)
             t0 = time.perf_counter()
@@ -466,8 +468,9 @@ def integrated_run(wl_cfg, genome, contig_len, n_contigs, enc_ref, index, n_read
                 return {"unavailable": f"{name} run failed: {r.stderr[-300:]}"}
             built = "Building reference index" in r.stderr or "Building reference index" in r.stdout
             sams[name] = sorted(ln for ln in open(sam) if not ln.startswith("@"))
+            stats = [ln for ln in r.stderr.splitlines() if ln.startswith("[ngmlr_b200]")]
             out[name] = {"threads": t, "wall_s": wall, "gbp_per_s": bases / wall / 1e9, "built_its_own_index": built,
-                         "env": extra}
+                         "env": extra, "plugin_stats": stats[-1] if stats else None}
         out["sam_identical"] = sams["cpu"] == sams["b200"]
         out["sam_records"] = len(sams["cpu"])
         out["speedup"] = out["cpu"]["wall_s"] / out["b200"]["wall_s"]

@@ -9,9 +9,11 @@
 //     SingleScore (StrippedSW, src/StrippedSW.cpp:118-202); GetScoreBatchSize() = 1024 like
 //     StrippedSW.h:53-55.
 // Argument meaning, buffer ownership and error behaviour follow SURVEY.md section 8(b).
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <mutex>
@@ -37,6 +39,22 @@ struct ParkedContext {
 std::mutex g_pool_mutex;
 std::vector<ParkedContext> g_pool;
 
+// Counters of the cross-thread batchers, printed at exit with NGMLR_B200_STATS=1.
+struct PluginStats {
+  std::atomic<long long> align_calls{0}, align_batches{0}, align_problems{0}, align_batch_us{0};
+  std::atomic<long long> score_calls{0}, score_batches{0}, score_pairs{0};
+  ~PluginStats() {
+    if (!getenv("NGMLR_B200_STATS")) return;
+    fprintf(stderr,
+            "[ngmlr_b200] SingleAlign calls %lld in %lld batches (%.1f per batch, %.2f ms per batch); "
+            "BatchScore/SingleScore calls %lld in %lld launches (%.0f pairs per launch)\n",
+            align_calls.load(), align_batches.load(),
+            align_batches ? (double)align_problems / (double)align_batches : 0.0,
+            align_batches ? 1e-3 * (double)align_batch_us / (double)align_batches : 0.0, score_calls.load(),
+            score_batches.load(), score_batches ? (double)score_pairs / (double)score_batches : 0.0);
+  }
+} g_stats;
+
 bool same_scoring(const ngmlr_b200_scoring& a, const ngmlr_b200_scoring& b) {
   return memcmp(&a, &b, sizeof(a)) == 0;
 }
@@ -53,6 +71,8 @@ struct AlignRequest {
   std::string error;  // owned by the request: the next batch cannot overwrite what a client is still throwing
 };
 class B200Alignment;
+bool score_batcher_submit(int gpu_id, const ngmlr_b200_scoring& scoring, int n, char const* const* refs,
+                          char const* const* qrys, float* results);
 // what a thrown `const char*` points at must outlive the throw: one string per calling thread
 std::string& thread_error() {
   static thread_local std::string e;
@@ -67,17 +87,28 @@ class B200Alignment : public IAlignment {
       const long v = atol(e);
       if (v > 0) max_matrix_mb_ = (unsigned long)v;
     }
+    // fail loudly at construction when there is no usable device; the context itself (stream, events, device
+    // and pinned arenas) is made on first direct use -- with the cross-thread batchers on, ngmlr's hundreds of
+    // per-thread aligner objects never need one of their own
+    device_ok_ = gpu_id >= 0 && gpu_id < ngmlr_b200_device_count();
+  }
+  ngmlr_b200_ctx* ctx() {
+    if (ctx_) return ctx_;
     {
       std::lock_guard<std::mutex> lock(g_pool_mutex);
       for (size_t i = 0; i < g_pool.size(); ++i) {
-        if (g_pool[i].gpu_id == gpu_id && same_scoring(g_pool[i].scoring, scoring_)) {
+        if (g_pool[i].gpu_id == gpu_id_ && same_scoring(g_pool[i].scoring, scoring_)) {
           ctx_ = g_pool[i].ctx;
           g_pool.erase(g_pool.begin() + i);
-          return;
+          return ctx_;
         }
       }
     }
-    if (ngmlr_b200_create(gpu_id, &scoring_, &ctx_) != 0) ctx_ = nullptr;
+    if (ngmlr_b200_create(gpu_id_, &scoring_, &ctx_) != 0) {
+      ctx_ = nullptr;
+      throw "ngmlr_b200: cannot create a device context (no CUDA device? there is no CPU fallback)";
+    }
+    return ctx_;
   }
   ~B200Alignment() override {
     if (!ctx_) return;
@@ -89,7 +120,7 @@ class B200Alignment : public IAlignment {
       ngmlr_b200_destroy(ctx_);
     }
   }
-  bool ok() const { return ctx_ != nullptr; }
+  bool ok() const { return device_ok_; }
 
   int GetScoreBatchSize() const override { return 1024; }
   int GetAlignBatchSize() const override { return 1024; }
@@ -97,7 +128,11 @@ class B200Alignment : public IAlignment {
   int BatchScore(int const, int const batchSize, char const* const* const refSeqList,
                  char const* const* const qrySeqList, float* const results, void*) override {
     if (batchSize <= 0) return 0;
-    int rc = ngmlr_b200_sw_score_batch(ctx_, batchSize, refSeqList, qrySeqList, results);
+    if (score_batcher_submit(gpu_id_, scoring_, batchSize, refSeqList, qrySeqList, results)) return batchSize;
+    return score_direct(batchSize, refSeqList, qrySeqList, results);
+  }
+  int score_direct(int n, char const* const* refs, char const* const* qrys, float* results) {
+    int rc = ngmlr_b200_sw_score_batch(ctx(), n, refs, qrys, results);
     if (rc < 0) throw ngmlr_b200_last_error(ctx_);
     return rc;
   }
@@ -105,8 +140,7 @@ class B200Alignment : public IAlignment {
   int SingleScore(int const, int const, char const* const refSeq, char const* const qrySeq,
                   float& result, void*) override {
     float r = -1.0f;
-    int rc = ngmlr_b200_sw_score_batch(ctx_, 1, &refSeq, &qrySeq, &r);
-    if (rc < 0) throw ngmlr_b200_last_error(ctx_);
+    if (!score_batcher_submit(gpu_id_, scoring_, 1, &refSeq, &qrySeq, &r)) score_direct(1, &refSeq, &qrySeq, &r);
     result = r;
     return r == -1.0f ? 0 : 1;  // StrippedSW::SingleScore returns 0 for over-long input (:175-178)
   }
@@ -126,6 +160,7 @@ class B200Alignment : public IAlignment {
       req.qry = qrySeq;
       req.result = &result;
       req.args = a;
+      g_stats.align_calls++;
       if (batcher_submit(gpu_id_, scoring_, req)) {  // false: batching is off -> direct path below
         if (req.failed) {
           thread_error() = req.error;
@@ -223,7 +258,7 @@ class B200Alignment : public IAlignment {
       if (threw_out) threw_out[i] = false;
     }
     if (m > 0) {
-      int rc = ngmlr_b200_convex_align_batch(ctx_, m, krefs_.data(), krl_.data(), kqrys_.data(), kql_.data(),
+      int rc = ngmlr_b200_convex_align_batch(ctx(), m, krefs_.data(), krl_.data(), kqrys_.data(), kql_.data(),
                                              off_.data(), len_.data(), row_start_.data(), kqs_.data(),
                                              kqe_.data(), res_.data());
       if (rc != 0) {
@@ -294,6 +329,7 @@ class B200Alignment : public IAlignment {
 
  private:
   int gpu_id_ = 0;
+  bool device_ok_ = false;
   ngmlr_b200_scoring scoring_;
   ngmlr_b200_ctx* ctx_ = nullptr;
   unsigned long max_matrix_mb_ = 10000ul;  // Config.getMaxMatrixSizeMB() default (src/IConfig.h)
@@ -363,6 +399,9 @@ class Batcher {
       }
       bool failed = false;
       std::string error;
+      const auto t_b0 = std::chrono::steady_clock::now();
+      g_stats.align_batches++;
+      g_stats.align_problems += n;
       try {
         server_->align_many(n, refs.data(), qrys.data(), results.data(), args.data(), rets.data(),
                             reinterpret_cast<bool*>(threw.data()));
@@ -373,6 +412,8 @@ class Batcher {
         failed = true;
         error = "batched alignment failed";
       }
+      g_stats.align_batch_us += std::chrono::duration_cast<std::chrono::microseconds>(
+                                    std::chrono::steady_clock::now() - t_b0).count();
       {
         std::lock_guard<std::mutex> lk(m_);
         for (int i = 0; i < n; ++i) {
@@ -397,24 +438,159 @@ class Batcher {
   std::vector<AlignRequest*> queue_;
 };
 
-bool batcher_submit(int gpu_id, const ngmlr_b200_scoring& scoring, AlignRequest& r) {
-  static const int window_us = [] {
+int batch_window_us() {
+  static const int v = [] {
     const char* e = getenv("NGMLR_B200_BATCH_WINDOW_US");
     return e ? atoi(e) : 0;
   }();
+  return v;
+}
+
+int batch_servers() {  // dispatcher threads (each with its own context) that take batches in turn
+  static const int v = [] {
+    const char* e = getenv("NGMLR_B200_BATCH_SERVERS");
+    const int n = e ? atoi(e) : 2;
+    return n < 1 ? 1 : (n > 8 ? 8 : n);
+  }();
+  return v;
+}
+
+bool batcher_submit(int gpu_id, const ngmlr_b200_scoring& scoring, AlignRequest& r) {
+  const int window_us = batch_window_us();
   if (window_us <= 0) return false;
   static std::mutex create_mutex;
-  static Batcher* batcher = nullptr;  // leaked on purpose (see the detach above)
+  static std::vector<Batcher*> batchers;  // leaked on purpose (see the detach above)
+  static std::atomic<unsigned> next(0);
   {
     std::lock_guard<std::mutex> lk(create_mutex);
-    if (!batcher) {
+    if (batchers.empty()) {
       const char* e = getenv("NGMLR_B200_BATCH_MAX");
       const int mx = e && atoi(e) > 0 ? atoi(e) : 256;
-      batcher = new Batcher(gpu_id, scoring, window_us, mx);
+      for (int i = 0; i < batch_servers(); ++i) batchers.push_back(new Batcher(gpu_id, scoring, window_us, mx));
     }
   }
-  if (!batcher->usable(gpu_id, scoring)) return false;
-  batcher->submit(r);
+  Batcher* b = batchers[next.fetch_add(1) % batchers.size()];
+  if (!b->usable(gpu_id, scoring)) return false;
+  b->submit(r);
+  return true;
+}
+
+// ---- the same for BatchScore / SingleScore ------------------------------------------------------
+// ScoreBuffer calls BatchScore once per read with a few dozen (window, sub-read) pairs, every thread on its
+// own; here the calls of all threads that arrive within the window become ONE scoring launch.
+struct ScoreRequest {
+  int n;
+  char const* const* refs;
+  char const* const* qrys;
+  float* results;
+  bool done = false, failed = false;
+  std::string error;
+};
+
+class ScoreBatcher {
+ public:
+  ScoreBatcher(int gpu_id, const ngmlr_b200_scoring& sc, int window_us, int max_pairs)
+      : gpu_id_(gpu_id), window_us_(window_us), max_pairs_(max_pairs) {
+    server_ = new B200Alignment(gpu_id, sc);
+    if (server_->ok()) {
+      worker_ = std::thread([this] { loop(); });
+      worker_.detach();
+    }
+  }
+  bool usable(int gpu_id) const { return server_->ok() && gpu_id == gpu_id_; }
+  void submit(ScoreRequest& r) {
+    std::unique_lock<std::mutex> lk(m_);
+    queue_.push_back(&r);
+    pending_pairs_ += r.n;
+    cv_work_.notify_one();
+    cv_done_.wait(lk, [&] { return r.done; });
+  }
+
+ private:
+  void loop() {
+    std::vector<ScoreRequest*> batch;
+    std::vector<char const*> refs, qrys;
+    std::vector<float> out;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_work_.wait(lk, [&] { return !queue_.empty(); });
+        const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(window_us_);
+        while (pending_pairs_ < max_pairs_ && cv_work_.wait_until(lk, deadline) != std::cv_status::timeout) {
+        }
+        batch.swap(queue_);
+        queue_.clear();
+        pending_pairs_ = 0;
+      }
+      refs.clear();
+      qrys.clear();
+      for (ScoreRequest* r : batch) {
+        refs.insert(refs.end(), r->refs, r->refs + r->n);
+        qrys.insert(qrys.end(), r->qrys, r->qrys + r->n);
+      }
+      out.assign(refs.size(), -1.0f);
+      bool failed = false;
+      std::string error;
+      try {
+        server_->score_direct((int)refs.size(), refs.data(), qrys.data(), out.data());
+      } catch (const char* e) {
+        failed = true;
+        error = e ? e : "batched scoring failed";
+      } catch (...) {
+        failed = true;
+        error = "batched scoring failed";
+      }
+      g_stats.score_batches++;
+      g_stats.score_pairs += (long long)refs.size();
+      {
+        std::lock_guard<std::mutex> lk(m_);
+        size_t at = 0;
+        for (ScoreRequest* r : batch) {
+          if (!failed) memcpy(r->results, out.data() + at, (size_t)r->n * sizeof(float));
+          at += (size_t)r->n;
+          r->failed = failed;
+          r->error = error;
+          r->done = true;
+        }
+      }
+      batch.clear();
+      cv_done_.notify_all();
+    }
+  }
+  int gpu_id_, window_us_, max_pairs_;
+  long long pending_pairs_ = 0;
+  B200Alignment* server_ = nullptr;
+  std::thread worker_;
+  std::mutex m_;
+  std::condition_variable cv_work_, cv_done_;
+  std::vector<ScoreRequest*> queue_;
+};
+
+bool score_batcher_submit(int gpu_id, const ngmlr_b200_scoring& scoring, int n, char const* const* refs,
+                          char const* const* qrys, float* results) {
+  const int window_us = batch_window_us();
+  if (window_us <= 0) return false;
+  static std::mutex create_mutex;
+  static std::vector<ScoreBatcher*> batchers;
+  static std::atomic<unsigned> next(0);
+  {
+    std::lock_guard<std::mutex> lk(create_mutex);
+    if (batchers.empty())
+      for (int i = 0; i < batch_servers(); ++i) batchers.push_back(new ScoreBatcher(gpu_id, scoring, window_us, 65536));
+  }
+  ScoreBatcher* b = batchers[next.fetch_add(1) % batchers.size()];
+  if (!b->usable(gpu_id)) return false;
+  ScoreRequest r;
+  r.n = n;
+  r.refs = refs;
+  r.qrys = qrys;
+  r.results = results;
+  g_stats.score_calls++;
+  b->submit(r);
+  if (r.failed) {
+    thread_error() = r.error;
+    throw thread_error().c_str();
+  }
   return true;
 }
 
