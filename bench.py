@@ -470,7 +470,7 @@ def integrated_run(wl_cfg, genome, contig_len, n_contigs, enc_ref, index, n_read
             sams[name] = sorted(ln for ln in open(sam) if not ln.startswith("@"))
             stats = [ln for ln in r.stderr.splitlines() if ln.startswith("[ngmlr_b200]")]
             out[name] = {"threads": t, "wall_s": wall, "gbp_per_s": bases / wall / 1e9, "built_its_own_index": built,
-                         "env": extra, "plugin_stats": stats[-1] if stats else None}
+                         "env": extra, "plugin_stats": stats or None}
         out["sam_identical"] = sams["cpu"] == sams["b200"]
         out["sam_records"] = len(sams["cpu"])
         out["speedup"] = out["cpu"]["wall_s"] / out["b200"]["wall_s"]
@@ -497,6 +497,8 @@ def main():
                          "roofline phase always runs at full occupancy)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     ap.add_argument("--parity-reads", type=int, default=0, help="reads compared CPU vs GPU (0 = the CPU sample)")
+    ap.add_argument("--integrated-only", action="store_true", help="run only the whole-ngmlr comparison")
+    ap.add_argument("--integrated-threads", type=int, default=96, help="worker threads of the plugin-linked ngmlr")
     ap.add_argument("--integrated-reads", type=int, default=-1,
                     help="reads of the whole-ngmlr comparison (plain binary vs plugin-linked binary); "
                          "-1 = 2000 at N=1 on configs up to 100 Mb, else 0 (skipped)")
@@ -569,6 +571,14 @@ def main():
     genome, contig_len, enc_ref, t_ref = build_reference(args, cfg, rank, world, dev)
 
     from ngmlr_b200 import B200Aligner, IntervalBatch, PackedReads
+    if args.integrated_only:
+        a0 = B200Aligner(local_rank)
+        a0.set_reference(enc_ref)
+        a0.build_index(enc_ref)
+        print(json.dumps(integrated_run(cfg, genome, contig_len, cfg["contigs"], enc_ref, a0.get_index(),
+                                        max(args.integrated_reads, 500), cores, args.integrated_threads)))
+        a0.close()
+        return
     wl = Workload(genome, contig_len, enc_ref, args.reads, 2 + rank, cfg)   # reads sharded by rank: own reads per rank
     bases = wl.bases
     all_reads = PackedReads(wl.reads)
@@ -841,7 +851,7 @@ def main():
         if n_int > 0:
             try:
                 line["integrated"] = integrated_run(cfg, genome, contig_len, cfg["contigs"], enc_ref, al.get_index(),
-                                                    n_int, cores)
+                                                    n_int, cores, args.integrated_threads)
             except Exception as ex:
                 line["integrated"] = {"unavailable": repr(ex)}
         print(json.dumps(line))

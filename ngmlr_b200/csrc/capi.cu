@@ -645,13 +645,14 @@ int ngmlr_b200_cs_search_batch(ngmlr_b200_ctx* ctx, int n, const char* const* se
         return ctx->fail("cs_search_batch: (sub-)read %d has %llu k-mer hits; split the read (ReadProvider::splitRead)",
                          last, hits[last]);
       const uint32_t cap = (uint32_t)cap64;
-      const size_t need = (size_t)cap * 16 + (size_t)hits[last] * 4 + (size_t)hits[last] * 2 * 16;
+      const size_t arena_cap = cap > CS_SMEM_CAP ? cap : 0;  // small tables live in shared memory
+      const size_t need = arena_cap * 16 + (size_t)hits[last] * 4 + (size_t)hits[last] * 2 * 16;
       if (last > first && (tent * 16 + oent * 4 + rent * 16 + need) > budget) break;
       caps[last] = cap;
       toff[last] = tent;
       ooff[last] = oent;
       roff[last] = rent;
-      tent += cap;
+      tent += arena_cap;
       oent += (size_t)hits[last];
       rent += (size_t)hits[last] * 2;
       ++last;

@@ -25,7 +25,7 @@ __global__ void cs_sizes_kernel(const unsigned long long* __restrict__ hits, int
   unsigned long long cp = 16;  // 64-bit: a table of 2^31 entries and more is refused by the host (totals check)
   while (cp < 2 * h + 2) cp <<= 1;
   cap[i] = cp > 0x80000000ull ? 0x80000000u : (uint32_t)cp;
-  a[i] = cp;      // vote table entries
+  a[i] = cap[i] > CS_SMEM_CAP ? cp : 0ull;  // vote table entries in the arena (small tables live in shared memory)
   b[i] = h;       // order list entries
   c[i] = 2 * h;   // candidate slots (forward + reverse per listed bin)
 }

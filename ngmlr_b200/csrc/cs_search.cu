@@ -32,15 +32,35 @@ __device__ __forceinline__ uint32_t rev_comp(uint32_t prefix, int k, uint32_t ma
   return c >> (32 - 2 * k);
 }
 
-struct VoteEntry {
+struct alignas(16) VoteEntry {
   uint32_t key;    // bin = (loc - correction) >> bin_shift   (CSTableEntry::m_Location is a uint)
   uint32_t state;  // bit 0: used, bit 1: already listed
   float f, r;
 };
 
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int CS_WARPS = 4;
+
+__device__ __forceinline__ unsigned lowmask(int n) { return n >= 32 ? 0xffffffffu : ((1u << n) - 1u); }
+
+// One WARP per (sub-)read. The reference's vote is order dependent (the acceptance threshold 0.8 x
+// max-so-far runs along with the hits, candidates are emitted in the order in which their bin first
+// crossed it), but only through three quantities that have closed forms over the canonical hit sequence:
+//   score of hit j          = 1 + number of earlier hits with the same (bin, strand)
+//   max-so-far at hit j     = prefix maximum of the scores
+//   bin b is listed at      = its first hit (either strand) whose score >= 0.8 x max-so-far
+// So the warp replays the hits 32 AT A TIME in canonical order (lane = hit): equal bins of a batch are
+// grouped with __match_any_sync (the group's leader finds / inserts the table entry, everybody derives its
+// own score from the entry's old counts and its rank within the group), the running maximum is a warp
+// max-scan, listing is a ballot. 32 k-mer lookups, 32 position reads and up to 32 table probes are in
+// flight per warp instead of one dependent chain per sub-read -- the kernel was bound by exactly that
+// latency (one thread per sub-read: issue slots 17 %, 5.3 ms per 299 k sub-reads; 7 300 hits per sub-read
+// on a human-sized index). Small vote tables (<= CS_SMEM_CAP entries) live in shared memory.
 template <bool COUNT_ONLY>
-__global__ void __launch_bounds__(128) cs_search_kernel(const CsParams p) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(CS_WARPS * 32) cs_search_kernel(const CsParams p) {
+  __shared__ VoteEntry s_tab[COUNT_ONLY ? 1 : CS_WARPS][COUNT_ONLY ? 1 : CS_SMEM_CAP];  // 32 KB per CTA
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int i = blockIdx.x * CS_WARPS + wib;
   if (i >= p.n) return;
   const uint8_t* __restrict__ seq = p.seq + p.seq_off[i];
   const int len = p.seq_len[i];
@@ -54,130 +74,192 @@ __global__ void __launch_bounds__(128) cs_search_kernel(const CsParams p) {
   float max_hits = 0.0f, thresh = 0.0f;
   unsigned long long hits = 0;
   if (!COUNT_ONLY) {
-    tab = reinterpret_cast<VoteEntry*>(p.tables) + p.table_off[i];
-    cap_mask = p.table_cap[i] - 1u;
+    const uint32_t cap = p.table_cap[i];
+    cap_mask = cap - 1u;
+    if (cap <= CS_SMEM_CAP) {
+      tab = s_tab[wib];
+      uint4* z = reinterpret_cast<uint4*>(tab);
+      for (uint32_t j = lane; j < cap; j += 32) z[j] = make_uint4(0u, 0u, 0u, 0u);
+      __syncwarp();
+    } else {
+      tab = reinterpret_cast<VoteEntry*>(p.tables) + p.table_off[i];
+    }
     order = p.order + p.order_off[i];
   }
 
-  auto vote = [&](uint32_t bin, bool reverse) {
-    uint32_t s = (bin * 2654435761u) >> 7;
-    s &= cap_mask;
-    while ((tab[s].state & 1u) && tab[s].key != bin) s = (s + 1u) & cap_mask;
-    VoteEntry e = tab[s];
-    float score;
-    if (!(e.state & 1u)) {
-      e.key = bin;
-      e.state = 1u;
-      e.f = reverse ? 0.0f : 1.0f;
-      e.r = reverse ? 1.0f : 0.0f;
-      score = 1.0f;
-    } else if (reverse) {
-      e.r += 1.0f;
-      score = e.r;
-    } else {
-      e.f += 1.0f;
-      score = e.f;
+  // CS::PrefixIteration with prefixskip = 0 (src/CSstatic.cpp:23-73): a callback for every N-free window of
+  // k characters, in order; the walk ends early when an N-run (reached through the N-skipping branch: it
+  // starts the sequence or is at least two long) leaves no more than k characters (:38-41) -- which drops
+  // exactly one window, the last one, when it starts right behind such a run.
+  const int n_win = len - k + 1;
+  for (int c0 = 0; c0 < n_win; c0 += 32) {
+    const int pos = c0 + lane;  // read offset of this lane's k-mer
+    uint32_t prefix = 0;
+    bool ok = pos < n_win;
+    if (ok) {
+      for (int j = 0; j < k; ++j) {
+        const uint32_t ch = seq[pos + j];
+        if (ch == 'N') ok = false;
+        prefix = (prefix << 2) | ((ch >> 1) & 3u);
+      }
+      prefix &= mask;
+      if (ok && pos + k == len && pos >= 1 && seq[pos - 1] == 'N') {
+        // is the N-run in front of the window two long, or does it start the sequence?
+        int q = pos - 1;
+        while (q > 0 && seq[q - 1] == 'N') --q;
+        if (q == 0 || pos - q >= 2) ok = false;
+      }
     }
-    if (score > max_hits) {  // (:136-141)
-      max_hits = score;
-      thresh = __fmul_rn(max_hits, p.sensitivity);
+    // ---- CompactPrefixTable::GetRefEntry: forward list, then the list of the reverse-complement k-mer ----
+    uint32_t fs = 0, fn = 0, rs = 0, rn = 0;
+    if (ok) {
+      if ((p.used_bits[prefix >> 5] >> (prefix & 31u)) & 1u) {
+        fs = p.tab[prefix] - 1u;
+        fn = p.tab[prefix + 1] - 1u - fs;
+      }
+      const uint32_t rc = rev_comp(prefix, k, mask);
+      if ((p.used_bits[rc >> 5] >> (rc & 31u)) & 1u) {
+        rs = p.tab[rc] - 1u;
+        rn = p.tab[rc + 1] - 1u - rs;
+      }
     }
-    if (!(e.state & 2u) && score >= thresh) {  // (:143-147)
-      e.state |= 2u;
-      order[n_order++] = s;
+    if (COUNT_ONLY) {
+      hits += fn + rn;
+      continue;
     }
-    tab[s] = e;
-  };
-
-  auto kmer = [&](uint32_t prefix, int pos) {
-    // forward list, then the list of the reverse-complement k-mer (GetRefEntry)
-    if ((p.used_bits[prefix >> 5] >> (prefix & 31u)) & 1u) {
-      const uint32_t start = p.tab[prefix] - 1u, n = p.tab[prefix + 1] - 1u - start;
-      if (COUNT_ONLY) {
-        hits += n;
-      } else {
-        for (uint32_t j = 0; j < n; ++j) {
-          const unsigned long long loc = (unsigned long long)p.pos[start + j] + p.unit_offset;
-          vote((uint32_t)((loc - (unsigned long long)pos) >> p.bin_shift), false);
+    // canonical hit order of the chunk: lane 0 forward, lane 0 reverse, lane 1 forward, ...
+    uint32_t incl = fn + rn;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const uint32_t T = __shfl_sync(FULL, incl, 31);
+    for (uint32_t hb = 0; hb < T; hb += 32) {
+      const uint32_t h = hb + (uint32_t)lane;
+      const bool act = h < T;
+      // owner = first lane whose inclusive count exceeds h
+      int lo = 0;
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const uint32_t v = __shfl_sync(FULL, incl, lo + step - 1);
+        if (v <= h) lo += step;
+      }
+      const int owner = lo > 31 ? 31 : lo;
+      const uint32_t o_incl = __shfl_sync(FULL, incl, owner);
+      const uint32_t o_fn = __shfl_sync(FULL, fn, owner), o_rn = __shfl_sync(FULL, rn, owner);
+      const uint32_t o_fs = __shfl_sync(FULL, fs, owner), o_rs = __shfl_sync(FULL, rs, owner);
+      const uint32_t off = h - (o_incl - o_fn - o_rn);
+      const bool rev = off >= o_fn;
+      uint32_t bin = 0;
+      if (act) {
+        const uint32_t idx = rev ? o_rs + (off - o_fn) : o_fs + off;
+        const unsigned long long loc = (unsigned long long)p.pos[idx] + p.unit_offset;
+        const int kpos = c0 + owner;
+        const unsigned long long corr = rev ? (unsigned long long)(len - (kpos + k)) : (unsigned long long)kpos;
+        bin = (uint32_t)((loc - corr) >> p.bin_shift);
+      }
+      // ---- CS::AddLocationStd for 32 hits at once ----
+      const unsigned long long mkey = act ? (unsigned long long)bin : (0x100000000ull | (unsigned long long)lane);
+      const unsigned peers = __match_any_sync(FULL, mkey);
+      const int leader = __ffs(peers) - 1;
+      uint32_t slot = 0;
+      VoteEntry e;
+      e.key = 0; e.state = 0; e.f = 0.0f; e.r = 0.0f;
+      if (act && lane == leader) {
+        uint32_t sidx = ((bin * 2654435761u) >> 7) & cap_mask;
+        const unsigned long long want = (unsigned long long)bin | (1ull << 32);
+        for (;;) {
+          unsigned long long* w = reinterpret_cast<unsigned long long*>(tab + sidx);
+          const unsigned long long old = atomicCAS(w, 0ull, want);  // empty -> {bin, used}
+          if (old == 0ull || ((uint32_t)old == bin && ((old >> 32) & 1ull))) break;
+          sidx = (sidx + 1u) & cap_mask;
         }
+        slot = sidx;
+        e = tab[sidx];
       }
-    }
-    const uint32_t rc = rev_comp(prefix, k, mask);
-    if ((p.used_bits[rc >> 5] >> (rc & 31u)) & 1u) {
-      const uint32_t start = p.tab[rc] - 1u, n = p.tab[rc + 1] - 1u - start;
-      if (COUNT_ONLY) {
-        hits += n;
-      } else {
-        const unsigned long long corr = (unsigned long long)(len - (pos + k));
-        for (uint32_t j = 0; j < n; ++j) {
-          const unsigned long long loc = (unsigned long long)p.pos[start + j] + p.unit_offset;
-          vote((uint32_t)((loc - corr) >> p.bin_shift), true);
-        }
+      slot = __shfl_sync(FULL, slot, leader);
+      const float f_old = __shfl_sync(FULL, e.f, leader), r_old = __shfl_sync(FULL, e.r, leader);
+      const uint32_t st_old = __shfl_sync(FULL, e.state, leader);
+      const unsigned rev_mask = __ballot_sync(FULL, act && rev);
+      const unsigned same = peers & (rev ? rev_mask : ~rev_mask);
+      const float score = (rev ? r_old : f_old) + (float)(__popc(same & lowmask(lane)) + 1);
+      // running maximum in canonical order (:136-141)
+      float m = act ? score : 0.0f;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float t = __shfl_up_sync(FULL, m, o);
+        if (lane >= o) m = fmaxf(m, t);
       }
-    }
-  };
-
-  // ---- CS::PrefixIteration with prefixskip = 0, tail recursion as a loop ----
-  {
-    int cur = 0, length = len;
-    for (;;) {
-      if (length < k) break;
-      if (seq[cur] == 'N') {
-        int n_skip = 1;
-        while (cur + n_skip < len && seq[cur + n_skip] == 'N') ++n_skip;
-        cur += n_skip;
-        if (n_skip >= length - k) break;
-        length -= n_skip;
+      m = fmaxf(m, max_hits);
+      const float th = m > max_hits ? __fmul_rn(m, p.sensitivity) : thresh;
+      // listing (:143-147): the first hit of a bin that is not listed yet and reaches the threshold
+      const bool cond = act && score >= th;
+      const unsigned cm = __ballot_sync(FULL, cond);
+      const unsigned mine = peers & cm;
+      const bool lister = cond && !(st_old & 2u) && lane == (__ffs(mine) - 1);
+      const unsigned lm = __ballot_sync(FULL, lister);
+      if (lister) order[n_order + __popc(lm & lowmask(lane))] = slot;
+      n_order += __popc(lm);
+      if (act && lane == leader) {
+        e.f = f_old + (float)__popc(peers & ~rev_mask);
+        e.r = r_old + (float)__popc(peers & rev_mask);
+        e.state = st_old | 1u | ((mine && !(st_old & 2u)) ? 2u : 0u);
+        e.key = bin;
+        tab[slot] = e;
       }
-      uint32_t prefix = 0;
-      int j = 0;
-      bool restart = false;
-      for (; j < k - 1; ++j) {
-        const uint32_t c = seq[cur + j];
-        if (c == 'N') { restart = true; break; }
-        prefix = (prefix << 2) | ((c >> 1) & 3u);
+      const float m_all = __shfl_sync(FULL, m, 31);
+      if (m_all > max_hits) {
+        max_hits = m_all;
+        thresh = __fmul_rn(max_hits, p.sensitivity);
       }
-      if (!restart) {
-        for (j = k - 1; j < length; ++j) {
-          const uint32_t c = seq[cur + j];
-          if (c == 'N') { restart = true; break; }
-          prefix = ((prefix << 2) | ((c >> 1) & 3u)) & mask;
-          kmer(prefix, cur + j + 1 - k);
-        }
-      }
-      if (!restart) break;
-      cur += j + 1;
-      length -= j + 1;
+      __syncwarp();
     }
   }
 
   if (COUNT_ONLY) {
-    p.hits[i] = hits;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) hits += __shfl_xor_sync(FULL, hits, o);
+    if (lane == 0) p.hits[i] = hits;
     return;
   }
-  // ---- CS::CollectResultsStd ----
+  // ---- CS::CollectResultsStd: listed bins in listing order, forward before reverse ----
   const float thr = fmaxf(p.min_kmer_hits, thresh);
   CsCandidate* out = p.out + p.out_off[i];
   int n = 0;
   const unsigned long long half = p.bin_shift > 0 ? (1ull << (p.bin_shift - 1)) : 0ull;
-  for (int j = 0; j < n_order; ++j) {
-    const VoteEntry e = tab[order[j]];
+  for (int j0 = 0; j0 < n_order; j0 += 32) {
+    const int j = j0 + lane;
+    VoteEntry e;
+    e.key = 0; e.state = 0; e.f = -1.0f; e.r = -1.0f;
+    if (j < n_order) e = tab[order[j]];
+    const bool ef = j < n_order && e.f >= thr, er = j < n_order && e.r >= thr;
+    int cnt = (ef ? 1 : 0) + (er ? 1 : 0);
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(FULL, inc, o);
+      if (lane >= o) inc += t;
+    }
+    int at = n + inc - cnt;
     const unsigned long long loc = ((unsigned long long)e.key << p.bin_shift) + half;  // ResolveBin
-    if (e.f >= thr) {
-      out[n].loc = loc;
-      out[n].score = e.f;
-      out[n].reverse = 0;
-      ++n;
+    if (ef) {
+      out[at].loc = loc;
+      out[at].score = e.f;
+      out[at].reverse = 0;
+      ++at;
     }
-    if (e.r >= thr) {
-      out[n].loc = loc;
-      out[n].score = e.r;
-      out[n].reverse = 1;
-      ++n;
+    if (er) {
+      out[at].loc = loc;
+      out[at].score = e.r;
+      out[at].reverse = 1;
     }
+    n += __shfl_sync(FULL, inc, 31);
   }
-  p.out_count[i] = n;
-  p.max_hits[i] = max_hits;
+  if (lane == 0) {
+    p.out_count[i] = n;
+    p.max_hits[i] = max_hits;
+  }
 }
 
 // Unpack the reference's 5-byte Index records {uint m_TabIndex; char m_RevCompIndex}
@@ -201,11 +283,11 @@ __global__ void unpack_index_kernel(const uint8_t* __restrict__ packed, uint32_t
 
 cudaError_t launch_cs_search(const CsParams& p, bool count_only, cudaStream_t stream) {
   if (p.n <= 0) return cudaSuccess;
-  const int grid = (p.n + 127) / 128;
+  const int grid = (p.n + CS_WARPS - 1) / CS_WARPS;
   if (count_only)
-    cs_search_kernel<true><<<grid, 128, 0, stream>>>(p);
+    cs_search_kernel<true><<<grid, CS_WARPS * 32, 0, stream>>>(p);
   else
-    cs_search_kernel<false><<<grid, 128, 0, stream>>>(p);
+    cs_search_kernel<false><<<grid, CS_WARPS * 32, 0, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -52,6 +52,7 @@ cudaError_t launch_convex_text(const TextParams& p, cudaStream_t stream);
 // read parts (optionally reverse-complemented) from the resident read set into the sequence arena
 cudaError_t launch_gather_reads(const GatherParams& p, cudaStream_t stream);
 
+constexpr uint32_t CS_SMEM_CAP = 512;  // vote tables up to this many entries live in shared memory (no arena space)
 cudaError_t launch_cs_search(const CsParams& p, bool count_only, cudaStream_t stream);
 cudaError_t launch_unpack_index(const uint8_t* packed, uint32_t n, uint32_t* tab, uint32_t* used_bits,
                                 cudaStream_t stream);

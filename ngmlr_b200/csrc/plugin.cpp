@@ -43,6 +43,8 @@ std::vector<ParkedContext> g_pool;
 struct PluginStats {
   std::atomic<long long> align_calls{0}, align_batches{0}, align_problems{0}, align_batch_us{0};
   std::atomic<long long> score_calls{0}, score_batches{0}, score_pairs{0};
+  // phases of the batched SingleAlign launches, microseconds (from ngmlr_b200_convex_stats + the copy back)
+  std::atomic<long long> us_pack{0}, us_h2d{0}, us_run{0}, us_fill{0}, us_trace{0}, us_d2h{0}, us_text{0}, us_copy{0};
   ~PluginStats() {
     if (!getenv("NGMLR_B200_STATS")) return;
     fprintf(stderr,
@@ -52,6 +54,12 @@ struct PluginStats {
             align_batches ? (double)align_problems / (double)align_batches : 0.0,
             align_batches ? 1e-3 * (double)align_batch_us / (double)align_batches : 0.0, score_calls.load(),
             score_batches.load(), score_batches ? (double)score_pairs / (double)score_batches : 0.0);
+    const double nb = align_batches ? (double)align_batches : 1.0;
+    fprintf(stderr,
+            "[ngmlr_b200] per SingleAlign batch (ms): pack %.2f, H2D %.2f, run %.2f (fill kernel %.2f, traceback kernel "
+            "%.2f), D2H %.2f, CIGAR/MD/nmPerPosition text %.2f, copy into the callers' Align %.2f\n",
+            1e-3 * us_pack / nb, 1e-3 * us_h2d / nb, 1e-3 * us_run / nb, 1e-3 * us_fill / nb, 1e-3 * us_trace / nb,
+            1e-3 * us_d2h / nb, 1e-3 * us_text / nb, 1e-3 * us_copy / nb);
   }
 } g_stats;
 
@@ -270,6 +278,19 @@ class B200Alignment : public IAlignment {
         throw error_.c_str();
       }
     }
+    if (m > 0) {
+      ngmlr_b200_batch_stats bs;
+      if (ngmlr_b200_convex_stats(ctx_, &bs) == 0) {
+        g_stats.us_pack += (long long)(1e3 * bs.host_pack_ms);
+        g_stats.us_h2d += (long long)(1e3 * bs.host_h2d_ms);
+        g_stats.us_run += (long long)(1e3 * bs.host_run_ms);
+        g_stats.us_fill += (long long)(1e3 * bs.fill_ms);
+        g_stats.us_trace += (long long)(1e3 * bs.traceback_ms);
+        g_stats.us_d2h += (long long)(1e3 * bs.host_d2h_ms);
+        g_stats.us_text += (long long)(1e3 * bs.host_text_ms);
+      }
+    }
+    const auto t_copy0 = std::chrono::steady_clock::now();
     bool threw = false;
     for (int j = 0; j < m; ++j) {
       const int i = keep_[j];
@@ -324,6 +345,7 @@ class B200Alignment : public IAlignment {
       a.svType = r.sv_type;
       rets[i] = r.ret;
     }
+    g_stats.us_copy += std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_copy0).count();
     if (threw && n == 1 && !threw_out) throw 1;  // caller wraps SingleAlign in try/catch(...) -> unmapped
   }
 
