@@ -624,7 +624,7 @@ int ngmlr_b200_cs_search_batch(ngmlr_b200_ctx* ctx, int n, const char* const* se
   p.hits = cs->d_hits.p;
   // ---- pass 1: hits per read ----
   CU(cudaEventRecord(ctx->ev[4], st));
-  CU(launch_cs_search(p, true, st));
+  CU(launch_cs_search(p, true, false, st));
   std::vector<unsigned long long> hits(n);
   CU(cudaMemcpyAsync(hits.data(), cs->d_hits.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
@@ -679,7 +679,9 @@ int ngmlr_b200_cs_search_batch(ngmlr_b200_ctx* ctx, int n, const char* const* se
     q.out_off = cs->d_off.p + (size_t)3 * n;
     q.out_count = cs->d_count.p;
     q.max_hits = cs->d_max.p;
-    CU(launch_cs_search(q, false, st));
+    bool any_small = false;
+    for (int i = first; i < last; ++i) any_small = any_small || caps[i] <= CS_SMEM_CAP;
+    CU(launch_cs_search(q, false, any_small, st));
     hout.resize(rent + 1);
     CU(cudaMemcpyAsync(counts.data() + first, cs->d_count.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(max_hits + first, cs->d_max.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
@@ -993,7 +995,8 @@ int ngmlr_b200_cs_run(ngmlr_b200_ctx* ctx, float sensitivity, float min_kmer_hit
   p.n = n;
   p.hits = cs->d_hits.p;
   CU(cudaEventRecord(cs->ev0, st));
-  CU(launch_cs_search(p, true, st));
+  CU(launch_cs_search(p, true, false, st));
+  CU(cudaMemsetAsync(cs->d_hits.p + n, 0, 8, st));  // counter of small (shared-memory) tables
   CU(launch_cs_sizes(cs->d_hits.p, n, cs->d_cap.p, cs->d_a.p, cs->d_b.p, cs->d_c.p, st));
   size_t tb = cs->d_scan_tmp.cap;
   CU(cs_exclusive_scan(cs->d_scan_tmp.p, tb, cs->d_a.p, cs->d_sa.p, (int)n1, st));
@@ -1002,12 +1005,15 @@ int ngmlr_b200_cs_run(ngmlr_b200_ctx* ctx, float sensitivity, float min_kmer_hit
   tb = cs->d_scan_tmp.cap;
   CU(cs_exclusive_scan(cs->d_scan_tmp.p, tb, cs->d_c.p, cs->d_sc.p, (int)n1, st));
   unsigned long long totals[3] = {0, 0, 0};
+  unsigned long long n_small = 1;
+  CU(cudaMemcpyAsync(&n_small, cs->d_hits.p + n, 8, cudaMemcpyDeviceToHost, st));  // cs_sizes_kernel's counter
   CU(cudaMemcpyAsync(&totals[0], cs->d_sa.p + n, 8, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(&totals[1], cs->d_sb.p + n, 8, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(&totals[2], cs->d_sc.p + n, 8, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  cs->n_small_tables = n_small;
   const size_t need = (size_t)totals[0] * 16 + (size_t)totals[1] * 4 + (size_t)totals[2] * 16;
-  if (need > ((size_t)48 << 30))
+  if (need > ((size_t)96 << 30))
     return ctx->fail("cs_run: %zu bytes of vote tables needed; use cs_score_batch (chunked) for this batch", need);
   CU(cs->d_tables.reserve((size_t)totals[0] * 16 + 16));
   CU(cs->d_order.reserve((size_t)totals[1] + 4));
@@ -1022,7 +1028,11 @@ int ngmlr_b200_cs_run(ngmlr_b200_ctx* ctx, float sensitivity, float min_kmer_hit
   p.out_off = reinterpret_cast<const uint64_t*>(cs->d_sc.p);
   p.out_count = cs->d_count.p;
   p.max_hits = cs->d_max.p;
-  CU(launch_cs_search(p, false, st));
+  // small tables take no arena space: the arena holds exactly sum(cap > CS_SMEM_CAP ? cap : 0) entries, and every big
+  // table has at least 2 * CS_SMEM_CAP of them -- so "no small table" <=> arena >= 2 * CS_SMEM_CAP * n can only be
+  // decided safely in one direction; the shared-memory variant is always correct, the other only without small tables
+  const bool any_small = cs->n_small_tables != 0;
+  CU(launch_cs_search(p, false, any_small, st));
   CU(launch_cs_count_to_u64(cs->d_count.p, n, cs->d_cnt64.p, st));
   tb = cs->d_scan_tmp.cap;
   CU(cs_exclusive_scan(cs->d_scan_tmp.p, tb, cs->d_cnt64.p, cs->d_cstart.p, (int)n1, st));

@@ -12,7 +12,8 @@ namespace nb {
 
 namespace {
 
-__global__ void cs_sizes_kernel(const unsigned long long* __restrict__ hits, int n, uint32_t* __restrict__ cap,
+// hits[n] doubles as the counter of small tables (zeroed by the host before the launch)
+__global__ void cs_sizes_kernel(unsigned long long* __restrict__ hits, int n, uint32_t* __restrict__ cap,
                                 unsigned long long* __restrict__ a, unsigned long long* __restrict__ b,
                                 unsigned long long* __restrict__ c) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -26,6 +27,7 @@ __global__ void cs_sizes_kernel(const unsigned long long* __restrict__ hits, int
   while (cp < 2 * h + 2) cp <<= 1;
   cap[i] = cp > 0x80000000ull ? 0x80000000u : (uint32_t)cp;
   a[i] = cap[i] > CS_SMEM_CAP ? cp : 0ull;  // vote table entries in the arena (small tables live in shared memory)
+  if (cap[i] <= CS_SMEM_CAP) atomicAdd(hits + n, 1ull);
   b[i] = h;       // order list entries
   c[i] = 2 * h;   // candidate slots (forward + reverse per listed bin)
 }
@@ -67,7 +69,7 @@ cudaError_t cs_exclusive_scan(void* temp, size_t& temp_bytes, const unsigned lon
   return cub::DeviceScan::ExclusiveSum(temp, temp_bytes, in, out, n, stream);
 }
 
-cudaError_t launch_cs_sizes(const unsigned long long* hits, int n, uint32_t* cap, unsigned long long* a,
+cudaError_t launch_cs_sizes(unsigned long long* hits, int n, uint32_t* cap, unsigned long long* a,
                             unsigned long long* b, unsigned long long* c, cudaStream_t stream) {
   cs_sizes_kernel<<<(n + 1 + 255) / 256, 256, 0, stream>>>(hits, n, cap, a, b, c);
   return cudaGetLastError();

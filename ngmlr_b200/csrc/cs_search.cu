@@ -56,9 +56,12 @@ __device__ __forceinline__ unsigned lowmask(int n) { return n >= 32 ? 0xffffffff
 // flight per warp instead of one dependent chain per sub-read -- the kernel was bound by exactly that
 // latency (one thread per sub-read: issue slots 17 %, 5.3 ms per 299 k sub-reads; 7 300 hits per sub-read
 // on a human-sized index). Small vote tables (<= CS_SMEM_CAP entries) live in shared memory.
-template <bool COUNT_ONLY>
+// SMEM_TAB = false: no table of the batch is small (human-sized index: thousands of hits per sub-read), the
+// 32 KB of shared memory per CTA are not reserved and more warps are resident.
+template <bool COUNT_ONLY, bool SMEM_TAB>
 __global__ void __launch_bounds__(CS_WARPS * 32) cs_search_kernel(const CsParams p) {
-  __shared__ VoteEntry s_tab[COUNT_ONLY ? 1 : CS_WARPS][COUNT_ONLY ? 1 : CS_SMEM_CAP];  // 32 KB per CTA
+  constexpr bool HAS_SMEM = !COUNT_ONLY && SMEM_TAB;
+  __shared__ VoteEntry s_tab[HAS_SMEM ? CS_WARPS : 1][HAS_SMEM ? CS_SMEM_CAP : 1];  // 32 KB per CTA
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int i = blockIdx.x * CS_WARPS + wib;
   if (i >= p.n) return;
@@ -76,7 +79,7 @@ __global__ void __launch_bounds__(CS_WARPS * 32) cs_search_kernel(const CsParams
   if (!COUNT_ONLY) {
     const uint32_t cap = p.table_cap[i];
     cap_mask = cap - 1u;
-    if (cap <= CS_SMEM_CAP) {
+    if (HAS_SMEM && cap <= CS_SMEM_CAP) {
       tab = s_tab[wib];
       uint4* z = reinterpret_cast<uint4*>(tab);
       for (uint32_t j = lane; j < cap; j += 32) z[j] = make_uint4(0u, 0u, 0u, 0u);
@@ -163,20 +166,35 @@ __global__ void __launch_bounds__(CS_WARPS * 32) cs_search_kernel(const CsParams
       const unsigned long long mkey = act ? (unsigned long long)bin : (0x100000000ull | (unsigned long long)lane);
       const unsigned peers = __match_any_sync(FULL, mkey);
       const int leader = __ffs(peers) - 1;
-      uint32_t slot = 0;
+      // The group leaders find or insert their entries (open addressing). No atomics: only this warp touches
+      // the table, and leaders that reach the same empty slot in the same round settle it with a match --
+      // the lowest lane takes the slot, the others probe on.
+      uint32_t slot = ((bin * 2654435761u) >> 7) & cap_mask;
       VoteEntry e;
       e.key = 0; e.state = 0; e.f = 0.0f; e.r = 0.0f;
-      if (act && lane == leader) {
-        uint32_t sidx = ((bin * 2654435761u) >> 7) & cap_mask;
-        const unsigned long long want = (unsigned long long)bin | (1ull << 32);
-        for (;;) {
-          unsigned long long* w = reinterpret_cast<unsigned long long*>(tab + sidx);
-          const unsigned long long old = atomicCAS(w, 0ull, want);  // empty -> {bin, used}
-          if (old == 0ull || ((uint32_t)old == bin && ((old >> 32) & 1ull))) break;
-          sidx = (sidx + 1u) & cap_mask;
+      bool pending = act && lane == leader;
+      while (__any_sync(FULL, pending)) {
+        bool empty = false;
+        if (pending) {
+          e = tab[slot];
+          if (e.state & 1u) {
+            if (e.key == bin) pending = false;               // found
+            else slot = (slot + 1u) & cap_mask;              // occupied by another bin
+          } else {
+            empty = true;
+          }
         }
-        slot = sidx;
-        e = tab[sidx];
+        const unsigned claim = __match_any_sync(FULL, empty ? (unsigned long long)slot : (0x100000000ull | (unsigned long long)lane));
+        if (empty) {
+          if (lane == __ffs(claim) - 1) {
+            e.key = bin; e.state = 1u; e.f = 0.0f; e.r = 0.0f;
+            tab[slot] = e;                                   // inserted
+            pending = false;
+          } else {
+            slot = (slot + 1u) & cap_mask;                   // lost the slot to a lower lane
+          }
+        }
+        __syncwarp();
       }
       slot = __shfl_sync(FULL, slot, leader);
       const float f_old = __shfl_sync(FULL, e.f, leader), r_old = __shfl_sync(FULL, e.r, leader);
@@ -281,13 +299,15 @@ __global__ void unpack_index_kernel(const uint8_t* __restrict__ packed, uint32_t
 
 }  // namespace
 
-cudaError_t launch_cs_search(const CsParams& p, bool count_only, cudaStream_t stream) {
+cudaError_t launch_cs_search(const CsParams& p, bool count_only, bool small_tables, cudaStream_t stream) {
   if (p.n <= 0) return cudaSuccess;
   const int grid = (p.n + CS_WARPS - 1) / CS_WARPS;
   if (count_only)
-    cs_search_kernel<true><<<grid, CS_WARPS * 32, 0, stream>>>(p);
+    cs_search_kernel<true, false><<<grid, CS_WARPS * 32, 0, stream>>>(p);
+  else if (small_tables)
+    cs_search_kernel<false, true><<<grid, CS_WARPS * 32, 0, stream>>>(p);
   else
-    cs_search_kernel<false><<<grid, CS_WARPS * 32, 0, stream>>>(p);
+    cs_search_kernel<false, false><<<grid, CS_WARPS * 32, 0, stream>>>(p);
   return cudaGetLastError();
 }
 

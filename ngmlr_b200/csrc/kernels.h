@@ -53,7 +53,8 @@ cudaError_t launch_convex_text(const TextParams& p, cudaStream_t stream);
 cudaError_t launch_gather_reads(const GatherParams& p, cudaStream_t stream);
 
 constexpr uint32_t CS_SMEM_CAP = 512;  // vote tables up to this many entries live in shared memory (no arena space)
-cudaError_t launch_cs_search(const CsParams& p, bool count_only, cudaStream_t stream);
+// small_tables: some vote table of the batch has at most CS_SMEM_CAP entries (shared-memory tables compiled in)
+cudaError_t launch_cs_search(const CsParams& p, bool count_only, bool small_tables, cudaStream_t stream);
 cudaError_t launch_unpack_index(const uint8_t* packed, uint32_t n, uint32_t* tab, uint32_t* used_bits,
                                 cudaStream_t stream);
 
@@ -64,7 +65,7 @@ size_t index_build_cub_bytes(unsigned long long concat_len, unsigned long long m
 // device-resident candidate pipeline glue (cs_pipeline.cu)
 cudaError_t cs_exclusive_scan(void* temp, size_t& temp_bytes, const unsigned long long* in,
                               unsigned long long* out, int n, cudaStream_t stream);
-cudaError_t launch_cs_sizes(const unsigned long long* hits, int n, uint32_t* cap, unsigned long long* a,
+cudaError_t launch_cs_sizes(unsigned long long* hits, int n, uint32_t* cap, unsigned long long* a,
                             unsigned long long* b, unsigned long long* c, cudaStream_t stream);
 cudaError_t launch_cs_count_to_u64(const int32_t* cnt, int n, unsigned long long* out, cudaStream_t stream);
 cudaError_t launch_cs_compact(const CsCandidate* out, const uint64_t* out_off, const int32_t* out_count,

@@ -344,6 +344,7 @@ struct CsState {
   DevBuf<uint8_t> d_scan_tmp;
   DevBuf<float> d_cscore;
   long long n_cand = 0;
+  unsigned long long n_small_tables = 1;  // tables of the last run that live in shared memory
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<int64_t> h_cstart;
   // pinned staging for the resident pipeline's upload / fetch
