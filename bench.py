@@ -416,7 +416,7 @@ def ialignment_batch_align(wl, ivs, gpu_results, steps, gpu_id):
                     "Align buffers out incl. nmPerPosition; one aligner object, one batch in flight"}
 
 
-def integrated_run(wl_cfg, genome, contig_len, n_contigs, enc_ref, index, n_reads, cpu_threads, gpu_threads=96):
+def integrated_run(wl_cfg, genome, contig_len, n_contigs, enc_ref, index, n_reads, cpu_threads, gpu_threads=16):
     """The UNMODIFIED ngmlr end to end, twice on the same FASTQ: the plain binary (oracle/_ref/ngmlr, its own
     ConvexAlignFast / StrippedSW on `cpu_threads` threads) and the same objects linked with the CUDA plugin
     behind IAlignment (oracle/_ref/ngmlr_b200; every blocking SingleAlign of its `gpu_threads` worker threads
@@ -497,8 +497,12 @@ def main():
                          "roofline phase always runs at full occupancy)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     ap.add_argument("--parity-reads", type=int, default=0, help="reads compared CPU vs GPU (0 = the CPU sample)")
+    ap.add_argument("--profile-only", action="store_true",
+                    help="stop after the solo phase (one context, whole batch resident): what ncu captures")
     ap.add_argument("--integrated-only", action="store_true", help="run only the whole-ngmlr comparison")
-    ap.add_argument("--integrated-threads", type=int, default=96, help="worker threads of the plugin-linked ngmlr")
+    ap.add_argument("--integrated-threads", type=int, default=16,
+                    help="worker threads of the plugin-linked ngmlr (16 = the GPU boxes' CPU quota measured best: "
+                         "every thread blocks ~10 ms per SingleAlign batch, more threads only oversubscribe the CPUs)")
     ap.add_argument("--integrated-reads", type=int, default=-1,
                     help="reads of the whole-ngmlr comparison (plain binary vs plugin-linked binary); "
                          "-1 = 2000 at N=1 on configs up to 100 Mb, else 0 (skipped)")
@@ -643,6 +647,11 @@ def main():
     e1.record(streams[0])
     torch.cuda.synchronize(dev)
     solo_ms = e0.elapsed_time(e1)
+    if args.profile_only:
+        print(json.dumps({"profile_only": True, "fill_ms": float(np.mean(fill_ms)), "traceback_ms": float(np.mean(tb_ms)),
+                          "text_ms": float(np.mean(tx_ms)), "stage02_ms": float(np.mean(cs_ms)), "solo_ms_per_step":
+                          solo_ms / args.steps}))
+        return
     gpu_first = al.fetch()                 # first-attempt alignments of every interval (parity check below)
     st = al.stats()
     cells = st["cells"]
