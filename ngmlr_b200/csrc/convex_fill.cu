@@ -55,6 +55,9 @@ constexpr unsigned X_BIAS = 1u << 20;
 #ifndef FILL_TEAM_CHUNK
 #define FILL_TEAM_CHUNK 16
 #endif
+#ifndef FILL_LANE0_LDS
+#define FILL_LANE0_LDS 0  // 1: lane 0 loads its strip record itself instead of receiving it through lane 31's shuffle sources
+#endif
 
 __device__ __forceinline__ uint4 ld_strip(const uint4* p) { return __ldcg(p); }
 __device__ __forceinline__ void st_strip(uint4* p, uint4 v) { __stcg(p, v); }
@@ -284,6 +287,7 @@ convex_fill_kernel(const FillParams p) {
         if (lane < CHUNK) io_s[2 * lane] = pa;
         if (CHUNK > 32) io_s[2 * (lane + 32)] = pb;
         __syncwarp();
+#if !FILL_LANE0_LDS
         if (is31) {  // lane 31's shuffle sources carry the strip record lane 0 needs next
           const uint4 t = io_s[0];
           oS = __uint_as_float(t.x);
@@ -291,6 +295,7 @@ convex_fill_kernel(const FillParams p) {
           oP = t.z;
           oC = t.w;
         }
+#endif
         if (c + 1 < nchunks) {  // fetch the next chunk while this one is computed
           const int x0 = base + (c + 1) * CHUNK + lane;
           wait_for(base + (c + 2) * CHUNK);
@@ -308,17 +313,26 @@ convex_fill_kernel(const FillParams p) {
         // (the common case away from the block's leading and trailing wavefront).
         auto do_group = [&](auto all_active_tag, int g) {
           constexpr bool ALL_ACTIVE = decltype(all_active_tag)::value;
-          uint4* io_g = io_s + ((g % GPC) << 5);
+          uint4* iop = io_s + ((g % GPC) << 5);  // [0] lane 0's input of this step, [1] lane 31's output
           uint32_t dw = 0;
           {
 #pragma unroll 2  // 2 keeps the per-step predicates in registers; 4 makes ptxas spill them to a bit mask
             for (int k = 0; k < 16; ++k) {
               const int s = (g << 4) + k;
               uint4 v;
+#if FILL_LANE0_LDS
+              // lanes 1..31 take their upper neighbour's cell from lane t-1, lane 0 from the staged strip record
+              v.x = __float_as_uint(__shfl_up_sync(FULL, oS, 1));
+              v.y = __float_as_uint(__shfl_up_sync(FULL, oU, 1));
+              v.z = __shfl_up_sync(FULL, oP, 1);
+              v.w = __shfl_up_sync(FULL, oC, 1);
+              if (is0) v = iop[0];
+#else
               v.x = __float_as_uint(__shfl_sync(FULL, oS, src_lane));
               v.y = __float_as_uint(__shfl_sync(FULL, oU, src_lane));
               v.z = __shfl_sync(FULL, oP, src_lane);
               v.w = __shfl_sync(FULL, oC, src_lane);
+#endif
               const float nS = __uint_as_float(v.x), nU = __uint_as_float(v.y);
               const uint32_t r = v.w;
               const bool act = ALL_ACTIVE ? true : ((unsigned)rel < rlen);
@@ -395,15 +409,20 @@ convex_fill_kernel(const FillParams p) {
                 kStep = s;
               }
               dw = __funnelshift_r(dw, code, 2);
+#if FILL_LANE0_LDS
+              if (is31) iop[1] = make_uint4(__float_as_uint(oS), __float_as_uint(oU), oP, oC);
+#else
               if (is31) {
                 // the record is exactly the four shuffle sources (w is rewritten when the chunk is staged)
-                io_g[2 * k + 1] = make_uint4(__float_as_uint(oS), __float_as_uint(oU), oP, oC);
-                const uint4 t = io_g[2 * k + 2];
+                iop[1] = make_uint4(__float_as_uint(oS), __float_as_uint(oU), oP, oC);
+                const uint4 t = iop[2];
                 oS = __uint_as_float(t.x);
                 oU = __uint_as_float(t.y);
                 oP = t.z;
                 oC = t.w;
               }
+#endif
+              iop += 2;
               if (!ALL_ACTIVE || RAW) ++rel;  // the RAW kernel needs the column for its tail rule
             }
           }

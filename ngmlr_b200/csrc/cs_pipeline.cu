@@ -27,7 +27,9 @@ __global__ void cs_sizes_kernel(unsigned long long* __restrict__ hits, int n, ui
   while (cp < 2 * h + 2) cp <<= 1;
   cap[i] = cp > 0x80000000ull ? 0x80000000u : (uint32_t)cp;
   a[i] = cap[i] > CS_SMEM_CAP ? cp : 0ull;  // vote table entries in the arena (small tables live in shared memory)
-  if (cap[i] <= CS_SMEM_CAP) atomicAdd(hits + n, 1ull);
+  // one atomic per warp, not per sub-read (the guard above only removes threads at the very end of the grid)
+  const unsigned small = __ballot_sync(__activemask(), cap[i] <= CS_SMEM_CAP);
+  if (small && (threadIdx.x & 31) == (__ffs(__activemask()) - 1)) atomicAdd(hits + n, (unsigned long long)__popc(small));
   b[i] = h;       // order list entries
   c[i] = 2 * h;   // candidate slots (forward + reverse per listed bin)
 }

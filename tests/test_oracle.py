@@ -115,3 +115,21 @@ def test_oracle_score_select_vs_compiled_reference(oracle):
         o = oracle.score_select(sc)
         r = CsReference.score_select(sc)
         assert o[1:] == r[1:] and np.array_equal(o[0], r[0])
+
+
+def test_raw_tail_corner_fuzz_against_the_compiled_reference():
+    """scripts/fuzz_raw_tail.py: the compiled reference's fill vs the single-pass rule 2
+    the CUDA RAW kernel implements, on inputs built to hit the tail-cell best-tracking corner (narrow
+    corridors, scorings outside the default class). The full run (1.2e8 cells, 0 mismatches) is recorded in
+    DESIGN.md; this is its quick version."""
+    import os
+    import subprocess
+    import sys
+    from oracle_lib import Reference
+    if not Reference.available():
+        pytest.skip("oracle/_ref/libngmlr_ref.so not built")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "fuzz_raw_tail.py"), "--cells", "4e6", "--seed", "3"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-500:] + r.stderr[-500:]
+    assert "mismatches 0" in r.stdout and "not vacuous" in r.stdout
