@@ -427,7 +427,9 @@ convex_fill_kernel(const FillParams p) {
             }
           }
           if (ALL_ACTIVE && !RAW) rel += 16;
-          dwp[(size_t)g * 32] = dw;
+          // a lane whose 16 steps all lie outside its row has nothing the traceback will ever read: the block's
+          // leading and trailing wavefront stays out of HBM (whole 32-byte sectors, the idle lanes are neighbours)
+          if (ALL_ACTIVE || (rel > 0 && rel - 16 < (int)rlen)) dwp[(size_t)g * 32] = dw;
         };
         for (int g = c * GPC; g < g_end; ++g) {
           const bool all_active = __all_sync(FULL, rel >= 0 && rel + 15 < (int)rlen);
