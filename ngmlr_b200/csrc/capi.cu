@@ -91,6 +91,8 @@ int ngmlr_b200_create(int gpu_id, const ngmlr_b200_scoring* s, ngmlr_b200_ctx** 
   cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&ctx->ev_big, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventDisableTiming | cudaEventBlockingSync);
+  if (const char* e = getenv("NGMLR_B200_SPIN_SYNC")) ctx->spin_sync = atoi(e) != 0;
   for (auto& ev : ctx->ev) cudaEventCreate(&ev);
   ngmlr_b200_scoring d = {2.0f, -5.0f, -5.0f, -5.0f, -1.0f, 0.15f};
   if (s) d = *s;
@@ -112,7 +114,7 @@ int ngmlr_b200_create(int gpu_id, const ngmlr_b200_scoring* s, ngmlr_b200_ctx** 
 void ngmlr_b200_destroy(ngmlr_b200_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  nb_stream_sync(ctx, ctx->stream);
   nb_cs_release(ctx);
   ctx->h_seq.release(); ctx->h_coff.release(); ctx->h_clen.release(); ctx->h_order.release(); ctx->h_blkbase.release(); ctx->h_delta.release();
   ctx->h_desc.release(); ctx->h_fill.release(); ctx->h_trace.release(); ctx->h_runs.release();
@@ -126,6 +128,7 @@ void ngmlr_b200_destroy(ngmlr_b200_ctx* ctx) {
   ctx->d_sw_scratch.release();
   for (auto& ev : ctx->ev) cudaEventDestroy(ev);
   if (ctx->ev_big) cudaEventDestroy(ctx->ev_big);
+  if (ctx->ev_sync) cudaEventDestroy(ctx->ev_sync);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -134,7 +137,7 @@ void ngmlr_b200_destroy(ngmlr_b200_ctx* ctx) {
 int ngmlr_b200_set_stream(ngmlr_b200_ctx* ctx, void* s) {
   if (!ctx) return -1;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  nb_stream_sync(ctx, ctx->stream);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   if (s) {
     ctx->stream = (cudaStream_t)s;
@@ -340,7 +343,7 @@ int ngmlr_b200_sw_score_batch(ngmlr_b200_ctx* ctx, int n, const char* const* ref
   CU(launch_sw_score(sp, grid, st));
   CU(cudaEventRecord(ctx->ev[5], st));
   CU(cudaMemcpyAsync(ctx->h_sw_out.p, ctx->d_sw_out.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
+  CU(nb_stream_sync(ctx, st));
   memcpy(results, ctx->h_sw_out.p, (size_t)n * sizeof(float));
   return n;
 }
@@ -421,9 +424,9 @@ int ngmlr_b200_cs_set_index(ngmlr_b200_ctx* ctx, const void* packed_index, uint3
     for (size_t i = 0; i < index_len; ++i) rci[i] = (int8_t)src[5 * i + 4];
     CU(cs->d_rci.reserve((size_t)index_len + 1));
     CU(cudaMemcpyAsync(cs->d_rci.p, rci.data(), index_len, cudaMemcpyHostToDevice, st));
-    CU(cudaStreamSynchronize(st));
+    CU(nb_stream_sync(ctx, st));
   }
-  CU(cudaStreamSynchronize(st));
+  CU(nb_stream_sync(ctx, st));
   cs->d_packed.release();
   cs->index_len = index_len;
   cs->n_pos = n_positions;
@@ -527,7 +530,7 @@ int ngmlr_b200_cs_build_index(ngmlr_b200_ctx* ctx, const uint64_t* contig_start,
   CU(cudaEventRecord(ctx->ev[4], st));
   CU(build_kmer_index(p, s, st));
   CU(cudaEventRecord(ctx->ev[5], st));
-  CU(cudaStreamSynchronize(st));
+  CU(nb_stream_sync(ctx, st));
   cs->index_len = n_kmers + 1;
   cs->n_pos = s.n_positions;
   cs->unit_offset = 0;
@@ -627,7 +630,7 @@ int ngmlr_b200_cs_search_batch(ngmlr_b200_ctx* ctx, int n, const char* const* se
   CU(launch_cs_search(p, true, false, st));
   std::vector<unsigned long long> hits(n);
   CU(cudaMemcpyAsync(hits.data(), cs->d_hits.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
+  CU(nb_stream_sync(ctx, st));
   // ---- pass 2 in chunks bounded by a device-memory budget ----
   const size_t budget = (size_t)4 << 30;
   std::vector<uint64_t> toff(n), ooff(n), roff(n);
@@ -686,7 +689,7 @@ int ngmlr_b200_cs_search_batch(ngmlr_b200_ctx* ctx, int n, const char* const* se
     CU(cudaMemcpyAsync(counts.data() + first, cs->d_count.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(max_hits + first, cs->d_max.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
     if (rent) CU(cudaMemcpyAsync(hout.data(), cs->d_out.p, rent * sizeof(CsCandidate), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(nb_stream_sync(ctx, st));
     for (int i = first; i < last; ++i) {
       const CsCandidate* c = hout.data() + roff[i];
       for (int j = 0; j < counts[i]; ++j) {
@@ -699,7 +702,7 @@ int ngmlr_b200_cs_search_batch(ngmlr_b200_ctx* ctx, int n, const char* const* se
     first = last;
   }
   CU(cudaEventRecord(ctx->ev[5], st));
-  CU(cudaStreamSynchronize(st));
+  CU(nb_stream_sync(ctx, st));
   *scores = cs->scores.data();
   *locs = cs->locs.data();
   *reverse = cs->reverse.data();
@@ -719,7 +722,7 @@ int ngmlr_b200_cs_set_reference(ngmlr_b200_ctx* ctx, const uint8_t* bin_ref, uin
   CU(cs->d_enc.reserve(n_bytes + 64));
   CU(cudaMemsetAsync(cs->d_enc.p, 0x44, n_bytes + 64, ctx->stream));  // 'N','N' past the end
   CU(cudaMemcpyAsync(cs->d_enc.p, bin_ref, n_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
+  CU(nb_stream_sync(ctx, ctx->stream));
   cs->enc_bytes = n_bytes;
   cs->concat_len = concat_len;
   return 0;
@@ -736,7 +739,7 @@ int ngmlr_b200_set_ref_starts(ngmlr_b200_ctx* ctx, const uint64_t* ref_start_pos
   CU(cs->d_ref_starts.reserve((size_t)n_entries));
   CU(cudaMemcpyAsync(cs->d_ref_starts.p, cs->ref_starts.data(), (size_t)n_entries * 8, cudaMemcpyHostToDevice,
                      ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
+  CU(nb_stream_sync(ctx, ctx->stream));
   return 0;
 }
 
@@ -802,7 +805,7 @@ int ngmlr_b200_decode_windows(ngmlr_b200_ctx* ctx, int n, const uint64_t* start,
   rp.out = ctx->d_sw_seq.p;
   CU(launch_decode_windows(rp, st));
   CU(cudaMemcpyAsync(ctx->h_sw_seq.p, ctx->d_sw_seq.p, total, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
+  CU(nb_stream_sync(ctx, st));
   parallel_for(n, 64, [&](int i) { memcpy(out + out_off[i], ctx->h_sw_seq.p + hw[n + i], (size_t)seq_len[i]); });
   return n;
 }
@@ -908,7 +911,7 @@ int ngmlr_b200_cs_score_batch(ngmlr_b200_ctx* ctx, int n, const char* const* seq
   sp.win_len = win_len;
   CU(launch_sw_score_gather(sp, grid, st));
   CU(cudaMemcpyAsync(cs->sw_scores.data(), cs->d_sw.p, m * 4, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
+  CU(nb_stream_sync(ctx, st));
   return rc;
 }
 
@@ -943,7 +946,7 @@ int ngmlr_b200_cs_upload(ngmlr_b200_ctx* ctx, int n, const char* const* seqs, co
     CU(cudaMemcpyAsync(cs->d_off.p, seq_off.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(cs->d_len.p, lens, (size_t)n * 4, cudaMemcpyHostToDevice, st));
   }
-  CU(cudaStreamSynchronize(st));
+  CU(nb_stream_sync(ctx, st));
   cs->rn = n;
   cs->rbytes = bytes;
   cs->seq_base = cs->d_seq.p;
@@ -1010,7 +1013,7 @@ int ngmlr_b200_cs_run(ngmlr_b200_ctx* ctx, float sensitivity, float min_kmer_hit
   CU(cudaMemcpyAsync(&totals[0], cs->d_sa.p + n, 8, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(&totals[1], cs->d_sb.p + n, 8, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(&totals[2], cs->d_sc.p + n, 8, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
+  CU(nb_stream_sync(ctx, st));
   cs->n_small_tables = n_small;
   const size_t need = (size_t)totals[0] * 16 + (size_t)totals[1] * 4 + (size_t)totals[2] * 16;
   if (need > ((size_t)96 << 30))
@@ -1038,7 +1041,7 @@ int ngmlr_b200_cs_run(ngmlr_b200_ctx* ctx, float sensitivity, float min_kmer_hit
   CU(cs_exclusive_scan(cs->d_scan_tmp.p, tb, cs->d_cnt64.p, cs->d_cstart.p, (int)n1, st));
   unsigned long long m64 = 0;
   CU(cudaMemcpyAsync(&m64, cs->d_cstart.p + n, 8, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
+  CU(nb_stream_sync(ctx, st));
   const size_t m = (size_t)m64;
   if (m > 0x7fffffffull) return ctx->fail("cs_run: %zu candidates in one batch; use smaller batches", m);
   cs->n_cand = (long long)m;
@@ -1077,7 +1080,7 @@ int ngmlr_b200_cs_run(ngmlr_b200_ctx* ctx, float sensitivity, float min_kmer_hit
     CU(launch_sw_score_gather(sp, grid, st));
   }
   CU(cudaEventRecord(cs->ev1, st));
-  CU(cudaStreamSynchronize(st));
+  CU(nb_stream_sync(ctx, st));
   if (n_candidates) *n_candidates = (int64_t)m;
   if (kernel_ms) cudaEventElapsedTime(kernel_ms, cs->ev0, cs->ev1);
   return 0;
@@ -1107,7 +1110,7 @@ int ngmlr_b200_cs_fetch(ngmlr_b200_ctx* ctx, int64_t* cand_start, const float** 
     CU(cudaMemcpyAsync(cs->p_rev.p, cs->d_rev.p, m, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(cs->p_sw.p, cs->d_sw.p, m * 4, cudaMemcpyDeviceToHost, st));
   }
-  CU(cudaStreamSynchronize(st));
+  CU(nb_stream_sync(ctx, st));
   *cs_scores = cs->p_score.p;
   *locs = cs->p_loc.p;
   *reverse = cs->p_rev.p;

@@ -354,7 +354,7 @@ int convex_upload_spec(ngmlr_b200_ctx* ctx, const UploadSpec& sp) {
   CU(cudaMemcpyAsync(ctx->d_desc.p, ctx->h_desc.p, (size_t)n * sizeof(AlnDesc), cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(ctx->d_order.p, ctx->h_order.p, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   h2d += (size_t)n * (sizeof(AlnDesc) + 4);
-  CU(cudaStreamSynchronize(st));
+  CU(nb_stream_sync(ctx, st));
   ctx->stats = ngmlr_b200_batch_stats();
   ctx->stats.host_pack_ms = (float)(t_pack1 - t_pack0);
   ctx->stats.host_h2d_ms = (float)(now_ms() - t_pack1);
@@ -541,7 +541,7 @@ int ngmlr_b200_convex_run(ngmlr_b200_ctx* ctx) {
     }
     CU(cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, 8 * sizeof(unsigned long long),
                        cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(nb_stream_sync(ctx, st));
     bool again = false;
     if (need_fill) {
       const unsigned long long dir_used = ctx->h_counters.p[0], runs_used = ctx->h_counters.p[1];
@@ -624,7 +624,7 @@ int fetch_device_text(ngmlr_b200_ctx* ctx, ngmlr_b200_align_result* results) {
   if (ctx->nm_used)
     CU(cudaMemcpyAsync(ctx->h_nm[slot].p, ctx->d_nm.p, (size_t)ctx->nm_used * sizeof(int32_t),
                        cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
+  CU(nb_stream_sync(ctx, st));
   const double t_f1 = now_ms();
   ctx->stats.d2h_bytes = (int64_t)((size_t)n * (sizeof(FillOut) + sizeof(TraceOut) + sizeof(TextOut)) +
                                    ctx->text_used + ctx->peaks_used * sizeof(int4) + ctx->nm_used * 4);
@@ -710,7 +710,7 @@ int ngmlr_b200_convex_fetch(ngmlr_b200_ctx* ctx, ngmlr_b200_align_result* result
     extra_d2h = (int64_t)ctx->seq_bytes;
     ctx->ref_on_host = true;
   }
-  CU(cudaStreamSynchronize(st));
+  CU(nb_stream_sync(ctx, st));
   const double t_f1 = now_ms();
   ctx->stats.d2h_bytes = (int64_t)((size_t)n * (sizeof(FillOut) + sizeof(TraceOut)) + ctx->runs_used * 4) +
                          ctx->upload_d2h_bytes + extra_d2h;

@@ -6,10 +6,16 @@
 
 namespace nb {
 
-constexpr int FILL_WARPS_PER_CTA = 4;
-constexpr int FILL_CTAS_PER_SM = 5;
+#ifndef FILL_WARPS_OVERRIDE
+#define FILL_WARPS_OVERRIDE 4
+#endif
+#ifndef FILL_CTAS_OVERRIDE
+#define FILL_CTAS_OVERRIDE 5
+#endif
+constexpr int FILL_WARPS_PER_CTA = FILL_WARPS_OVERRIDE;  // warps per CTA = team size of the ordinary team kernel
+constexpr int FILL_CTAS_PER_SM = FILL_CTAS_OVERRIDE;
 #ifndef FILL_TEAM_CTAS_PER_SM
-#define FILL_TEAM_CTAS_PER_SM 6  // the 4-warp team kernel needs 80 registers: 6 CTAs = 24 warps per SM
+#define FILL_TEAM_CTAS_PER_SM (FILL_CTAS_OVERRIDE + (FILL_WARPS_OVERRIDE == 4 ? 1 : 0))  // 4-warp teams: 80 registers, 6 CTAs = 24 warps per SM
 #endif
 constexpr int FILL_BIG_TEAM = 16;  // warps that pipeline one huge matrix (one CTA per SM)
 

@@ -248,7 +248,7 @@ int ngmlr_b200_reads_upload(ngmlr_b200_ctx* ctx, int n_reads, const char* const*
     CU(cudaMemcpyAsync(cs->d_off.p, soff, n_sub * 8, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(cs->d_len.p, slen, n_sub * 4, cudaMemcpyHostToDevice, st));
   }
-  CU(cudaStreamSynchronize(st));
+  CU(nb_stream_sync(ctx, st));
   ctx->n_reads = n_reads;
   ctx->reads_bytes = bytes;
   // stage 0/2 now runs on the sub-reads of the resident set (ngmlr_b200_cs_run / cs_fetch)

@@ -184,6 +184,8 @@ struct ngmlr_b200_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;   // the big-team fill launch runs beside the ordinary one
   cudaEvent_t ev_big = nullptr;
+  cudaEvent_t ev_sync = nullptr;    // cudaEventBlockingSync: waiting host threads sleep instead of spinning
+  bool spin_sync = false;           // NGMLR_B200_SPIN_SYNC=1: cudaStreamSynchronize (lowest latency, one busy CPU per waiter)
   unsigned long long big_cells = 8ull << 20;  // a problem is "big" from this many cells ...
   int big_width = 768;                        // ... in a corridor at least this wide
   int n_big = 0;                    // leading problems of the order that get FILL_BIG_TEAM-warp teams
@@ -293,6 +295,16 @@ struct ngmlr_b200_ctx {
     return -1;
   }
 };
+
+// Wait for the context's stream. By default the waiting thread SLEEPS (event with cudaEventBlockingSync): a process
+// drives several contexts per GPU from as many host threads, and on the multi-GPU boxes all ranks share one CPU quota --
+// spinning waiters would take it away from the threads that have host work to do.
+inline cudaError_t nb_stream_sync(ngmlr_b200_ctx* ctx, cudaStream_t st) {
+  if (ctx->spin_sync || !ctx->ev_sync) return cudaStreamSynchronize(st);
+  cudaError_t e = cudaEventRecord(ctx->ev_sync, st);
+  if (e != cudaSuccess) return e;
+  return cudaEventSynchronize(ctx->ev_sync);
+}
 
 #define CU(call)                                                                          \
   do {                                                                                    \
