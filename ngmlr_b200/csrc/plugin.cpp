@@ -63,6 +63,35 @@ struct PluginStats {
   }
 } g_stats;
 
+// fn(i) for i in [0, n) on a few host threads (the per-problem copies of a big BatchAlign: CorridorLine[] in,
+// nmPerPosition out -- 12 bytes per alignment column into the caller's buffers)
+template <typename F>
+void plugin_parallel_for(int n, int chunk, F fn) {
+  static const int max_threads = [] {
+    const char* e = getenv("NGMLR_B200_HOST_THREADS");
+    const int v = e ? atoi(e) : 0;
+    return v > 0 ? v : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+  }();
+  const int threads = std::min(max_threads, (n + chunk - 1) / chunk);
+  if (threads <= 1) {
+    for (int i = 0; i < n; ++i) fn(i);
+    return;
+  }
+  std::atomic<int> next(0);
+  auto work = [&]() {
+    for (;;) {
+      const int b = next.fetch_add(chunk);
+      if (b >= n) break;
+      const int e = std::min(n, b + chunk);
+      for (int i = b; i < e; ++i) fn(i);
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < threads; ++t) pool.emplace_back(work);
+  work();
+  for (auto& t : pool) t.join();
+}
+
 bool same_scoring(const ngmlr_b200_scoring& a, const ngmlr_b200_scoring& b) {
   return memcmp(&a, &b, sizeof(a)) == 0;
 }
@@ -216,7 +245,7 @@ class B200Alignment : public IAlignment {
       qe_[i] = args[i].externalQEnd;
       if (args[i].corridorHeight < qry_len_[i]) throw "corridorHeight < read length";
     }
-    for (int i = 0; i < n; ++i) {
+    plugin_parallel_for(n, 16, [&](int i) {
       // matrix->prepare(): rows = qryLen; also publishes offsetInMatrix to the caller's lines
       // (src/AlignmentMatrixFast.cpp:36-43)
       CorridorLine* c = args[i].corridor;
@@ -229,7 +258,7 @@ class B200Alignment : public IAlignment {
       // prepare() refuses matrices of >= maxMatrixSizeMB MB -> the alignment fails (:45-58); such a
       // problem never reaches the device
       too_big[i] = (unsigned long)((float)at / 1000.0f / 1000.0f) >= max_matrix_mb_;
-    }
+    });
     // the problems that go to the device, in order
     keep_.clear();
     for (int i = 0; i < n; ++i)
@@ -248,7 +277,7 @@ class B200Alignment : public IAlignment {
     row_start_[m] = (int64_t)rows;
     off_.resize(rows);
     len_.resize(rows);
-    for (int j = 0; j < m; ++j) {
+    plugin_parallel_for(m, 16, [&](int j) {
       const int i = keep_[j];
       CorridorLine* c = args[i].corridor;
       int32_t* o = off_.data() + row_start_[j];
@@ -257,7 +286,7 @@ class B200Alignment : public IAlignment {
         o[y] = c[y].offset;
         l[y] = c[y].length;
       }
-    }
+    });
     res_.resize((size_t)std::max(m, 1));
     for (int i = 0; i < n; ++i) {
       results[i]->svType = 0;  // (:454-457)
@@ -291,23 +320,21 @@ class B200Alignment : public IAlignment {
       }
     }
     const auto t_copy0 = std::chrono::steady_clock::now();
-    bool threw = false;
-    for (int j = 0; j < m; ++j) {
+    std::vector<char> threw_j((size_t)std::max(m, 1), 0);
+    plugin_parallel_for(m, 16, [&](int j) {
       const int i = keep_[j];
       const ngmlr_b200_align_result& r = res_[j];
       Align& a = *results[i];
       if (a.pBuffer2) a.pBuffer2[0] = '\0';  // (:469)
       if (r.threw) {
-        threw = true;
-        if (threw_out) threw_out[i] = true;
-        continue;
+        threw_j[j] = 1;
+        return;
       }
-      if (r.ret < 0) continue;
+      if (r.ret < 0) return;
       // caller-owned buffers; grow MD / nmPerPosition like checkMdBufferLength / addPosition do
       if (r.cigar_len + 1 > a.maxBufferLength || !a.pBuffer1) {
-        threw = true;  // "CIGAR/MD buffer not long enough" -> throw 1 (:289-294)
-        if (threw_out) threw_out[i] = true;
-        continue;
+        threw_j[j] = 1;  // "CIGAR/MD buffer not long enough" -> throw 1 (:289-294)
+        return;
       }
       memcpy(a.pBuffer1, r.cigar, (size_t)r.cigar_len + 1);
       if (r.md_len + 1 > a.maxMdBufferLength || !a.pBuffer2) {
@@ -344,7 +371,13 @@ class B200Alignment : public IAlignment {
       a.Score = r.score;
       a.svType = r.sv_type;
       rets[i] = r.ret;
-    }
+    });
+    bool threw = false;
+    for (int j = 0; j < m; ++j)
+      if (threw_j[j]) {
+        threw = true;
+        if (threw_out) threw_out[keep_[j]] = true;
+      }
     g_stats.us_copy += std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_copy0).count();
     if (threw && n == 1 && !threw_out) throw 1;  // caller wraps SingleAlign in try/catch(...) -> unmapped
   }
