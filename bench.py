@@ -491,6 +491,8 @@ def main():
     ap.add_argument("--reads", type=int, default=8192, help="reads per step per GPU")
     ap.add_argument("--genome-mb", type=float, default=0.0, help="reference size (0 = the config's)")
     ap.add_argument("--dp-only", action="store_true", help="time stage 4 (convex alignment) alone")
+    ap.add_argument("--stagger-ms", type=float, default=0.0,
+                    help="device-resident leg: context j starts j x this many ms after context 0 (inside the timed region)")
     ap.add_argument("--contexts", type=int, default=4, help="aligner contexts (host threads/streams) per GPU")
     ap.add_argument("--fill-ctas", type=int, default=4,
                     help="fill CTAs per SM per launch in the concurrent phases (0 = full occupancy; the solo "
@@ -593,7 +595,7 @@ def main():
     # hides the tail of each fill launch and the traceback behind another context's fill, and (end to
     # end) the host side of one slice behind the kernels of the others.
     S = max(1, args.contexts)
-    streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
+    streams = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(S)]  # outrank the fill launches
     als = [B200Aligner(local_rank, stream=st_.cuda_stream) for st_ in streams]
     al = als[0]
     # one copy of the encoded reference per GPU; the k-mer index is built from it ON the device
@@ -685,6 +687,8 @@ def main():
     ends = [torch.cuda.Event() for _ in range(S)]
 
     def dev_worker(j):
+        if args.stagger_ms > 0:
+            time.sleep(j * args.stagger_ms * 1e-3)
         for _ in range(args.steps):
             if not args.dp_only:
                 als[j].cs_run()

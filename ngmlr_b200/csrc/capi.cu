@@ -88,8 +88,15 @@ int ngmlr_b200_create(int gpu_id, const ngmlr_b200_scoring* s, ngmlr_b200_ctx** 
     delete ctx;
     return -1;
   }
-  cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
-  cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+  int prio_least = 0, prio_greatest = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+  // the context's stream (candidate search, traceback, text, copies) outranks its fill launches
+  cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_greatest);
+  cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_least);
+  cudaStreamCreateWithPriority(&ctx->stream_fill, cudaStreamNonBlocking, prio_least);
+  cudaEventCreateWithFlags(&ctx->ev_fill, cudaEventDisableTiming);
+  if (const char* e = getenv("NGMLR_B200_FILL_PERSISTENT")) ctx->fill_persistent = atoi(e);
+  if (const char* e = getenv("NGMLR_B200_FILL_RESIDENT")) ctx->fill_resident = std::max(0, atoi(e));
   cudaEventCreateWithFlags(&ctx->ev_big, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventDisableTiming | cudaEventBlockingSync);
   if (const char* e = getenv("NGMLR_B200_SPIN_SYNC")) ctx->spin_sync = atoi(e) != 0;
@@ -130,6 +137,8 @@ void ngmlr_b200_destroy(ngmlr_b200_ctx* ctx) {
   if (ctx->ev_big) cudaEventDestroy(ctx->ev_big);
   if (ctx->ev_sync) cudaEventDestroy(ctx->ev_sync);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+  if (ctx->stream_fill) cudaStreamDestroy(ctx->stream_fill);
+  if (ctx->ev_fill) cudaEventDestroy(ctx->ev_fill);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -143,7 +152,9 @@ int ngmlr_b200_set_stream(ngmlr_b200_ctx* ctx, void* s) {
     ctx->stream = (cudaStream_t)s;
     ctx->own_stream = false;
   } else {
-    cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    int prio_least = 0, prio_greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_greatest);
     ctx->own_stream = true;
   }
   return 0;

@@ -108,7 +108,7 @@ struct TeamBest {
 // CTA is the team: 4 warps for ordinary corridors, FILL_BIG_TEAM warps for the few huge matrices of a batch
 // -- a 10^8-cell realignment matrix would otherwise keep one 4-warp team busy long after the rest of the
 // grid has drained).
-template <bool RAW, int NW>
+template <bool RAW, int NW, bool PERSIST>
 __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS_PER_CTA : NW) * 32,
                                   NW > FILL_WARPS_PER_CTA ? 1 : (NW == 1 ? FILL_CTAS_PER_SM : FILL_TEAM_CTAS_PER_SM))
 convex_fill_kernel(const FillParams p) {
@@ -119,12 +119,34 @@ convex_fill_kernel(const FillParams p) {
   // s_io[w][2 * j + 1] = what lane 31 produced at step j (one base register + immediates serve both)
   __shared__ uint4 s_io[WARPS][2 * (CHUNK + 1)];  // +1: lane 31 reads one record ahead
   __shared__ volatile unsigned long long s_prog[WARPS];
-  __shared__ int s_work;
+  __shared__ int s_work, s_slot;
   __shared__ TeamBest s_best[WARPS];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int tw = NW == 1 ? 0 : wib;  // warp index within the team
-  const int team_global = NW == 1 ? blockIdx.x * WARPS + wib : blockIdx.x;
+  // Boundary strips: a persistent launch (grid capped, every CTA loops over problems) owns strip blockIdx.x. A
+  // launch of short-lived CTAs (one problem each, so that SM slots keep coming free for the other kernels of the
+  // step) takes one of p.sm_slot_count strips of the SM it happens to run on and gives it back when it exits; a
+  // CTA that finds them all taken (registers would let one more team in than the kernel runs best with: more
+  // strips competing for L2) sleeps until one is returned.
+  unsigned smid = 0, slot_bit = 0;
+  if (!PERSIST) {
+    if (threadIdx.x == 0) {
+      asm("mov.u32 %0, %%smid;" : "=r"(smid));
+      int got = -1;
+      for (;;) {
+        for (int b = 0; b < p.sm_slot_count && got < 0; ++b)
+          if (!(atomicOr(p.sm_slots + smid, 1u << b) & (1u << b))) got = b;
+        if (got >= 0) break;
+        __nanosleep(2000);
+      }
+      slot_bit = 1u << got;
+      s_slot = (int)smid * FILL_SM_SLOTS + got;
+    }
+    __syncthreads();
+  }
+  const int cta_slot = PERSIST ? (int)blockIdx.x : s_slot;
+  const int team_global = NW == 1 ? cta_slot * WARPS + wib : cta_slot;
   uint4* const io_s = s_io[wib];
   // strip[x + STRIP_PAD] = {S, U, run, ref byte} of column x of the most recently finished bottom row
   uint4* const strip = reinterpret_cast<uint4*>(p.bnd) + (size_t)team_global * p.bnd_stride + STRIP_PAD;
@@ -134,7 +156,10 @@ convex_fill_kernel(const FillParams p) {
   const bool is0 = lane == 0, is31 = lane == 31;
   const int src_lane = (lane + 31) & 31;  // rotate: lane 0 receives what lane 31 staged for it
 
-  for (;;) {
+  // A short-lived CTA takes p.problems_per_cta (= 1) problems per warp / team. The bound is a kernel parameter on
+  // purpose: with a literal 1 the compiler peels the loop away and allocates registers for straight-line code,
+  // which runs slower than the loop form the kernel was tuned in.
+  for (int taken = 0; PERSIST || taken < p.problems_per_cta; ++taken) {
     int w = 0;
     if (NW == 1) {
       if (is0) w = atomicAdd(p.work_counter, 1);
@@ -518,26 +543,39 @@ convex_fill_kernel(const FillParams p) {
       p.out[ai] = o;
     }
   }
+  if (!PERSIST) {
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAnd(p.sm_slots + smid, ~slot_bit);
+  }
 }
 
 }  // namespace
 
+namespace {
+template <bool RAW, int NW>
+void launch_fill(const FillParams& p, int grid, cudaStream_t stream) {
+  const int threads = (NW == 1 ? FILL_WARPS_PER_CTA : NW) * 32;
+  if (p.sm_slots) convex_fill_kernel<RAW, NW, false><<<grid, threads, 0, stream>>>(p);
+  else convex_fill_kernel<RAW, NW, true><<<grid, threads, 0, stream>>>(p);
+}
+}  // namespace
+
+// p.sm_slots != nullptr selects the short-lived-CTA instantiation (one problem per warp / team, strips by SM slot)
 cudaError_t launch_convex_fill(const FillParams& p, bool raw, bool team, int grid, cudaStream_t stream) {
-  const int threads = FILL_WARPS_PER_CTA * 32;
   if (raw) {
-    if (team) convex_fill_kernel<true, FILL_WARPS_PER_CTA><<<grid, threads, 0, stream>>>(p);
-    else convex_fill_kernel<true, 1><<<grid, threads, 0, stream>>>(p);
+    if (team) launch_fill<true, FILL_WARPS_PER_CTA>(p, grid, stream);
+    else launch_fill<true, 1>(p, grid, stream);
   } else {
-    if (team) convex_fill_kernel<false, FILL_WARPS_PER_CTA><<<grid, threads, 0, stream>>>(p);
-    else convex_fill_kernel<false, 1><<<grid, threads, 0, stream>>>(p);
+    if (team) launch_fill<false, FILL_WARPS_PER_CTA>(p, grid, stream);
+    else launch_fill<false, 1>(p, grid, stream);
   }
   return cudaGetLastError();
 }
 
 cudaError_t launch_convex_fill_big(const FillParams& p, bool raw, int grid, cudaStream_t stream) {
   const int threads = FILL_BIG_TEAM * 32;
-  if (raw) convex_fill_kernel<true, FILL_BIG_TEAM><<<grid, threads, 0, stream>>>(p);
-  else convex_fill_kernel<false, FILL_BIG_TEAM><<<grid, threads, 0, stream>>>(p);
+  if (raw) convex_fill_kernel<true, FILL_BIG_TEAM, true><<<grid, threads, 0, stream>>>(p);
+  else convex_fill_kernel<false, FILL_BIG_TEAM, true><<<grid, threads, 0, stream>>>(p);
   return cudaGetLastError();
 }
 
@@ -545,11 +583,11 @@ int fill_max_ctas_per_sm(bool raw, bool team) {
   int n = 0;
   const int threads = FILL_WARPS_PER_CTA * 32;
   if (raw) {
-    if (team) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, convex_fill_kernel<true, FILL_WARPS_PER_CTA>, threads, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, convex_fill_kernel<true, 1>, threads, 0);
+    if (team) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, convex_fill_kernel<true, FILL_WARPS_PER_CTA, true>, threads, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, convex_fill_kernel<true, 1, true>, threads, 0);
   } else {
-    if (team) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, convex_fill_kernel<false, FILL_WARPS_PER_CTA>, threads, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, convex_fill_kernel<false, 1>, threads, 0);
+    if (team) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, convex_fill_kernel<false, FILL_WARPS_PER_CTA, true>, threads, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, convex_fill_kernel<false, 1, true>, threads, 0);
   }
   return n;
 }

@@ -421,13 +421,27 @@ int ngmlr_b200_convex_run(ngmlr_b200_ctx* ctx) {
   team = team && ctx->team_safe;
   const int variant = (raw ? 1 : 0) | (team ? 2 : 0);
   if (!ctx->ctas_per_sm[variant]) ctx->ctas_per_sm[variant] = std::max(1, fill_max_ctas_per_sm(raw, team));
-  int per_sm = ctx->ctas_per_sm[variant];
+  int per_sm = std::min(ctx->ctas_per_sm[variant], team ? (int)FILL_TEAM_CTAS_PER_SM : (int)FILL_CTAS_PER_SM);
+  if (ctx->fill_resident > 0) per_sm = std::min(per_sm, ctx->fill_resident);
   if (ctx->fill_ctas_cap > 0) per_sm = std::min(per_sm, ctx->fill_ctas_cap);
   const int max_grid = ctx->num_sms * per_sm;
   const int want_grid = team ? n : (n + FILL_WARPS_PER_CTA - 1) / FILL_WARPS_PER_CTA;
-  const int grid = std::max(1, std::min(max_grid, want_grid));
+  // Persistent launch (grid capped at what is resident, CTAs loop over problems) when a cap is set; otherwise
+  // short-lived CTAs -- one problem per team / warp -- on a low-priority stream: SM slots keep coming free, and the
+  // latency-bound kernels of this and the other contexts (candidate search, traceback, text: high-priority
+  // streams) slip in beside the ALU-bound fill instead of queueing behind a grid that never lets go.
+  const bool persistent = ctx->fill_ctas_cap > 0 || ctx->fill_persistent;
+  const int grid = persistent ? std::max(1, std::min(max_grid, want_grid)) : std::max(1, want_grid);
   ctx->fill_grid = grid;
-  const size_t warps = (size_t)grid * FILL_WARPS_PER_CTA;
+  const size_t strips = persistent ? (size_t)grid : (size_t)ctx->num_sms * FILL_SM_SLOTS;
+  const size_t warps = strips * (team ? 1 : FILL_WARPS_PER_CTA);  // a team shares one strip
+  if (!persistent) {
+    CU(ctx->d_sm_slots.reserve((size_t)ctx->num_sms + 8));
+    if (!ctx->sm_slots_zeroed) {
+      CU(cudaMemsetAsync(ctx->d_sm_slots.p, 0, ((size_t)ctx->num_sms + 8) * sizeof(unsigned int), st));
+      ctx->sm_slots_zeroed = true;
+    }
+  }
   const size_t bnd_stride = align_up((size_t)ctx->max_ref_len + STRIP_SLACK, 8);
   // huge matrices: their own launch with FILL_BIG_TEAM-warp teams, concurrent with the rest (second stream)
   int n_big = (ctx->team_safe && ctx->force_team != 0 && !getenv("NGMLR_B200_NO_BIG_TEAMS")) ? ctx->n_big : 0;
@@ -468,6 +482,9 @@ int ngmlr_b200_convex_run(ngmlr_b200_ctx* ctx) {
       fp.n = n;
       fp.first = n_big;
       fp.last = n;
+      fp.sm_slots = persistent ? nullptr : ctx->d_sm_slots.p;
+      fp.sm_slot_count = std::min(per_sm, (int)FILL_SM_SLOTS);
+      fp.problems_per_cta = 1;
       fp.blocks = ctx->d_blocks.p;
       fp.dir = ctx->d_dir.p;
       fp.dir_capacity = ctx->d_dir.cap;
@@ -500,12 +517,25 @@ int ngmlr_b200_convex_run(ngmlr_b200_ctx* ctx) {
         fb.first = 0;
         fb.last = n_big;
         fb.work_counter = reinterpret_cast<int*>(ctx->d_counters.p + 3);
+        fb.sm_slots = nullptr;  // the few huge matrices: one resident 16-warp CTA per SM that loops
+        fb.sm_slot_count = 0;
+        fb.problems_per_cta = 0;
         fb.bnd = ctx->d_bnd.p + warps * bnd_stride;
         CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev[0], 0));
         CU(launch_convex_fill_big(fb, raw, big_grid, ctx->stream2));
         CU(cudaEventRecord(ctx->ev_big, ctx->stream2));
       }
-      if (n - n_big > 0) CU(launch_convex_fill(fp, raw, team, grid, st));
+      if (n - n_big > 0) {
+        const int g = persistent ? grid : std::max(1, team ? n - n_big : (n - n_big + FILL_WARPS_PER_CTA - 1) / FILL_WARPS_PER_CTA);
+        if (persistent || !ctx->stream_fill) {
+          CU(launch_convex_fill(fp, raw, team, g, st));
+        } else {  // on the low-priority stream, between two events of the context's stream
+          CU(cudaStreamWaitEvent(ctx->stream_fill, ctx->ev[0], 0));
+          CU(launch_convex_fill(fp, raw, team, g, ctx->stream_fill));
+          CU(cudaEventRecord(ctx->ev_fill, ctx->stream_fill));
+          CU(cudaStreamWaitEvent(st, ctx->ev_fill, 0));
+        }
+      }
       if (n_big > 0) CU(cudaStreamWaitEvent(st, ctx->ev_big, 0));
       CU(cudaEventRecord(ctx->ev[1], st));
       CU(launch_convex_traceback(tp, st));

@@ -121,6 +121,9 @@ struct FillParams {
   const int32_t* order;   // problem indices, largest first
   int n;
   int first, last;        // this launch works on order[first, last)
+  int problems_per_cta;   // short-lived CTAs: problems a warp / team takes before it exits (1)
+  int sm_slot_count;      // strips per SM (<= FILL_SM_SLOTS) = teams of this launch that run on an SM at a time
+  unsigned int* sm_slots; // non-persistent launches: per-SM bitmask of boundary strips in use (nullptr: strip = blockIdx.x)
   BlockRec* blocks;
   uint32_t* dir;                        // direction arena (32-bit words)
   unsigned long long dir_capacity;      // words

@@ -17,6 +17,7 @@ constexpr int FILL_CTAS_PER_SM = FILL_CTAS_OVERRIDE;
 #ifndef FILL_TEAM_CTAS_PER_SM
 #define FILL_TEAM_CTAS_PER_SM (FILL_CTAS_OVERRIDE + (FILL_WARPS_OVERRIDE == 4 ? 1 : 0))  // 4-warp teams: 80 registers, 6 CTAs = 24 warps per SM
 #endif
+constexpr int FILL_SM_SLOTS = 8;   // boundary strips per SM for launches of short-lived CTAs (>= resident CTAs per SM)
 constexpr int FILL_BIG_TEAM = 16;  // warps that pipeline one huge matrix (one CTA per SM)
 
 // team = all FILL_WARPS_PER_CTA warps of a CTA pipeline one problem; otherwise one warp per problem

@@ -183,6 +183,12 @@ struct ngmlr_b200_ctx {
   int num_sms = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;   // the big-team fill launch runs beside the ordinary one
+  cudaStream_t stream_fill = nullptr;  // lowest priority: the launch of short-lived fill CTAs
+  cudaEvent_t ev_fill = nullptr;
+  int fill_resident = 0;            // NGMLR_B200_FILL_RESIDENT: resident fill CTAs per SM (0 = what the kernel was tuned for)
+  int fill_persistent = 0;          // NGMLR_B200_FILL_PERSISTENT=1: always the capped persistent grid
+  bool sm_slots_zeroed = false;
+  nb::DevBuf<unsigned int> d_sm_slots;
   cudaEvent_t ev_big = nullptr;
   cudaEvent_t ev_sync = nullptr;    // cudaEventBlockingSync: waiting host threads sleep instead of spinning
   bool spin_sync = false;           // NGMLR_B200_SPIN_SYNC=1: cudaStreamSynchronize (lowest latency, one busy CPU per waiter)
