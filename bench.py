@@ -494,9 +494,9 @@ def main():
     ap.add_argument("--stagger-ms", type=float, default=0.0,
                     help="device-resident leg: context j starts j x this many ms after context 0 (inside the timed region)")
     ap.add_argument("--contexts", type=int, default=4, help="aligner contexts (host threads/streams) per GPU")
-    ap.add_argument("--fill-ctas", type=int, default=4,
-                    help="fill CTAs per SM per launch in the concurrent phases (0 = full occupancy; the solo "
-                         "roofline phase always runs at full occupancy)")
+    ap.add_argument("--fill-ctas", type=int, default=0,
+                    help="0 (default): fill launches of short-lived CTAs on a low-priority stream; n > 0: a persistent "
+                         "fill grid of n CTAs per SM per launch in the concurrent phases")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     ap.add_argument("--parity-reads", type=int, default=0, help="reads compared CPU vs GPU (0 = the CPU sample)")
     ap.add_argument("--profile-only", action="store_true",
@@ -662,8 +662,9 @@ def main():
     n_first_valid = sum(1 for r, iv in zip(gpu_first, wl.ivs) if r.ret == len(wl.reads[iv.read]))
 
     # ---- (b) device-resident timed region: every context keeps its slice in HBM, exactly K steps ----
-    # Smaller persistent fill grids per launch so that the launches of the S contexts (and their
-    # memory-bound candidate-search / traceback / text kernels) share the SMs instead of queueing.
+    # By default the fill launches are short-lived CTAs on a low-priority stream, so the latency-bound kernels of
+    # the S contexts (candidate search, traceback, text) and the copies' bookkeeping kernels slip in between;
+    # --fill-ctas n selects a persistent fill grid of n CTAs per SM per launch instead.
     for a_ in als:
         a_.set_fill_ctas_per_sm(args.fill_ctas if S > 1 else 0)
 
@@ -785,7 +786,8 @@ def main():
                        "intervals_per_step_per_gpu": len(wl.ivs),
                        "read_bases_per_step": tot_bases, "dp_cells_per_step": tot_cells,
                        "parallelism": f"read-sharded x{world}, no per-step collective; {S} aligner contexts/GPU, "
-                                      f"fill grid {args.fill_ctas or 'full'} CTAs/SM per launch",
+                                      + (f"persistent fill grid {args.fill_ctas} CTAs/SM per launch" if args.fill_ctas
+                                         else "fill = short-lived CTAs on a low-priority stream"),
                        "l2": "inputs+direction arena per step exceed L2 (direction writes alone "
                              f"{st['dir_bytes'] / 1e6:.0f} MB/step/GPU)",
                        "vs_baseline_note": "e2e (host buffers in, CIGAR/MD text out) / README.md:25 whole-pipeline "
