@@ -111,6 +111,12 @@ void* ngmlr_b200_get_stream(ngmlr_b200_ctx* ctx);
  * reference counterpart. Results do not depend on it. */
 int ngmlr_b200_set_fill_ctas_per_sm(ngmlr_b200_ctx* ctx, int ctas_per_sm);
 
+/* Tuning: a batch of at most one problem per SM (the plugin's SingleAlign batches -- a handful of blocking
+ * callers) is filled by 16-warp teams, one SM per problem, because such a batch is about latency; `on` = 0
+ * keeps the 4-warp teams / one-warp-per-problem kernels for every batch size (also
+ * NGMLR_B200_SMALL_BATCH_BIG_TEAMS=0). Default on. No reference counterpart. Results do not depend on it. */
+int ngmlr_b200_set_small_batch_teams(ngmlr_b200_ctx* ctx, int on);
+
 /* ---- convex banded alignment: IAlignment::SingleAlign(mode, CorridorLine*, ...) batched -------
  * Replaces ConvexAlignFast::SingleAlign (src/ConvexAlignFast.cpp:452-559) for n independent
  * problems. Problem i: refs[i]/qrys[i] are the reference window and read part (need not be

@@ -55,7 +55,7 @@ class Interval(C.Structure):
 C_API_SYMBOLS = (
     "ngmlr_b200_abi_version", "ngmlr_b200_device_count", "ngmlr_b200_create", "ngmlr_b200_destroy",
     "ngmlr_b200_last_error", "ngmlr_b200_set_stream", "ngmlr_b200_get_stream",
-    "ngmlr_b200_set_fill_ctas_per_sm",
+    "ngmlr_b200_set_fill_ctas_per_sm", "ngmlr_b200_set_small_batch_teams",
     "ngmlr_b200_convex_align_batch", "ngmlr_b200_convex_upload", "ngmlr_b200_convex_run",
     "ngmlr_b200_convex_fetch", "ngmlr_b200_convex_stats", "ngmlr_b200_convex_debug_directions",
     "ngmlr_b200_sw_score_batch", "ngmlr_b200_cs_set_index", "ngmlr_b200_cs_search_batch",
@@ -93,6 +93,7 @@ def load():
     lib.ngmlr_b200_set_force_raw.argtypes = [vp, C.c_int]
     lib.ngmlr_b200_set_force_team.argtypes = [vp, C.c_int]
     lib.ngmlr_b200_set_fill_ctas_per_sm.argtypes = [vp, C.c_int]
+    lib.ngmlr_b200_set_small_batch_teams.argtypes = [vp, C.c_int]
     lib.ngmlr_b200_debug_set_arena_words.argtypes = [vp, C.c_longlong]
     lib.ngmlr_b200_debug_set_big_team.argtypes = [vp, C.c_longlong, C.c_int]
     batch = [vp, C.c_int, cpp, i32p, cpp, i32p, i32p, i32p, i64p, i32p, i32p]

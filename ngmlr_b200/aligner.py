@@ -452,6 +452,10 @@ class B200Aligner:
         """Test hook: initial size of the direction arena (-1 = the host's estimate)."""
         self.lib.ngmlr_b200_debug_set_arena_words(self.h, int(words))
 
+    def set_small_batch_teams(self, on):
+        """16-warp teams for batches of at most one problem per SM (default on); see ngmlr_b200_set_small_batch_teams."""
+        self.lib.ngmlr_b200_set_small_batch_teams(self.h, int(bool(on)))
+
     def set_fill_ctas_per_sm(self, v):
         """Cap the persistent fill grid (0 = full occupancy); see ngmlr_b200_set_fill_ctas_per_sm."""
         self.lib.ngmlr_b200_set_fill_ctas_per_sm(self.h, int(v))

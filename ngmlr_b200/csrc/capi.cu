@@ -96,6 +96,7 @@ int ngmlr_b200_create(int gpu_id, const ngmlr_b200_scoring* s, ngmlr_b200_ctx** 
   cudaStreamCreateWithPriority(&ctx->stream_fill, cudaStreamNonBlocking, prio_least);
   cudaEventCreateWithFlags(&ctx->ev_fill, cudaEventDisableTiming);
   if (const char* e = getenv("NGMLR_B200_FILL_PERSISTENT")) ctx->fill_persistent = atoi(e);
+  if (const char* e = getenv("NGMLR_B200_SMALL_BATCH_BIG_TEAMS")) ctx->small_batch_big_teams = atoi(e);
   if (const char* e = getenv("NGMLR_B200_FILL_RESIDENT")) ctx->fill_resident = std::max(0, atoi(e));
   cudaEventCreateWithFlags(&ctx->ev_big, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventDisableTiming | cudaEventBlockingSync);
@@ -176,6 +177,12 @@ int ngmlr_b200_debug_set_arena_words(ngmlr_b200_ctx* ctx, long long words) {
 int ngmlr_b200_set_fill_ctas_per_sm(ngmlr_b200_ctx* ctx, int v) {
   if (!ctx) return -1;
   ctx->fill_ctas_cap = v > 0 ? v : 0;
+  return 0;
+}
+
+int ngmlr_b200_set_small_batch_teams(ngmlr_b200_ctx* ctx, int on) {
+  if (!ctx) return -1;
+  ctx->small_batch_big_teams = on ? 1 : 0;
   return 0;
 }
 

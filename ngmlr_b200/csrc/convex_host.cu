@@ -444,8 +444,12 @@ int ngmlr_b200_convex_run(ngmlr_b200_ctx* ctx) {
   }
   const size_t bnd_stride = align_up((size_t)ctx->max_ref_len + STRIP_SLACK, 8);
   // huge matrices: their own launch with FILL_BIG_TEAM-warp teams, concurrent with the rest (second stream)
-  int n_big = (ctx->team_safe && ctx->force_team != 0 && !getenv("NGMLR_B200_NO_BIG_TEAMS")) ? ctx->n_big : 0;
+  const bool big_ok = ctx->team_safe && ctx->force_team != 0 && !getenv("NGMLR_B200_NO_BIG_TEAMS");
+  int n_big = big_ok ? ctx->n_big : 0;
   if (n_big > 2 * ctx->num_sms && n_big * 2 > n) n_big = 0;  // a batch of huge problems only: 4-warp teams fill the GPU
+  // A batch smaller than the GPU (the plugin's SingleAlign batches: a handful of blocking callers) is latency, not
+  // throughput: every problem gets an SM and a 16-warp team of its own.
+  if (big_ok && n <= ctx->num_sms && ctx->small_batch_big_teams) n_big = n;
   const int big_grid = std::min(n_big, ctx->num_sms);
   CU(ctx->d_bnd.reserve((warps + (size_t)big_grid) * bnd_stride));
   size_t dir_words = std::max(ctx->dir_words_needed, (size_t)4096);

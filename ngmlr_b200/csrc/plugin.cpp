@@ -42,7 +42,10 @@ std::vector<ParkedContext> g_pool;
 // Counters of the cross-thread batchers, printed at exit with NGMLR_B200_STATS=1.
 struct PluginStats {
   std::atomic<long long> align_calls{0}, align_batches{0}, align_problems{0}, align_batch_us{0};
-  std::atomic<long long> score_calls{0}, score_batches{0}, score_pairs{0};
+  std::atomic<long long> score_calls{0}, score_batches{0}, score_pairs{0}, score_batch_us{0};
+  // time the calling threads spent blocked inside the batched calls (summed over threads), microseconds
+  std::atomic<long long> align_wait_us{0}, score_wait_us{0};
+  const std::chrono::steady_clock::time_point t_start = std::chrono::steady_clock::now();
   // phases of the batched SingleAlign launches, microseconds (from ngmlr_b200_convex_stats + the copy back)
   std::atomic<long long> us_pack{0}, us_h2d{0}, us_run{0}, us_fill{0}, us_trace{0}, us_d2h{0}, us_text{0}, us_copy{0};
   ~PluginStats() {
@@ -55,6 +58,13 @@ struct PluginStats {
             align_batches ? 1e-3 * (double)align_batch_us / (double)align_batches : 0.0, score_calls.load(),
             score_batches.load(), score_batches ? (double)score_pairs / (double)score_batches : 0.0);
     const double nb = align_batches ? (double)align_batches : 1.0;
+    fprintf(stderr,
+            "[ngmlr_b200] caller threads blocked: %.2f s in SingleAlign (%.2f ms per call), %.2f s in BatchScore/SingleScore "
+            "(%.2f ms per call; %.2f ms per scoring launch); process lifetime of the plugin %.2f s\n",
+            1e-6 * align_wait_us, align_calls ? 1e-3 * (double)align_wait_us / (double)align_calls : 0.0,
+            1e-6 * score_wait_us, score_calls ? 1e-3 * (double)score_wait_us / (double)score_calls : 0.0,
+            score_batches ? 1e-3 * (double)score_batch_us / (double)score_batches : 0.0,
+            1e-6 * (double)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_start).count());
     fprintf(stderr,
             "[ngmlr_b200] per SingleAlign batch (ms): pack %.2f, H2D %.2f, run %.2f (fill kernel %.2f, traceback kernel "
             "%.2f), D2H %.2f, CIGAR/MD/nmPerPosition text %.2f, copy into the callers' Align %.2f\n",
@@ -198,7 +208,10 @@ class B200Alignment : public IAlignment {
       req.result = &result;
       req.args = a;
       g_stats.align_calls++;
-      if (batcher_submit(gpu_id_, scoring_, req)) {  // false: batching is off -> direct path below
+      const auto t_w0 = std::chrono::steady_clock::now();
+      const bool batched = batcher_submit(gpu_id_, scoring_, req);
+      g_stats.align_wait_us += std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_w0).count();
+      if (batched) {  // false: batching is off -> direct path below
         if (req.failed) {
           thread_error() = req.error;
           throw thread_error().c_str();
@@ -586,6 +599,7 @@ class ScoreBatcher {
       out.assign(refs.size(), -1.0f);
       bool failed = false;
       std::string error;
+      const auto t_s0 = std::chrono::steady_clock::now();
       try {
         server_->score_direct((int)refs.size(), refs.data(), qrys.data(), out.data());
       } catch (const char* e) {
@@ -597,6 +611,7 @@ class ScoreBatcher {
       }
       g_stats.score_batches++;
       g_stats.score_pairs += (long long)refs.size();
+      g_stats.score_batch_us += std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_s0).count();
       {
         std::lock_guard<std::mutex> lk(m_);
         size_t at = 0;
@@ -641,7 +656,9 @@ bool score_batcher_submit(int gpu_id, const ngmlr_b200_scoring& scoring, int n, 
   r.qrys = qrys;
   r.results = results;
   g_stats.score_calls++;
+  const auto t_w0 = std::chrono::steady_clock::now();
   b->submit(r);
+  g_stats.score_wait_us += std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_w0).count();
   if (r.failed) {
     thread_error() = r.error;
     throw thread_error().c_str();

@@ -185,6 +185,7 @@ struct ngmlr_b200_ctx {
   cudaStream_t stream2 = nullptr;   // the big-team fill launch runs beside the ordinary one
   cudaStream_t stream_fill = nullptr;  // lowest priority: the launch of short-lived fill CTAs
   cudaEvent_t ev_fill = nullptr;
+  int small_batch_big_teams = 1;    // NGMLR_B200_SMALL_BATCH_BIG_TEAMS=0: batches of <= num_sms problems keep 4-warp teams
   int fill_resident = 0;            // NGMLR_B200_FILL_RESIDENT: resident fill CTAs per SM (0 = what the kernel was tuned for)
   int fill_persistent = 0;          // NGMLR_B200_FILL_PERSISTENT=1: always the capped persistent grid
   bool sm_slots_zeroed = false;

@@ -11,6 +11,15 @@ from oracle_lib import DEFAULT_SCORING, same_alignment
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=[1, 0], ids=["small-batch-teams", "regular-kernels"])
+def _small_batch_mode(request, aligner):
+    """Every test of this module runs twice: with the default (batches of <= one problem per SM are filled by
+    16-warp teams) and with the regular kernels (4-warp teams / one warp per problem) for every batch size."""
+    aligner.set_small_batch_teams(request.param)
+    yield
+    aligner.set_small_batch_teams(1)
+
+
 def _compare_batch(aligner, oracle, probs, scoring=DEFAULT_SCORING, rule=0, check_dirs=False):
     batch = PackedBatch.from_problems(probs)
     res = aligner.BatchAlign(batch)
