@@ -86,18 +86,25 @@ class Workload:
 
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.proc = None
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -111,16 +118,26 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
             out = ""
-        sm, mx, reasons = [], [], set()
+        import datetime
+        rows = []
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, f, float(f[1]), float(f[2])))
             except ValueError:
                 continue
+        # nvidia-smi is started ahead of the warm-up (it takes a few hundred ms to come up); only the samples taken
+        # between mark_begin() and mark_end() -- the timed region -- count
+        if self.t0 is not None and self.t1 is not None:
+            inside = [r for r in rows if self.t0 - 0.025 <= r[0] <= self.t1 + 0.025]
+            rows = inside or rows[-1:]
+        sm, mx, reasons = [], [], set()
+        for _ts, f, a, b in rows:
+            sm.append(a)
+            mx.append(b)
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
@@ -676,10 +693,11 @@ def main():
                 als[j].cs_run()
             als[j].run()
 
-    run_threads(resident_warm)
     sampler = ClockSampler(local_rank)
-    barrier()
     sampler.start()
+    run_threads(resident_warm)
+    barrier()
+    sampler.mark_begin()
     cur = torch.cuda.current_stream(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(cur)
@@ -701,6 +719,7 @@ def main():
         cur.wait_event(ends[j])
     e1.record(cur)
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop()
     dev_ms = e0.elapsed_time(e1)
 
@@ -771,12 +790,17 @@ def main():
         # 148 SMs x 128 lanes x clock / >= 25 instructions per cell
         issue_bound = 148 * 128 * sm_mhz * 1e6 / 25.0
         traffic = None
+        alu_ops = None
         try:  # DRAM bytes of one fill launch from the committed ncu capture (same workload only)
             tr = json.load(open(os.path.join(ROOT, "profiles", "fill_traffic.json")))
             if tr.get("reads_per_step") == args.reads and tr.get("config", "pacbio50") == args.config:
                 traffic = tr["dram_bytes_per_launch"]
+            alu_ops = tr.get("alu_pipe_lane_ops_per_cell")   # a property of the kernel's code, not of the batch
         except Exception:
             pass
+        # the pipe that binds: compares / selects / min-max run on the ALU pipe only, 16 lanes per
+        # clock and SM sub-partition; ops per cell from the same ncu capture
+        alu_bound = 148 * 4 * 16 * sm_mhz * 1e6 / alu_ops if alu_ops else None
         line = {
             "metric": "aligned_gbp_per_s", "value": value, "unit": "Gbp/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
@@ -802,6 +826,8 @@ def main():
                          "gcells_per_s_kernel": cells / fill_s / 1e9,
                          "issue_bound_gcells_per_s": issue_bound / 1e9,
                          "frac_of_issue_bound": cells / fill_s / issue_bound,
+                         "alu_pipe_bound_gcells_per_s": alu_bound / 1e9 if alu_bound else None,
+                         "frac_of_alu_pipe_bound": cells / fill_s / alu_bound if alu_bound else None,
                          "note": "integer/float DP: instruction-issue bound (SURVEY 8(d): 148 SMs x 128 lanes x clock / "
                                  "25 instructions per cell), not HBM bound; the HBM fraction is structurally ~0.02"},
             "kernel_ms_per_step": {"fill": float(np.mean(fill_ms)), "traceback": float(np.mean(tb_ms)),
