@@ -477,16 +477,21 @@ def integrated_run(wl_cfg, genome, contig_len, n_contigs, enc_ref, index, n_read
                                                                      "NGMLR_B200_STATS": "1"})):
             sam = os.path.join(d, name + ".sam")
             env = dict(os.environ, NGMLR_B200_LIB=os.path.join(ROOT, "ngmlr_b200", "libngmlr_b200.so"), **extra)
+            import resource
+            ru0 = resource.getrusage(resource.RUSAGE_CHILDREN)
             t0 = time.perf_counter()
             r = subprocess.run([exe, "-r", ref, "-q", fq, "-o", sam, "-t", str(t), "--no-progress"],
                                capture_output=True, text=True, env=env, timeout=1800)
             wall = time.perf_counter() - t0
+            ru1 = resource.getrusage(resource.RUSAGE_CHILDREN)
+            cpu_s = (ru1.ru_utime - ru0.ru_utime) + (ru1.ru_stime - ru0.ru_stime)
             if r.returncode != 0:
                 return {"unavailable": f"{name} run failed: {r.stderr[-300:]}"}
             built = "Building reference index" in r.stderr or "Building reference index" in r.stdout
             sams[name] = sorted(ln for ln in open(sam) if not ln.startswith("@"))
             stats = [ln for ln in r.stderr.splitlines() if ln.startswith("[ngmlr_b200]")]
-            out[name] = {"threads": t, "wall_s": wall, "gbp_per_s": bases / wall / 1e9, "built_its_own_index": built,
+            out[name] = {"threads": t, "wall_s": wall, "cpu_s": cpu_s, "gbp_per_s": bases / wall / 1e9,
+                         "built_its_own_index": built,
                          "env": extra, "plugin_stats": stats or None}
         out["sam_identical"] = sams["cpu"] == sams["b200"]
         out["sam_records"] = len(sams["cpu"])

@@ -361,8 +361,8 @@ convex_fill_kernel(const FillParams p) {
               const float nS = __uint_as_float(v.x), nU = __uint_as_float(v.y);
               const uint32_t r = v.w;
               const bool act = ALL_ACTIVE ? true : ((unsigned)rel < rlen);
-              const float sub = (r == q) ? sc.mat : sc.mis;
-              const float dg = __fadd_rn(dS, sub);
+              float dg = __fadd_rn(dS, sc.mis);
+              if (r == q) dg = __fadd_rn(dS, sc.mat);
               dS = nS;
               // Outside the corridor the cell must degenerate to {0, 0, STOP}: a NaN maximum makes every
               // equality below false, and fmaxf(NaN, 0) = 0 gives the score.
@@ -409,18 +409,25 @@ convex_fill_kernel(const FillParams p) {
                 const bool X = (eU & ur) | eG;  // bitwise on purpose: straight PLOP3s, no short-circuit
                 const bool pD = eL & (lr | !X);
                 const bool pI = (!pD) & eU & (ur | !eG);
-                code = pD ? DIR_D : (pI ? DIR_I : (eG ? DIR_DIAG : DIR_STOP));
+                code = eG ? DIR_DIAG : DIR_STOP;
+                if (pI) asm volatile("mad.lo.u32 %0, %1, 0, 1;" : "=r"(code) : "r"(code));
+                if (pD) asm volatile("mad.lo.u32 %0, %1, 0, 2;" : "=r"(code) : "r"(code));
                 // at most one of the two run counters is alive after this cell
-                const float newD = pD ? __fadd_rn(lRunF, 1.0f) : 0.0f;
-                const float newI = pI ? __fadd_rn(upRunF, 1.0f) : 0.0f;
+                // "zero, then an addition under the predicate" instead of add + select: the selects, compares and
+                // min/max of this loop all go through the half-rate ALU pipe, which is what binds the kernel; a
+                // predicated FADD runs on the FMA pipe (same for dg above and U / L below)
+                float newD = 0.0f, newI = 0.0f;
+                if (pD) asm volatile("add.rn.f32 %0, %1, 0f3F800000;" : "=f"(newD) : "f"(lRunF));
+                if (pI) asm volatile("add.rn.f32 %0, %1, 0f3F800000;" : "=f"(newI) : "f"(upRunF));
                 const float runF = __fadd_rn(newD, newI);
                 const float pen = fminf(sc.ext_min, __fadd_rn(sc.gap_ext, __fmul_rn(runF, sc.decay)));
                 // e = (S == 0) ? 0 : S + pen  as one exact fused op: S + pen * [S != 0]
                 float nz;
                 asm("set.ne.f32.f32 %0, %1, 0f00000000;" : "=f"(nz) : "f"(S));
-                const float e = __fmaf_rn(pen, nz, S);
-                U = pI ? e : __fadd_rn(S, sc.open_read);
-                L = pD ? e : __fadd_rn(S, sc.open_ref);
+                U = __fadd_rn(S, sc.open_read);
+                L = __fadd_rn(S, sc.open_ref);
+                if (pI) asm volatile("fma.rn.f32 %0, %1, %2, %3;" : "=f"(U) : "f"(pen), "f"(nz), "f"(S));
+                if (pD) asm volatile("fma.rn.f32 %0, %1, %2, %3;" : "=f"(L) : "f"(pen), "f"(nz), "f"(S));
                 oP = __float_as_uint(newI);
                 lRunF = newD;
                 lIsD = pD;
@@ -430,8 +437,9 @@ convex_fill_kernel(const FillParams p) {
               oC = r;
               lL = L;
               if (S > kS) {  // strict: first maximum in row-major order (:1165-1170)
-                kS = S;
-                kStep = s;
+                // S + 0 == S bit for bit (S >= +0); as predicated FMA-pipe instructions instead of two selects
+                asm volatile("add.rn.f32 %0, %1, 0f00000000;" : "=f"(kS) : "f"(S));
+                asm volatile("mad.lo.s32 %0, %1, 1, 0;" : "=r"(kStep) : "r"(s));
               }
               dw = __funnelshift_r(dw, code, 2);
 #if FILL_LANE0_LDS
