@@ -66,6 +66,17 @@ __device__ __forceinline__ void st_strip(uint4* p, uint4 v) { __stcg(p, v); }
 // (fence.acq_rel.cta instead of the sequentially consistent fence measured no difference)
 __device__ __forceinline__ void team_fence() { __threadfence_block(); }
 
+// progress words live in shared memory; plain 32-bit shared addresses (computed once per kernel) instead of the
+// generic-address sequence the compiler emits for a volatile shared array indexed at run time
+__device__ __forceinline__ unsigned long long ld_prog(uint32_t saddr) {
+  unsigned long long v;
+  asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_prog(uint32_t saddr, unsigned long long v) {
+  asm volatile("st.volatile.shared.u64 [%0], %1;" ::"r"(saddr), "l"(v) : "memory");
+}
+
 __device__ __forceinline__ unsigned long long prog_key(int blk, int x) {
   return ((unsigned long long)(unsigned)(blk + 1) << 32) | (unsigned long long)((unsigned)x + X_BIAS);
 }
@@ -155,6 +166,9 @@ convex_fill_kernel(const FillParams p) {
   const uint4 EMPTY = make_uint4(0u, __float_as_uint(sc.open_read), empty_pack, 0u);
   const bool is0 = lane == 0, is31 = lane == 31;
   const int src_lane = (lane + 31) & 31;  // rotate: lane 0 receives what lane 31 staged for it
+  const uint32_t my_prog = (uint32_t)__cvta_generic_to_shared(const_cast<unsigned long long*>(&s_prog[tw]));
+  const uint32_t prev_prog =
+      (uint32_t)__cvta_generic_to_shared(const_cast<unsigned long long*>(&s_prog[(tw + NW - 1) % NW]));
 
   // A short-lived CTA takes p.problems_per_cta (= 1) problems per warp / team. The bound is a kernel parameter on
   // purpose: with a literal 1 the compiler peels the loop away and allocates registers for straight-line code,
@@ -239,7 +253,6 @@ convex_fill_kernel(const FillParams p) {
           whi = wlo + (pg.ngroups << 4);
         }
       }
-      const int prev_tw = (tw + NW - 1) % NW;
       // team mode: block until the producer of block b-1 has flushed strip columns < x_end
       auto wait_for = [&](int x_end) {
         if (NW > 1 && b > 0) {
@@ -247,7 +260,7 @@ convex_fill_kernel(const FillParams p) {
           if (need > wlo) {
             const unsigned long long key = prog_key(b - 1, need);
             if (is0) {
-              while (s_prog[prev_tw] < key) __nanosleep(64);
+              while (ld_prog(prev_prog) < key) __nanosleep(64);
               team_fence();  // acquire on the polling lane, BEFORE the barrier that releases the others
             }
             __syncwarp();
@@ -479,7 +492,7 @@ convex_fill_kernel(const FillParams p) {
           if (NW > 1) {
             team_fence();
             __syncwarp();
-            if (is0) s_prog[tw] = prog_key(b, xo + done);
+            if (is0) st_prog(my_prog, prog_key(b, xo + done));
           }
         }
         __syncwarp();
@@ -494,12 +507,12 @@ convex_fill_kernel(const FillParams p) {
         wlo = base - 31;
         whi = base - 31 + (ngroups << 4);
       } else if (is0) {
-        s_prog[tw] = prog_key(b, (1 << 30));  // block complete
+        st_prog(my_prog, prog_key(b, (1 << 30)));  // block complete
       }
       __syncwarp();
     }
     if (NW > 1) {
-      if (is0) s_prog[tw] = ~0ull;  // also after an arena overflow: never leave a consumer waiting
+      if (is0) st_prog(my_prog, ~0ull);  // also after an arena overflow: never leave a consumer waiting
     }
 
     // first maximum in row-major order across lanes: larger score, then smaller y, then smaller x
