@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define NGMLR_B200_ABI_VERSION 2
+#define NGMLR_B200_ABI_VERSION 3
 
 /* Convex scoring parameters = ConvexAlignFast's constructor arguments
  * (src/ConvexAlignFast.h:20-27, src/ConvexAlignFast.cpp:29-43; CLI defaults src/IConfig.h:23-71):
@@ -342,6 +342,77 @@ int ngmlr_b200_compute_alignments_stats(ngmlr_b200_ctx* ctx, ngmlr_b200_batch_st
  * candidates (MappedRead::mappingQlty). No context: nothing runs on the device. Returns n or -1. */
 int ngmlr_b200_select_candidates(int n, const int64_t* cand_start, const float* sw_scores, int32_t* order,
                                  int32_t* kept, int32_t* mq);
+
+/* ---- SAM text ----------------------------------------------------------
+ * Replaces SAMWriter::DoWriteProlog / DoWriteRead -> DoWriteReadGeneric / DoWriteUnmappedRead
+ * (src/SAMWriter.cpp:22-85, 87-224, 301-363) and the per-read loop of GenericReadWriter::WriteRead
+ * (src/GenericReadWriter.h:78-108) for batches of reads: the records of a batch are sized and then
+ * written by host threads straight into the caller's buffer, in read order. Host code on purpose:
+ * every byte of a SAM record that is not already host resident (CIGAR / MD from the device text
+ * stage) is a few per cent of the record; names, bases and qualities never leave host memory.
+ * Byte-identical with the reference's writer on the same records (tests/test_sam_text.py drives the
+ * unmodified SAMWriter through oracle/_ref/libngmlr_full.so). Paired-end records (DoWritePair) are
+ * not produced by ngmlr's long-read pipeline and are not built. */
+
+/* One alignment of a read = MappedRead::Scores[i] + MappedRead::Alignments[i] as SAMWriter reads them. */
+typedef struct {
+  uint64_t ref_pos;     /* Scores[i].Location.m_Location (0-based on the contig; printed + 1) */
+  int32_t ref_id;       /* index into ref_names (SequenceProvider.GetRefName(getrefId())) */
+  int32_t reverse;      /* Location.isReverse() */
+  float score;          /* Scores[i].Score.f -> AS:i / XE:i as (int) */
+  int32_t mq;           /* Alignments[i].MQ */
+  int32_t nm;           /* Alignments[i].NM */
+  float identity;       /* Alignments[i].Identity -> XI:f as round(x * 10000) / 10000 with %g */
+  int32_t qstart, qend; /* Alignments[i].QStart / QEnd */
+  int32_t sv_type;      /* Alignments[i].svType, printed as SV:i when > -1 */
+  int32_t primary;      /* Alignments[i].primary (flag 0x800 when 0) */
+  int32_t skip;         /* Alignments[i].skip: no record, and left out of the other records' SA:Z */
+  int32_t cigar_ops;    /* Alignments[i].cigarOpCount (only read with bam_cigar_fix) */
+  const char* cigar;    /* Alignments[i].pBuffer1, NUL terminated */
+  const char* md;       /* Alignments[i].pBuffer2, NUL terminated */
+} ngmlr_b200_sam_aln;
+
+/* One read = the MappedRead handed to GenericReadWriter::WriteRead. */
+typedef struct {
+  const char* name;      /* MappedRead::name */
+  const char* seq;       /* MappedRead::Seq, `length` characters; the reverse complement (MappedRead::RevSeq,
+                            src/MappedRead.cpp:37-69: A<->T, C<->G, everything else unchanged) is derived here */
+  const char* qual;      /* MappedRead::qlty: `length` characters; "*" for FASTA input (src/IParser.h:93-95);
+                            NULL = no quality array */
+  int32_t length;        /* MappedRead::length */
+  int32_t n_aln;         /* MappedRead::Calculated (<= 0: unmapped) */
+  int64_t first_aln;     /* alignments [first_aln, first_aln + n_aln) of the alns array */
+  int32_t mapped;        /* the `mapped` argument of WriteRead (0: written as unmapped whatever it holds) */
+  int32_t empty;         /* read->HasFlag(NGMNames::Empty): an unmapped empty read is dropped */
+} ngmlr_b200_sam_read;
+
+typedef struct {
+  int32_t write_unmapped;   /* Config.getWriteUnampped() (default 1) */
+  int32_t bam_cigar_fix;    /* Config.getBamCigarFix(): >= 65536 CIGAR operations -> "<len>S" + CG:B:I tag */
+  /* 0 (default): as coded -- every reverse-strand record of a read reverses the read's quality string in
+   * place (src/SAMWriter.cpp:104-108), so the 2nd, 4th, ... reverse record of a read carries it forward
+   * again. 1: the quality string follows the record's strand. A "*" quality (FASTA) is never reversed in
+   * either mode; the reference reverses `length` bytes of its 2-byte buffer there (heap overflow). */
+  int32_t fix_quality_orientation;
+  int32_t threads;          /* host threads (<= 0: NGMLR_B200_HOST_THREADS / hardware default) */
+  const char* rg_id;        /* Config.getRgId(): RG:Z tag on every record when not NULL */
+} ngmlr_b200_sam_options;
+
+/* @HD / @SQ / @PG / @RG lines (DoWriteProlog). rg_fields: the 11 optional @RG values in the reference's
+ * order SM LB PL DS DT PU PI PG CN FO KS (NULL entries are left out; the line is written only with
+ * opts->rg_id). Returns the number of bytes the header needs; it is written (without NUL) only when that
+ * fits cap. */
+size_t ngmlr_b200_sam_header(int n_refs, const char* const* ref_names, const uint64_t* ref_lens,
+                             const char* version, const char* command_line, const ngmlr_b200_sam_options* opts,
+                             const char* const* rg_fields, char* out, size_t cap);
+
+/* The records of n_reads reads in read order (for each read: its non-skipped alignments in index order,
+ * or one unmapped record). ref_names[i] has ref_name_lens[i] characters (the reference prints "%.*s").
+ * Returns 0 and sets *written; -2 with *written = the bytes needed when cap is too small (nothing is
+ * written then); -1 on invalid arguments. No context: nothing runs on the device. */
+int ngmlr_b200_sam_format(const ngmlr_b200_sam_options* opts, int64_t n_reads, const ngmlr_b200_sam_read* reads,
+                          const ngmlr_b200_sam_aln* alns, int n_refs, const char* const* ref_names,
+                          const int32_t* ref_name_lens, char* out, size_t cap, size_t* written);
 
 #ifdef __cplusplus
 }

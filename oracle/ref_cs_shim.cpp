@@ -149,6 +149,16 @@ int ref_cs_init_save(const char* fasta) {
 
 unsigned long long ref_cs_concat_len() { return SequenceProvider.GetConcatRefLen(); }
 int ref_cs_ref_count() { return SequenceProvider.GetRefCount(); }
+// contig name as SAMWriter prints it ("%.*s" of GetRefName)
+int ref_cs_ref_name(int n, char* buf, int cap) {
+  int len = 0;
+  const char* name = SequenceProvider.GetRefName(n, len);
+  if (len < cap) {
+    memcpy(buf, name, len);
+    buf[len] = 0;
+  }
+  return len;
+}
 unsigned long long ref_cs_ref_start(int n) { return SequenceProvider.GetRefStart(n); }
 unsigned long long ref_cs_ref_len(int n) { return SequenceProvider.GetRefLen(n); }
 
@@ -410,6 +420,119 @@ int ref_stage02_read(void* probe, void* ssw, const char* qry, int len, int part_
     }
   }
   return n_cand;
+}
+
+}  // extern "C"
+
+// ---- SAM writer: the UNMODIFIED SAMWriter / GenericReadWriter::WriteRead driven on records
+// the test makes up; output captured through a FileWriter that appends every flush to a string.
+#include "SAMWriter.h"
+
+namespace {
+
+class CaptureWriter : public FileWriter {
+ public:
+  std::string text;
+
+ protected:
+  void doFlush(int& bufferPosition, int const, char* writeBuffer, bool) override {
+    text.append(writeBuffer, (size_t)bufferPosition);
+    bufferPosition = 0;
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+struct RefSamAln {
+  unsigned long long ref_pos;
+  int ref_id, reverse;
+  float score;
+  int mq, nm;
+  float identity;
+  int qstart, qend, sv_type, primary, skip, cigar_ops;
+  const char* cigar;
+  const char* md;
+};
+
+struct RefSamRead {
+  const char* name;
+  const char* seq;
+  const char* qual;  // NULL: MappedRead::qlty == 0
+  int length, n_aln;
+  long long first_aln;
+  int mapped, empty;
+};
+
+// needs ref_cs_init(fasta) (SequenceProvider holds the contig names). rg_id may be NULL.
+// what = 0: header only, 1: records only. Returns the number of bytes (copied when they fit cap).
+long long ref_sam_write(int what, const RefSamRead* reads, int n_reads, const RefSamAln* alns, int bam_fix,
+                        int write_unmapped, const char* rg_id, const char* const* rg_fields, const char* cmdline,
+                        char* out, long long cap) {
+  IConfig* c = _config;
+  c->bamCigarFix = bam_fix != 0;
+  c->writeUnmapped = write_unmapped != 0;
+  c->rgId = const_cast<char*>(rg_id);
+  char** f[11] = {&c->rgSm, &c->rgLb, &c->rgPl, &c->rgDs, &c->rgDt, &c->rgPu, &c->rgPi, &c->rgPg, &c->rgCn, &c->rgFo, &c->rgKs};
+  for (int k = 0; k < 11; ++k) *f[k] = rg_fields ? const_cast<char*>(rg_fields[k]) : 0;
+  c->fullCommandLineCall = const_cast<char*>(cmdline);
+  CaptureWriter cap_writer;
+  {
+    SAMWriter w(&cap_writer);
+    if (what == 0) {
+      w.WriteProlog();
+    } else {
+      for (int i = 0; i < n_reads; ++i) {
+        const RefSamRead& r = reads[i];
+        MappedRead* read = new MappedRead(i, r.length + 16);
+        strncpy(read->name, r.name, 249);
+        read->name[249] = 0;
+        read->length = r.length;
+        read->Seq = new char[r.length + 16];
+        memset(read->Seq, 0, r.length + 16);
+        memcpy(read->Seq, r.seq, r.length);
+        read->computeReverseSeq();
+        if (r.qual) {
+          const size_t ql = strlen(r.qual);
+          read->qlty = new char[ql + 1];
+          memcpy(read->qlty, r.qual, ql + 1);
+        }
+        if (r.empty) read->SetFlag(NGMNames::Empty);
+        read->Calculated = r.n_aln;
+        if (r.n_aln > 0) {
+          read->Scores = new LocationScore[r.n_aln];
+          read->Alignments = new Align[r.n_aln];
+          for (int j = 0; j < r.n_aln; ++j) {
+            const RefSamAln& a = alns[r.first_aln + j];
+            read->Scores[j].Score.f = a.score;
+            read->Scores[j].Location.m_Location = a.ref_pos;
+            read->Scores[j].Location.setRefId(a.ref_id);
+            read->Scores[j].Location.setReverse(a.reverse != 0);
+            Align& al = read->Alignments[j];
+            al.pBuffer1 = new char[strlen(a.cigar) + 1];
+            strcpy(al.pBuffer1, a.cigar);
+            al.pBuffer2 = new char[strlen(a.md) + 1];
+            strcpy(al.pBuffer2, a.md);
+            al.MQ = a.mq;
+            al.NM = a.nm;
+            al.Identity = a.identity;
+            al.QStart = a.qstart;
+            al.QEnd = a.qend;
+            al.svType = a.sv_type;
+            al.primary = a.primary != 0;
+            al.skip = a.skip != 0;
+            al.cigarOpCount = a.cigar_ops;
+          }
+        }
+        w.WriteRead(read, r.mapped != 0);
+        delete read;
+      }
+    }
+  }  // ~SAMWriter flushes the rest
+  const long long n = (long long)cap_writer.text.size();
+  if (out && n <= cap) memcpy(out, cap_writer.text.data(), (size_t)n);
+  return n;
 }
 
 }  // extern "C"

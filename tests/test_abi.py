@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.C_API_SYMBOLS), declared ^ set(_lib.C_API_SYMBOLS)
     for s in list(declared) + list(_lib.PLUGIN_SYMBOLS):
         assert hasattr(lib, s), s
-    assert lib.ngmlr_b200_abi_version() == 2
+    assert lib.ngmlr_b200_abi_version() == 3
     assert lib.ngmlr_b200_plugin_cookie() == 0x10201130  # cCookie, src/IAlignment.h:193
 
 

@@ -1,0 +1,111 @@
+"""the SAM text entry points (csrc/sam_text.cpp) against the unmodified reference writer.
+CPU tests: the library's record formatter needs no device."""
+import hashlib
+import os
+import subprocess
+import sys
+
+import pytest
+
+import golden_util as gu
+import sam_cases
+from ngmlr_b200 import samtext as st
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FULL = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "libngmlr_full.so")
+GOLD = gu.load("sam_golden.json")
+NAMES = [n.encode() for n in GOLD["ref_names"]]
+
+
+def _ours(name, **kw):
+    opts = dict(sam_cases.CONFIGS)[name]
+    return st.sam_format(sam_cases.config_reads(name), NAMES, write_unmapped=opts["write_unmapped"],
+                         bam_cigar_fix=opts["bam_cigar_fix"], rg_id=opts["rg_id"], **kw)
+
+
+@pytest.mark.parametrize("name", [c[0] for c in sam_cases.CONFIGS])
+def test_records_equal_the_reference_writers_golden_output(name):
+    g = GOLD["configs"][name]
+    text = _ours(name)
+    lines = text.split(b"\n")[:-1]
+    assert len(lines) == len(g["lines"])
+    for i, (l, d) in enumerate(zip(lines, g["lines"])):
+        assert hashlib.sha256(l).hexdigest()[:16] == d, f"{name}: line {i} differs: {l[:200]!r}"
+    assert len(text) == g["bytes"] and hashlib.sha256(text).hexdigest() == g["sha256"]
+
+
+@pytest.mark.parametrize("name", [c[0] for c in sam_cases.CONFIGS])
+def test_header_equals_the_reference_prolog(name):
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    from make_sam_golden import CMDLINE, RG_FIELDS
+    opts = dict(sam_cases.CONFIGS)[name]
+    got = st.sam_header(NAMES, GOLD["ref_lens"], b"0.2.8", CMDLINE, rg_id=opts["rg_id"],
+                        rg_fields=RG_FIELDS if opts["rg_id"] else None)
+    assert got.decode() == GOLD["configs"][name]["header"]
+
+
+@pytest.mark.skipif(not os.path.exists(FULL), reason="oracle/_ref/libngmlr_full.so not built")
+@pytest.mark.parametrize("name", [c[0] for c in sam_cases.CONFIGS])
+def test_records_equal_the_live_reference_writer(name):
+    # the reference keeps singletons (SequenceProvider, Config): its writer runs in a process of its own
+    p = subprocess.run([sys.executable, os.path.join(HERE, "golden", "make_sam_golden.py"), "--dump", name],
+                       capture_output=True, check=True)
+    want = p.stdout
+    got = _ours(name)
+    assert got == want
+
+
+def test_output_does_not_depend_on_the_thread_count():
+    one = _ours("default", threads=1)
+    for t in (2, 3, 7, 32):
+        assert _ours("default", threads=t) == one
+    many = sam_cases.make_reads(5, n_reads=1500)
+    assert st.sam_format(many, NAMES, threads=1) == st.sam_format(many, NAMES, threads=16)
+
+
+def test_small_buffer_reports_the_size_and_writes_nothing():
+    reads = sam_cases.config_reads("default")
+    full = st.sam_format(reads, NAMES)
+    rc, need, text = st.sam_format(reads, NAMES, cap=len(full) - 1)
+    assert (rc, need, text) == (-2, len(full), b"")
+    rc, need, text = st.sam_format(reads, NAMES, cap=len(full))
+    assert rc == 0 and text == full
+    assert st.sam_format([], NAMES) == b""
+
+
+def _aln(reverse, **kw):
+    d = dict(ref_pos=9, ref_id=0, reverse=reverse, score=10.0, mq=60, nm=0, identity=1.0, qstart=0, qend=0,
+             cigar=b"4M", md=b"4")
+    d.update(kw)
+    return st.Alignment(**d)
+
+
+def _quals(text):
+    return [l.split(b"\t")[10] for l in text.split(b"\n")[:-1]]
+
+
+def test_quality_orientation_as_coded_and_fixed():
+    # src/SAMWriter.cpp:104-108 reverses the read's quality string in place for every reverse-strand record
+    r = st.Read(b"q", b"ACGT", b"1234", [_aln(True), _aln(True), _aln(False), _aln(True)])
+    assert _quals(st.sam_format([r], NAMES)) == [b"4321", b"1234", b"1234", b"4321"]
+    assert _quals(st.sam_format([r], NAMES, fix_quality_orientation=True)) == [b"4321", b"4321", b"1234", b"4321"]
+    seqs = [l.split(b"\t")[9] for l in st.sam_format([r], NAMES).split(b"\n")[:-1]]
+    assert seqs == [b"ACGT", b"ACGT", b"ACGT", b"ACGT"]     # its own reverse complement
+    r2 = st.Read(b"q", b"AACGN", b"12345", [_aln(True, cigar=b"5M", md=b"5")])
+    assert st.sam_format([r2], NAMES).split(b"\t")[9:11] == [b"NCGTT", b"54321"]
+
+
+def test_fasta_quality_is_never_reversed():
+    # the reference reverses `length` bytes of the 2-byte "*" buffer here (undefined behaviour); a "*" stays a "*"
+    r = st.Read(b"fa", b"ACGTT", b"*", [_aln(True, cigar=b"5M", md=b"5"), _aln(False, cigar=b"5M", md=b"5")])
+    assert _quals(st.sam_format([r], NAMES)) == [b"*", b"*"]
+
+
+def test_positions_are_truncated_as_the_reference_prints_them():
+    # `m_Location + 1` is 64 bit, printed with %u in the POS column and with %d in SA:Z
+    a = _aln(False, ref_pos=2**32 + 5)
+    b = _aln(False, ref_pos=2**31 + 7, primary=False)
+    lines = st.sam_format([st.Read(b"p", b"ACGT", None, [a, b])], NAMES).split(b"\n")
+    assert lines[0].split(b"\t")[3] == b"6" and lines[1].split(b"\t")[3] == b"%d" % (2**31 + 8)
+    assert b"SA:Z:" + NAMES[0] + b",%d,+,4M,60,0;" % (2**31 + 8 - 2**32) in lines[0]
+    assert lines[1].split(b"\t")[1] == b"2048"
