@@ -433,6 +433,61 @@ def ialignment_batch_align(wl, ivs, gpu_results, steps, gpu_id):
                     "Align buffers out incl. nmPerPosition; one aligner object, one batch in flight"}
 
 
+def sam_text_run(wl, ivs, gpu_results, st02, threads, ref_sample=256):
+    """SURVEY 8(f)4 beside the alignment numbers: the SAM records of the first context's slice (its reads with the
+    CIGAR / MD / NM / identity the device text stage produced for them) formatted by the library's host threads
+    (ngmlr_b200_sam_format), MB of SAM text per second; the unmodified SAMWriter (one thread, as one ngmlr worker
+    runs it) on the first `ref_sample` reads of the same records beside it, and the two texts compared."""
+    from ngmlr_b200 import samtext as st
+    by_read = {}
+    for iv, g in zip(ivs, gpu_results):
+        if g.ret < 0:
+            continue
+        pos = iv.ref_start + g.PositionOffset
+        by_read.setdefault(iv.read, []).append(st.Alignment(
+            ref_pos=int(pos % wl.contig_len), ref_id=int(pos // wl.contig_len), reverse=bool(iv.reverse),
+            score=float(g.Score), mq=60, nm=int(g.NM), identity=float(g.Identity), qstart=int(g.QStart),
+            qend=int(g.QEnd), cigar=g.pBuffer1.encode() if isinstance(g.pBuffer1, str) else bytes(g.pBuffer1),
+            md=g.pBuffer2.encode() if isinstance(g.pBuffer2, str) else bytes(g.pBuffer2), sv_type=int(g.svType),
+            primary=len(by_read.get(iv.read, [])) == 0, cigar_ops=int(g.cigarOpCount)))
+    reads = []
+    for r in sorted(by_read):
+        seq = bytes(wl.reads[r])
+        qual = bytes((33 + (i * 7) % 41) for i in range(64)) * (len(seq) // 64 + 1)
+        reads.append(st.Read(b"read_%d" % r, seq, qual[:len(seq)], by_read[r]))
+    n_contigs = int(wl.genome.size // wl.contig_len)
+    names = [b"c%d" % i for i in range(n_contigs)]
+    packed = st.PackedReads(reads)
+    text = st.sam_format(packed, names, threads=threads)
+    out = {"unit": "MB/s of SAM text", "reads": len(reads), "records": sum(len(r.alignments) for r in reads),
+           "bytes": len(text)}
+    for label, t_ in (("value", threads), ("one_thread", 1)):
+        best = None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            rc, need, _txt = st.sam_format(packed, names, threads=t_, cap=len(text))
+            dt = time.perf_counter() - t0
+            assert rc == 0 and need == len(text)
+            best = dt if best is None else min(best, dt)
+        out[label] = len(text) / best / 1e6
+    out["threads"] = threads
+    if st02 is not None and getattr(st02, "kind", "") == "reference":
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib
+        ref = oracle_lib.SamReference(st02.lib)
+        sample = reads[:ref_sample]
+        pk = ref.pack(sample)
+        want = ref.write(1, pk)
+        t0 = time.perf_counter()
+        ref.write(1, pk, cap=len(want))
+        dt = time.perf_counter() - t0
+        got = st.sam_format(sample, ref.names, threads=threads)
+        assert got == want, "SAM text differs from the unmodified SAMWriter's"
+        out["reference_writer"] = {"value": len(want) / dt / 1e6, "threads": 1, "reads": len(sample),
+                                   "verified_bytes": len(want)}
+    return out
+
+
 def integrated_run(wl_cfg, genome, contig_len, n_contigs, enc_ref, index, n_reads, cpu_threads, gpu_threads=16):
     """The UNMODIFIED ngmlr end to end, twice on the same FASTQ: the plain binary (oracle/_ref/ngmlr, its own
     ConvexAlignFast / StrippedSW on `cpu_threads` threads) and the same objects linked with the CUDA plugin
@@ -891,6 +946,13 @@ def main():
             raise
         except Exception as ex:
             line["e2e_ialignment"] = {"value": None, "note": repr(ex)}
+        try:   # the SAM text of the same slice
+            st02_ = locals().get("st02")
+            line["sam_text"] = sam_text_run(wl, wl.ivs, gpu_first, st02_, cores)
+        except AssertionError:
+            raise
+        except Exception as ex:
+            line["sam_text"] = {"value": None, "note": repr(ex)}
         n_int = args.integrated_reads
         if n_int < 0:
             n_int = 2000 if (world == 1 and args.genome_mb <= 100 and not args.dp_only) else 0

@@ -342,3 +342,64 @@ class CsReference:
         mh = C.c_float()
         n = self.lib.ref_cs_search(bytes(seq), len(seq), table_bits, sc, lo, rv, cap, C.byref(mh))
         return [(sc[i], int(lo[i]), rv[i]) for i in range(max(0, min(n, cap)))], mh.value
+
+
+class _RefSamAln(C.Structure):
+    _fields_ = [("ref_pos", C.c_ulonglong), ("ref_id", C.c_int), ("reverse", C.c_int), ("score", C.c_float),
+                ("mq", C.c_int), ("nm", C.c_int), ("identity", C.c_float), ("qstart", C.c_int), ("qend", C.c_int),
+                ("sv_type", C.c_int), ("primary", C.c_int), ("skip", C.c_int), ("cigar_ops", C.c_int),
+                ("cigar", C.c_char_p), ("md", C.c_char_p)]
+
+
+class _RefSamRead(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("seq", C.c_char_p), ("qual", C.c_char_p), ("length", C.c_int),
+                ("n_aln", C.c_int), ("first_aln", C.c_longlong), ("mapped", C.c_int), ("empty", C.c_int)]
+
+
+class SamReference:
+    """The unmodified SAMWriter + GenericReadWriter::WriteRead (src/SAMWriter.cpp, src/GenericReadWriter.h)
+    through ref_sam_write of oracle/ref_cs_shim.cpp. `lib` = libngmlr_full.so AFTER ref_cs_init (the writer takes
+    the contig names from the reference's SequenceProvider singleton). Reads are ngmlr_b200.samtext.Read."""
+
+    def __init__(self, lib):
+        self.lib = lib
+        lib.ref_sam_write.restype = C.c_longlong
+        lib.ref_cs_ref_len.restype = C.c_ulonglong
+        self.names, self.lens = [], []
+        for i in range(0, lib.ref_cs_ref_count(), 2):   # every contig is listed twice (src/SAMWriter.cpp:30-35)
+            buf = C.create_string_buffer(1024)
+            k = lib.ref_cs_ref_name(i, buf, 1024)
+            self.names.append(buf.raw[:k])
+            self.lens.append(int(lib.ref_cs_ref_len(i)))
+
+    def pack(self, reads):
+        n_aln = sum(len(r.alignments) for r in reads)
+        rr = (_RefSamRead * max(len(reads), 1))()
+        aa = (_RefSamAln * max(n_aln, 1))()
+        k = 0
+        for i, r in enumerate(reads):
+            rr[i] = _RefSamRead(r.name, r.seq, r.qual, len(r.seq), len(r.alignments), k, int(r.mapped), int(r.empty))
+            for a in r.alignments:
+                # the reference's ref ids count forward / reverse slots: contig j is id 2 * j
+                aa[k] = _RefSamAln(a.ref_pos, 2 * a.ref_id, int(a.reverse), a.score, a.mq, a.nm, a.identity, a.qstart,
+                                   a.qend, a.sv_type, int(a.primary), int(a.skip), a.cigar_ops, a.cigar, a.md)
+                k += 1
+        return rr, aa, len(reads), reads
+
+    def write(self, what, packed, write_unmapped=True, bam_cigar_fix=False, rg_id=None, rg_fields=None,
+              cmdline=b"ngmlr", cap=None):
+        rr, aa, n, _keep = packed
+        fields = (C.c_char_p * 11)(*rg_fields) if rg_fields else None
+        args = (what, rr, n, aa, int(bam_cigar_fix), int(write_unmapped), rg_id, fields, cmdline)
+        if cap is None:
+            cap = self.lib.ref_sam_write(*args, None, 0)
+        buf = C.create_string_buffer(cap + 1)
+        got = self.lib.ref_sam_write(*args, buf, cap)
+        assert got <= cap
+        return buf.raw[:got]
+
+    def records(self, reads, **kw):
+        return self.write(1, self.pack(reads), **kw)
+
+    def header(self, **kw):
+        return self.write(0, self.pack([]), **kw)

@@ -109,3 +109,92 @@ def test_positions_are_truncated_as_the_reference_prints_them():
     assert lines[0].split(b"\t")[3] == b"6" and lines[1].split(b"\t")[3] == b"%d" % (2**31 + 8)
     assert b"SA:Z:" + NAMES[0] + b",%d,+,4M,60,0;" % (2**31 + 8 - 2**32) in lines[0]
     assert lines[1].split(b"\t")[1] == b"2048"
+
+
+# ---- real records: the SAM file the unmodified ngmlr writes for its own fixtures, re-created from its fields -----
+PLAIN = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "ngmlr")
+FIX = os.path.join(HERE, "golden", "ref_fixtures")
+
+
+def _fastq_with_varied_qualities(fa, fq):
+    import gzip
+    op = gzip.open if fa.endswith(".gz") else open
+    reads, name, seq = {}, None, []
+    with op(fa, "rt") as f:
+        for line in list(f) + [">"]:
+            line = line.rstrip("\n")
+            if line.startswith(">"):
+                if name is not None:
+                    # the parser's normalisation (src/IParser.h:66-76): upper case, everything but ACGT becomes N
+                    s = "".join(c if c in "ACGT" else "N" for c in "".join(seq).upper())
+                    reads[name.split()[0][:249]] = (s, "".join(chr(35 + (i * 7 + len(s)) % 38) for i in range(len(s))))
+                name, seq = line[1:], []
+            else:
+                seq.append(line.strip())
+    with open(fq, "w") as out:
+        for n, (s, q) in reads.items():
+            out.write(f"@{n}\n{s}\n+\n{q}\n")
+    return reads
+
+
+def _rc(s):
+    return s[::-1].translate(bytes.maketrans(b"ACGT", b"TGCA"))
+
+
+@pytest.mark.skipif(not os.path.exists(PLAIN), reason="oracle/_ref/ngmlr not built")
+@pytest.mark.parametrize("test,ref_name,reads_name", [("test_2", "ref_chr21_20kb.fa", "reads_100_2200bp.fa"),
+                                                      ("test_6", "reference.fasta.gz", "read.fa.gz")])
+def test_sam_file_of_the_unmodified_ngmlr_is_recreated_from_its_fields(tmp_path, test, ref_name, reads_name):
+    import gzip
+    import re
+    d = os.path.join(FIX, test)
+    ref = str(tmp_path / "ref.fa")
+    op = gzip.open if ref_name.endswith(".gz") else open
+    with op(os.path.join(d, ref_name), "rt") as f, open(ref, "w") as out:
+        out.write(f.read())
+    fq = str(tmp_path / "reads.fq")
+    fastq = _fastq_with_varied_qualities(os.path.join(d, reads_name), fq)
+    sam = str(tmp_path / "out.sam")
+    r = subprocess.run([PLAIN, "-r", ref, "-q", fq, "-o", sam, "--skip-write", "--no-progress", "-t", "1"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    raw = open(sam, "rb").read()
+    header = b"".join(l + b"\n" for l in raw.split(b"\n") if l.startswith(b"@"))
+    body = raw[len(header):]
+    # header fields
+    names, lens, version, cmdline = [], [], None, None
+    for l in header.split(b"\n"):
+        f = l.split(b"\t")
+        if f[0] == b"@SQ":
+            names.append(f[1][3:])
+            lens.append(int(f[2][3:]))
+        elif f[0] == b"@PG":
+            version = f[3][3:]
+            cmdline = l.split(b"\tCL:", 1)[1]
+    assert st.sam_header(names, lens, version, cmdline) == header
+    # records -> reads (the records of a read are consecutive, in alignment order)
+    reads, by_name = [], {}
+    for l in body.split(b"\n")[:-1]:
+        f = l.split(b"\t")
+        name = f[0].decode()
+        seq, qual = fastq[name]
+        if name not in by_name:
+            by_name[name] = st.Read(f[0], seq.encode(), qual.encode(), [])
+            reads.append(by_name[name])
+        flag = int(f[1])
+        if flag & 4:
+            continue
+        tags = {t[:2]: t[5:] for t in f[11:]}
+        length = len(seq)
+        qs = int(tags[b"QS"])
+        qe = length - int(tags[b"QE"])
+        assert length - qs - qe == int(tags[b"XR"])
+        assert f[9] == (_rc(seq.encode()) if flag & 16 else seq.encode())
+        by_name[name].alignments.append(st.Alignment(
+            ref_pos=int(f[3]) - 1, ref_id=names.index(f[2]), reverse=bool(flag & 16), score=float(tags[b"AS"]),
+            mq=int(f[4]), nm=int(tags[b"NM"]), identity=float(tags[b"XI"]), qstart=qs, qend=qe, cigar=f[5],
+            md=tags[b"MD"], sv_type=int(tags.get(b"SV", b"-1")), primary=not (flag & 0x800),
+            cigar_ops=len(re.findall(rb"\d+[A-Z=]", f[5]))))
+    assert sum(len(r.alignments) for r in reads) > 0
+    got = st.sam_format(reads, names)
+    assert got == body
