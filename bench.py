@@ -511,8 +511,8 @@ def integrated_run(wl_cfg, genome, contig_len, n_contigs, enc_ref, index, n_read
             for c in range(n_contigs):
                 s = genome[c * contig_len:(c + 1) * contig_len].tobytes().decode()
                 f.write(f">c{c}\n" + "\n".join(s[k:k + 80] for k in range(0, len(s), 80)) + "\n")
-        ngmfiles.write_encoded_reference(ref + "-enc.2.ngm", enc_ref, [f"c{c}" for c in range(n_contigs)])
-        ngmfiles.write_index(ref + "-ht-13-2.2.ngm", index, skip=2)
+        ngmfiles.c_write_encoded_reference(ref + "-enc.2.ngm", enc_ref, [f"c{c}" for c in range(n_contigs)])
+        ngmfiles.c_write_index(ref + "-ht-13-2.2.ngm", index, skip=2)
         reads, _ = synth.simulate_reads(n_reads, genome, contig_len, 77, median=wl_cfg["median"], err=wl_cfg["err"],
                                         ratio=wl_cfg["ratio"], sv=wl_cfg["sv"], hi=wl_cfg["hi"])
         fq = os.path.join(d, "reads.fq")

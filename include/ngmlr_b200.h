@@ -343,6 +343,29 @@ int ngmlr_b200_compute_alignments_stats(ngmlr_b200_ctx* ctx, ngmlr_b200_batch_st
 int ngmlr_b200_select_candidates(int n, const int64_t* cand_start, const float* sw_scores, int32_t* order,
                                  int32_t* kept, int32_t* mq);
 
+/* ---- ngmlr's on-disk caches, byte-compatible --------------------------------
+ * <ref>-ht-<k>-<skip>.2.ngm: CompactPrefixTable::saveToFile / readFromFile (src/PrefixTable.cpp:534-630), one table
+ * unit. packed_index / positions are the arrays of ngmlr_b200_cs_set_index / ngmlr_b200_cs_get_index, so an index
+ * built on the device becomes the cache an unmodified ngmlr starts from. 0 on success; -2 cannot open, -3 short or
+ * foreign file, -4 more than one table unit, -5 signature mismatch (the reference would rebuild the table). */
+int ngmlr_b200_ngm_write_index(const char* path, int k, int kmer_skip, const void* packed_index, uint32_t index_len,
+                               const uint32_t* positions, uint32_t n_positions, uint64_t unit_offset);
+/* Sizes and header fields always; the arrays where the pointers are not NULL (index_len x 5 bytes, n_positions words). */
+int ngmlr_b200_ngm_read_index(const char* path, int32_t* k, int32_t* kmer_skip, uint32_t* index_len,
+                              uint32_t* n_positions, uint64_t* unit_offset, void* packed_index, uint32_t* positions);
+/* <ref>-enc.2.ngm: _SequenceProvider::writeEncRefToFile / readEncRefFromFile (src/SequenceProvider.cpp:207-272).
+ * bin_ref = the encoded genome of ngmlr_b200_cs_set_reference (used_bytes of it); alloc_bytes = the size the
+ * reference allocates and writes, ((getSize() / 2) | 1) + 1 (src/SequenceProvider.cpp:274-290, 318) -- the tail
+ * behind the used part is written as zeros (uninitialised memory in the reference's own file); seq_start / seq_len
+ * = RefIdx::SeqStart / SeqLen per contig, names[i] (NULL: "c<i>") cut at 100 characters. */
+int ngmlr_b200_ngm_write_reference(const char* path, const uint8_t* bin_ref, uint64_t used_bytes, uint64_t alloc_bytes,
+                                   int n_refs, const uint64_t* seq_start, const uint32_t* seq_len,
+                                   const char* const* names);
+/* Counts always; arrays where not NULL: seq_start / seq_len[n_refs], names = n_refs x 101 bytes (NUL terminated),
+ * bin_ref = used_bytes. */
+int ngmlr_b200_ngm_read_reference(const char* path, uint32_t* n_refs, uint64_t* used_bytes, uint64_t* alloc_bytes,
+                                  uint64_t* seq_start, uint32_t* seq_len, char* names, uint8_t* bin_ref);
+
 /* ---- SAM text ----------------------------------------------------------
  * Replaces SAMWriter::DoWriteProlog / DoWriteRead -> DoWriteReadGeneric / DoWriteUnmappedRead
  * (src/SAMWriter.cpp:22-85, 87-224, 301-363) and the per-read loop of GenericReadWriter::WriteRead

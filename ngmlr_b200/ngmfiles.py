@@ -10,7 +10,9 @@ arrays ngmlr already has on disk can be handed to the device pipeline unchanged 
                          unit count, index size; per unit: uint cRefTableLen, Index[index size]
                          (5 bytes each), Location[cRefTableLen], uloc Offset; uint signature.
 
-Index *construction* on the device is SURVEY section 8(f).3 ("next"); this module only moves bytes.
+This module is the tests' independent restatement of the formats (numpy); the product's own writers / readers are
+the C entry points ngmlr_b200_ngm_* (csrc/ngm_files.cpp), bound below as c_write_index / c_read_index /
+c_write_encoded_reference / c_read_encoded_reference and held equal to these byte for byte.
 """
 import struct
 
@@ -109,3 +111,80 @@ def write_index(path, idx, skip=2, unit_offset=0):
         f.write(np.ascontiguousarray(idx.pos, dtype="<u4").tobytes())
         f.write(struct.pack("<Q", unit_offset))
         f.write(struct.pack("<I", (REF_TAB_COOKIE + idx.k + skip + 1 + index_size) & 0xFFFFFFFF))
+
+
+# ---- the library's C writers / readers (csrc/ngm_files.cpp) -------------------------------------------------------
+def _c():
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    u32p, u64p = C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
+    lib.ngmlr_b200_ngm_write_index.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p,
+                                               C.c_uint32, C.c_uint64]
+    lib.ngmlr_b200_ngm_read_index.argtypes = [C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), u32p, u32p, u64p,
+                                              C.c_void_p, C.c_void_p]
+    lib.ngmlr_b200_ngm_write_reference.argtypes = [C.c_char_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p,
+                                                   C.c_void_p, C.POINTER(C.c_char_p)]
+    lib.ngmlr_b200_ngm_read_reference.argtypes = [C.c_char_p, u32p, u64p, u64p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                  C.c_void_p]
+    return C, lib
+
+
+def c_write_index(path, idx, skip=2, unit_offset=0):
+    C, lib = _c()
+    packed = np.ascontiguousarray(idx.packed_index())
+    pos = np.ascontiguousarray(idx.pos, dtype="<u4")
+    rc = lib.ngmlr_b200_ngm_write_index(str(path).encode(), int(idx.k), int(skip), packed.ctypes.data, int(idx.tab.size),
+                                        pos.ctypes.data, int(pos.size), int(unit_offset))
+    if rc:
+        raise OSError(f"ngmlr_b200_ngm_write_index({path}) = {rc}")
+
+
+def c_read_index(path, bin_shift=4):
+    C, lib = _c()
+    k, skip, n_idx, n_pos, off = C.c_int32(), C.c_int32(), C.c_uint32(), C.c_uint32(), C.c_uint64()
+    args = (str(path).encode(), C.byref(k), C.byref(skip), C.byref(n_idx), C.byref(n_pos), C.byref(off))
+    rc = lib.ngmlr_b200_ngm_read_index(*args, None, None)
+    if rc:
+        raise ValueError(f"ngmlr_b200_ngm_read_index({path}) = {rc}")
+    raw = np.zeros((n_idx.value, 5), np.uint8)
+    pos = np.zeros(n_pos.value, "<u4")
+    rc = lib.ngmlr_b200_ngm_read_index(*args, raw.ctypes.data, pos.ctypes.data)
+    if rc:
+        raise ValueError(f"ngmlr_b200_ngm_read_index({path}) = {rc}")
+    tab = raw[:, :4].copy().view("<u4").reshape(-1)
+    rci = raw[:, 4].copy().view(np.int8)
+    return KmerIndex(int(k.value), bin_shift, tab, rci, pos), int(skip.value), int(off.value)
+
+
+def c_write_encoded_reference(path, ref, names=None, skipped_lens=()):
+    C, lib = _c()
+    n = len(ref.ref_start)
+    enc = np.ascontiguousarray(ref.enc, dtype=np.uint8)
+    starts = np.asarray(ref.ref_start, dtype="<u8")
+    lens = np.asarray(ref.ref_len, dtype="<u4")
+    alloc = max(reference_alloc_bytes(ref.ref_len, skipped_lens), int(enc.size))
+    nm = (C.c_char_p * max(n, 1))(*[x.encode() for x in names]) if names else None
+    rc = lib.ngmlr_b200_ngm_write_reference(str(path).encode(), enc.ctypes.data, int(enc.size), int(alloc), n,
+                                            starts.ctypes.data, lens.ctypes.data, nm)
+    if rc:
+        raise OSError(f"ngmlr_b200_ngm_write_reference({path}) = {rc}")
+
+
+def c_read_encoded_reference(path):
+    C, lib = _c()
+    n, used, alloc = C.c_uint32(), C.c_uint64(), C.c_uint64()
+    args = (str(path).encode(), C.byref(n), C.byref(used), C.byref(alloc))
+    rc = lib.ngmlr_b200_ngm_read_reference(*args, None, None, None, None)
+    if rc:
+        raise ValueError(f"ngmlr_b200_ngm_read_reference({path}) = {rc}")
+    starts = np.zeros(n.value, "<u8")
+    lens = np.zeros(n.value, "<u4")
+    names = np.zeros((n.value, 101), np.uint8)
+    enc = np.zeros(used.value, np.uint8)
+    rc = lib.ngmlr_b200_ngm_read_reference(*args, starts.ctypes.data, lens.ctypes.data, names.ctypes.data,
+                                           enc.ctypes.data)
+    if rc:
+        raise ValueError(f"ngmlr_b200_ngm_read_reference({path}) = {rc}")
+    ref = EncodedReference(enc, 2 * int(used.value) - 1, [int(v) for v in starts], [int(v) for v in lens])
+    return ref, [bytes(r).split(b"\0")[0].decode("ascii", "replace") for r in names]

@@ -116,6 +116,24 @@ def test_cache_files_round_trip(contigs, tmp_path, built):
         f.write(b"\0" * 64)
     with pytest.raises(ValueError):
         ngmfiles.read_index(str(tmp_path / "bad.ngm"))
+    # the library's C writers / readers (csrc/ngm_files.cpp): same bytes, same arrays
+    ngmfiles.c_write_encoded_reference(str(tmp_path / "c-enc.2.ngm"), ref, skipped_lens=[8])
+    ngmfiles.c_write_index(str(tmp_path / "c-ht-13-2.2.ngm"), idx)
+    assert open(tmp_path / "c-enc.2.ngm", "rb").read() == open(tmp_path / "r-enc.2.ngm", "rb").read()
+    assert open(tmp_path / "c-ht-13-2.2.ngm", "rb").read() == open(tmp_path / "r-ht-13-2.2.ngm", "rb").read()
+    ref3, names3 = ngmfiles.c_read_encoded_reference(str(tmp_path / "r-enc.2.ngm"))
+    assert np.array_equal(ref3.enc, ref.enc) and ref3.concat_len == ref.concat_len
+    assert ref3.ref_start == ref.ref_start and ref3.ref_len == ref.ref_len and names3 == names
+    idx3, skip3, off3 = ngmfiles.c_read_index(str(tmp_path / "r-ht-13-2.2.ngm"))
+    assert (idx3.k, skip3, off3) == (13, 2, 0)
+    assert np.array_equal(idx3.tab, idx.tab) and np.array_equal(idx3.rci, idx.rci) and np.array_equal(idx3.pos, idx.pos)
+    with pytest.raises(ValueError):
+        ngmfiles.c_read_index(str(tmp_path / "bad.ngm"))
+    blob = bytearray(open(tmp_path / "r-ht-13-2.2.ngm", "rb").read())
+    blob[-1] ^= 0x40                      # broken signature: the reference would rebuild the table
+    open(tmp_path / "sig.ngm", "wb").write(bytes(blob))
+    with pytest.raises(ValueError, match="-5"):
+        ngmfiles.c_read_index(str(tmp_path / "sig.ngm"))
 
 
 @pytest.mark.skipif(not CsReference.available(), reason="oracle/_ref/libngmlr_full.so not built")
@@ -154,6 +172,16 @@ def test_cache_files_are_byte_compatible_with_the_reference(contigs, tmp_path, b
     mine, theirs = open(tmp_path / "mine-enc.ngm", "rb").read(), open(enc_path, "rb").read()
     defined = 24 + 128 * len(ref.ref_start) + int(ref.enc.size)
     assert len(mine) == len(theirs) and mine[:defined] == theirs[:defined]
+    # ... and the library's C writers / readers on the reference's own files
+    ngmfiles.c_write_index(str(tmp_path / "c-ht.ngm"), idx)
+    assert open(tmp_path / "c-ht.ngm", "rb").read() == open(idx_path, "rb").read()
+    ngmfiles.c_write_encoded_reference(str(tmp_path / "c-enc.ngm"), ref, names, skipped_lens=skipped)
+    assert open(tmp_path / "c-enc.ngm", "rb").read() == mine
+    c_ref, c_names = ngmfiles.c_read_encoded_reference(enc_path)
+    assert np.array_equal(c_ref.enc, ref.enc) and c_ref.ref_start == ref.ref_start and c_names == names
+    c_idx, c_skip, c_off = ngmfiles.c_read_index(idx_path)
+    assert (c_idx.k, c_skip, c_off) == (13, 2, 0) and np.array_equal(c_idx.tab, idx.tab)
+    assert np.array_equal(c_idx.rci, idx.rci) and np.array_equal(c_idx.pos, idx.pos)
 
 
 class _OracleBackend:
