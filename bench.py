@@ -850,17 +850,21 @@ def main():
         # 148 SMs x 128 lanes x clock / >= 25 instructions per cell
         issue_bound = 148 * 128 * sm_mhz * 1e6 / 25.0
         traffic = None
-        alu_ops = None
+        alu_ops = lane_instr = None
         try:  # DRAM bytes of one fill launch from the committed ncu capture (same workload only)
             tr = json.load(open(os.path.join(ROOT, "profiles", "fill_traffic.json")))
             if tr.get("reads_per_step") == args.reads and tr.get("config", "pacbio50") == args.config:
                 traffic = tr["dram_bytes_per_launch"]
             alu_ops = tr.get("alu_pipe_lane_ops_per_cell")   # a property of the kernel's code, not of the batch
+            lane_instr = tr.get("lane_instructions_per_cell")
         except Exception:
             pass
         # the pipe that binds: compares / selects / min-max run on the ALU pipe only, 16 lanes per
         # clock and SM sub-partition; ops per cell from the same ncu capture
         alu_bound = 148 * 4 * 16 * sm_mhz * 1e6 / alu_ops if alu_ops else None
+        # what the kernel's own instruction count allows at one warp-instruction per clock and sub-partition (the
+        # final build issues 67.4 lane-instructions per useful cell incl. block ramp and chunk hand-off)
+        own_issue_bound = 148 * 128 * sm_mhz * 1e6 / lane_instr if lane_instr else None
         line = {
             "metric": "aligned_gbp_per_s", "value": value, "unit": "Gbp/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
@@ -888,8 +892,12 @@ def main():
                          "frac_of_issue_bound": cells / fill_s / issue_bound,
                          "alu_pipe_bound_gcells_per_s": alu_bound / 1e9 if alu_bound else None,
                          "frac_of_alu_pipe_bound": cells / fill_s / alu_bound if alu_bound else None,
+                         "own_instruction_count_bound_gcells_per_s": own_issue_bound / 1e9 if own_issue_bound else None,
+                         "frac_of_own_instruction_count_bound": cells / fill_s / own_issue_bound if own_issue_bound else None,
                          "note": "integer/float DP: instruction-issue bound (SURVEY 8(d): 148 SMs x 128 lanes x clock / "
-                                 "25 instructions per cell), not HBM bound; the HBM fraction is structurally ~0.02"},
+                                 "25 instructions per cell), not HBM bound; the HBM fraction is structurally ~0.02. The "
+                                 "kernel issues 67.4 lane-instructions per useful cell (ncu, profiles/fill_traffic.json): "
+                                 "issue slots 85 % busy, ALU pipe 67 %"},
             "kernel_ms_per_step": {"fill": float(np.mean(fill_ms)), "traceback": float(np.mean(tb_ms)),
                                    "text": float(np.mean(tx_ms)),
                                    "stage02_cs_vote_decode_score": float(np.mean(cs_ms))},
@@ -946,13 +954,13 @@ def main():
             raise
         except Exception as ex:
             line["e2e_ialignment"] = {"value": None, "note": repr(ex)}
-        try:   # the SAM text of the same slice
-            st02_ = locals().get("st02")
-            line["sam_text"] = sam_text_run(wl, wl.ivs, gpu_first, st02_, cores)
-        except AssertionError:
-            raise
-        except Exception as ex:
-            line["sam_text"] = {"value": None, "note": repr(ex)}
+        if world == 1:   # the SAM text of the batch's records
+            try:
+                line["sam_text"] = sam_text_run(wl, wl.ivs, gpu_first, locals().get("st02"), cores)
+            except AssertionError:
+                raise
+            except Exception as ex:
+                line["sam_text"] = {"value": None, "note": repr(ex)}
         n_int = args.integrated_reads
         if n_int < 0:
             n_int = 2000 if (world == 1 and args.genome_mb <= 100 and not args.dp_only) else 0

@@ -246,6 +246,19 @@ int ngmlr_b200_cs_fetch(ngmlr_b200_ctx* ctx, int64_t* cand_start, const float** 
                         const uint64_t** locs, const uint8_t** reverse, const float** sw_scores,
                         float* max_hits);
 
+/* The same encoded genome BUILT ON THE DEVICE from the contigs' text: replaces the encoding loop of
+ * _SequenceProvider::Init (src/SequenceProvider.cpp:292-400): A0 T1 G2 C3 in either case, everything else N;
+ * 1000-N spacers before, between and after the contigs; contigs of <= 10 characters are skipped. Installs the
+ * result as the context's reference AND its refStartPos (= ngmlr_b200_cs_set_reference + ngmlr_b200_set_ref_starts).
+ * kept_start / kept_len (n_contigs entries of room) receive SeqStart / SeqLen of the *n_kept contigs that were kept:
+ * the arguments of ngmlr_b200_cs_build_index and of the -enc.2.ngm writer. */
+int ngmlr_b200_cs_encode_reference(ngmlr_b200_ctx* ctx, int n_contigs, const char* const* seqs, const uint64_t* lens,
+                                   int32_t* n_kept, uint64_t* kept_start, uint64_t* kept_len, uint64_t* n_bytes,
+                                   uint64_t* concat_len);
+/* The context's encoded genome back in host memory: sizes always, the bytes where bin_ref is not NULL. */
+int ngmlr_b200_cs_get_reference(ngmlr_b200_ctx* ctx, uint8_t* bin_ref, uint64_t cap, uint64_t* n_bytes,
+                                uint64_t* concat_len);
+
 /* ---- reference windows for alignment, decoded on the device -------------------------------------
  * refStartPos as _SequenceProvider holds it (src/SequenceProvider.cpp:416-424): the concatenated
  * start position of every contig (forward strand entries only) followed by one artificial entry

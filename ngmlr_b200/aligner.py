@@ -303,6 +303,33 @@ class B200Aligner:
             out.append([(sc[j], int(lo[j]), int(rv[j])) for j in range(start[i], start[i + 1])])
         return out, mx[:n]
 
+    def encode_reference(self, contigs, fetch=True):
+        """_SequenceProvider::Init's encoding of the contigs (bytes / uint8 arrays) on the device; installs the encoded
+        genome and refStartPos in this context. Returns the EncodedReference (with its bytes when fetch=True)."""
+        from .refindex import EncodedReference
+        seqs = [bytes(c) if not isinstance(c, (bytes, bytearray)) else c for c in contigs]
+        n = len(seqs)
+        arr = (C.c_char_p * max(n, 1))(*seqs)
+        lens = (C.c_uint64 * max(n, 1))(*[len(s) for s in seqs])
+        kept = C.c_int32(0)
+        ks = (C.c_uint64 * max(n, 1))()
+        kl = (C.c_uint64 * max(n, 1))()
+        nb, cl = C.c_uint64(0), C.c_uint64(0)
+        self.lib.ngmlr_b200_cs_encode_reference.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p),
+                                                            C.POINTER(C.c_uint64), C.POINTER(C.c_int32),
+                                                            C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                                            C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        self.lib.ngmlr_b200_cs_get_reference.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64),
+                                                         C.POINTER(C.c_uint64)]
+        self._check(self.lib.ngmlr_b200_cs_encode_reference(self.h, n, arr, lens, C.byref(kept), ks, kl, C.byref(nb),
+                                                            C.byref(cl)))
+        enc = np.zeros(nb.value if fetch else 0, dtype=np.uint8)
+        if fetch:
+            self._check(self.lib.ngmlr_b200_cs_get_reference(self.h, enc.ctypes.data_as(C.c_void_p), enc.size, None,
+                                                             None))
+        return EncodedReference(enc, int(cl.value), [int(ks[i]) for i in range(kept.value)],
+                                [int(kl[i]) for i in range(kept.value)])
+
     def set_reference(self, ref):
         """ref: ngmlr_b200.refindex.EncodedReference (the reference's 4-bit `binRef`)."""
         enc = np.ascontiguousarray(ref.enc, dtype=np.uint8)

@@ -761,6 +761,72 @@ int ngmlr_b200_set_ref_starts(ngmlr_b200_ctx* ctx, const uint64_t* ref_start_pos
   return 0;
 }
 
+// The encoded genome built ON THE DEVICE from contig text: replaces the encoding loop of _SequenceProvider::Init
+// (src/SequenceProvider.cpp:292-400) -- 1000-N spacers (500 bytes of 0x44) before, between and after the contigs,
+// contigs of <= 10 characters skipped (minRefSeqLen), every contig starting on a byte boundary -- and installs the
+// result as the context's reference together with refStartPos (ngmlr_b200_cs_set_reference + set_ref_starts).
+int ngmlr_b200_cs_encode_reference(ngmlr_b200_ctx* ctx, int n_contigs, const char* const* seqs, const uint64_t* lens,
+                                   int32_t* n_kept, uint64_t* kept_start, uint64_t* kept_len, uint64_t* n_bytes,
+                                   uint64_t* concat_len) {
+  if (!ctx) return -1;
+  if (n_contigs < 0 || (n_contigs && (!seqs || !lens))) return ctx->fail("cs_encode_reference: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  CsState* cs = cs_state(ctx, true);
+  std::vector<unsigned long long> starts, klens;
+  std::vector<int> which;
+  unsigned long long bytes = 500, longest = 0;
+  for (int i = 0; i < n_contigs; ++i) {
+    if (!(lens[i] > 10)) continue;
+    starts.push_back(bytes * 2);
+    klens.push_back(lens[i]);
+    which.push_back(i);
+    bytes += (lens[i] + 1) / 2 + 500;
+    longest = std::max<unsigned long long>(longest, lens[i]);
+  }
+  CU(cs->d_enc.reserve(bytes + 64));
+  CU(cudaMemsetAsync(cs->d_enc.p, 0x44, bytes + 64, ctx->stream));  // spacers, and 'N','N' past the end
+  DevBuf<uint8_t> text;
+  CU(text.reserve(longest + 16));
+  for (size_t j = 0; j < which.size(); ++j) {
+    const int i = which[j];
+    CU(cudaMemcpyAsync(text.p, seqs[i], lens[i], cudaMemcpyHostToDevice, ctx->stream));
+    CU(launch_encode_contig(text.p, lens[i], cs->d_enc.p + starts[j] / 2, ctx->stream));
+  }
+  CU(nb_stream_sync(ctx, ctx->stream));
+  cs->enc_bytes = bytes;
+  cs->concat_len = bytes * 2 - 1;
+  if (n_kept) *n_kept = (int32_t)which.size();
+  for (size_t j = 0; j < which.size(); ++j) {
+    if (kept_start) kept_start[j] = starts[j];
+    if (kept_len) kept_len[j] = klens[j];
+  }
+  if (n_bytes) *n_bytes = bytes;
+  if (concat_len) *concat_len = cs->concat_len;
+  if (!starts.empty()) {   // refStartPos: the starts plus the artificial last entry (src/SequenceProvider.cpp:416-424)
+    std::vector<uint64_t> rs(starts.begin(), starts.end());
+    rs.push_back(starts.back() + klens.back() + 1000);
+    return ngmlr_b200_set_ref_starts(ctx, rs.data(), (int)rs.size());
+  }
+  return 0;
+}
+
+// The context's encoded genome back in host memory (for the -enc.2.ngm writer): *n_bytes always, the bytes where
+// bin_ref is not NULL and cap suffices.
+int ngmlr_b200_cs_get_reference(ngmlr_b200_ctx* ctx, uint8_t* bin_ref, uint64_t cap, uint64_t* n_bytes,
+                                uint64_t* concat_len) {
+  if (!ctx) return -1;
+  CsState* cs = cs_state(ctx, false);
+  if (!cs || !cs->enc_bytes) return ctx->fail("cs_get_reference: no reference");
+  if (n_bytes) *n_bytes = cs->enc_bytes;
+  if (concat_len) *concat_len = cs->concat_len;
+  if (bin_ref) {
+    if (cap < cs->enc_bytes) return ctx->fail("cs_get_reference: buffer too small");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpy(bin_ref, cs->d_enc.p, cs->enc_bytes, cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+
 namespace {
 
 // The contract of the window calls: the window starts inside a contig or inside the 1000-N spacer in

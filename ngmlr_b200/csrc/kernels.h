@@ -52,6 +52,8 @@ cudaError_t launch_sw_score(const SwParams& p, int grid, cudaStream_t stream);
 cudaError_t launch_sw_score_gather(const SwParams& p, int grid, cudaStream_t stream);
 
 cudaError_t launch_decode_windows(const RefDecodeParams& p, cudaStream_t stream);
+// one contig's characters (device) -> 4-bit codes, two per byte (_SequenceProvider::Init's encoding)
+cudaError_t launch_encode_contig(const uint8_t* text, unsigned long long len, uint8_t* out, cudaStream_t stream);
 
 // binary CIGAR -> CIGAR/MD text, NM, identity, positions, low-identity regions (convex_text.cu)
 cudaError_t launch_convex_text(const TextParams& p, cudaStream_t stream);

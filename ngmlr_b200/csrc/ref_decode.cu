@@ -12,6 +12,8 @@
 // base).
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include "device_types.h"
 #include "kernels.h"
 
@@ -89,11 +91,40 @@ __global__ void __launch_bounds__(256) gather_reads_kernel(const GatherParams p)
   }
 }
 
+
+// _SequenceProvider::Init's encoding of one contig (src/SequenceProvider.cpp:76-105, 342-400): two characters per
+// byte, high nibble first, A0 T1 G2 C3 (either case), everything else 4 (N); an odd contig ends with an N nibble.
+// One thread per 16 output bytes (32 characters, two 16-byte loads where aligned): pure HBM streaming, 1 B read and
+// 0.5 B written per base.
+__device__ __forceinline__ uint32_t enc4(uint32_t c) {
+  c &= 0xdfu;  // upper case
+  return c == 'A' ? 0u : (c == 'T' ? 1u : (c == 'G' ? 2u : (c == 'C' ? 3u : 4u)));
+}
+
+__global__ void __launch_bounds__(256) encode_contig_kernel(const uint8_t* __restrict__ text, unsigned long long len,
+                                                            uint8_t* __restrict__ out) {
+  const unsigned long long n_bytes = (len + 1ull) >> 1;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < n_bytes; j += stride) {
+    const uint32_t hi = enc4(text[2 * j]);
+    const uint32_t lo = (2 * j + 1 < len) ? enc4(text[2 * j + 1]) : 4u;
+    out[j] = (uint8_t)((hi << 4) | lo);
+  }
+}
+
 }  // namespace
 
 cudaError_t launch_gather_reads(const GatherParams& p, cudaStream_t stream) {
   if (p.n <= 0) return cudaSuccess;
   gather_reads_kernel<<<p.n, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_encode_contig(const uint8_t* text, unsigned long long len, uint8_t* out, cudaStream_t stream) {
+  if (!len) return cudaSuccess;
+  const unsigned long long n_bytes = (len + 1ull) >> 1;
+  const int grid = (int)std::min<unsigned long long>((n_bytes + 255ull) / 256ull, 148ull * 32ull);
+  encode_contig_kernel<<<grid, 256, 0, stream>>>(text, len, out);
   return cudaGetLastError();
 }
 

@@ -75,3 +75,46 @@ def test_cache_file_from_device_index_is_byte_identical(tmp_path):
     ngmfiles.write_index(a, want, skip=2)
     ngmfiles.write_index(b, got, skip=2)
     assert open(a, "rb").read() == open(b, "rb").read()
+
+
+def test_device_reference_encoding_equals_numpy_and_feeds_the_index(tmp_path):
+    """_SequenceProvider::Init's encoding on the device (ngmlr_b200_cs_encode_reference): same bytes, contig table
+    and concat length as refindex.encode_reference (itself held equal to the unmodified reference's binRef,
+    tests/test_cs_oracle.py) on contigs with lower case, IUPAC codes, N runs, odd lengths, a contig of <= 10
+    characters (skipped) and one of 11; the index built from it and the cache files written through the C writers
+    are the numpy builder's."""
+    contigs = [bytes(c) for c in cs_cases.genome_contigs()]
+    rng = np.random.default_rng(3)
+    messy = bytearray(rng.choice(np.frombuffer(b"ACGTacgtNnRYKMSWrykm-*", dtype=np.uint8), 4097).tobytes())
+    contigs = [contigs[0], b"ACGTACGTAC", bytes(messy), b"ACGTACGTACG"] + contigs[1:]
+    want = refindex.encode_reference([np.frombuffer(c, dtype=np.uint8) for c in contigs])
+    al = B200Aligner(0)
+    try:
+        got = al.encode_reference(contigs)
+        assert got.ref_start == want.ref_start and got.ref_len == want.ref_len and got.concat_len == want.concat_len
+        assert np.array_equal(got.enc, want.enc)
+        idx = al.build_index(got, fetch=True)
+        ref_idx = refindex.build_index(want)
+        assert np.array_equal(idx.tab, ref_idx.tab) and np.array_equal(idx.rci, ref_idx.rci)
+        assert np.array_equal(idx.pos, ref_idx.pos)
+        # windows decoded from the device-encoded genome (refStartPos was installed with it)
+        starts = [want.ref_start[1] + 5, want.ref_start[2] - 20]
+        assert al.decode_windows(starts, [200, 64]) == _numpy_windows(want, starts, [200, 64], al)
+        ngmfiles.c_write_encoded_reference(str(tmp_path / "a-enc.2.ngm"), got, skipped_lens=[10])
+        ngmfiles.write_encoded_reference(str(tmp_path / "b-enc.2.ngm"), want, skipped_lens=[10])
+        assert open(tmp_path / "a-enc.2.ngm", "rb").read() == open(tmp_path / "b-enc.2.ngm", "rb").read()
+        ngmfiles.c_write_index(str(tmp_path / "a-ht.ngm"), idx)
+        ngmfiles.write_index(str(tmp_path / "b-ht.ngm"), ref_idx)
+        assert open(tmp_path / "a-ht.ngm", "rb").read() == open(tmp_path / "b-ht.ngm", "rb").read()
+    finally:
+        al.close()
+
+
+def _numpy_windows(enc, starts, lens, al):
+    """The same windows from a context whose reference was uploaded the usual way."""
+    other = B200Aligner(0)
+    try:
+        other.set_reference(enc)
+        return other.decode_windows(starts, lens)
+    finally:
+        other.close()
