@@ -38,12 +38,15 @@ int main(void) {
          offsetof(ngmlr_b200_batch_stats, text_bytes), sizeof(ngmlr_b200_interval),
          offsetof(ngmlr_b200_interval, on_ref_stop), offsetof(ngmlr_b200_interval, read_seq),
          sizeof(ngmlr_b200_anchor), offsetof(ngmlr_b200_anchor, on_ref));
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(ngmlr_b200_sam_aln), offsetof(ngmlr_b200_sam_aln, cigar),
+         offsetof(ngmlr_b200_sam_aln, identity), sizeof(ngmlr_b200_sam_read), offsetof(ngmlr_b200_sam_read, first_aln),
+         offsetof(ngmlr_b200_sam_read, empty), sizeof(ngmlr_b200_sam_options), offsetof(ngmlr_b200_sam_options, rg_id));
   return 0;
 }'''
     import tempfile
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "t.c"), "w").write(src)
-        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"),
+        subprocess.run(["gcc", "-std=c99", "-pedantic-errors", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"),
                         os.path.join(d, "t.c")], check=True)
         out = subprocess.run([os.path.join(d, "t")], capture_output=True, text=True, check=True).stdout.split()
     got = [C.sizeof(_lib.AlignResult), _lib.AlignResult.cigar.offset, _lib.AlignResult.cells.offset,
@@ -51,6 +54,9 @@ int main(void) {
            _lib.AlignResult.sv_regions.offset, _lib.BatchStats.text_bytes.offset, C.sizeof(_lib.Interval),
            _lib.Interval.on_ref_stop.offset, _lib.Interval.read_seq.offset, C.sizeof(_lib.Anchor),
            _lib.Anchor.on_ref.offset]
+    from ngmlr_b200 import samtext as st
+    got += [C.sizeof(st.SamAln), st.SamAln.cigar.offset, st.SamAln.identity.offset, C.sizeof(st.SamRead),
+            st.SamRead.first_aln.offset, st.SamRead.empty.offset, C.sizeof(st.SamOptions), st.SamOptions.rg_id.offset]
     assert [int(x) for x in out] == got
 
 
