@@ -198,3 +198,42 @@ def test_sam_file_of_the_unmodified_ngmlr_is_recreated_from_its_fields(tmp_path,
     assert sum(len(r.alignments) for r in reads) > 0
     got = st.sam_format(reads, names)
     assert got == body
+
+
+# ---- the whole unmodified ngmlr with its SAMWriter replaced by the library at link time (oracle/swap_samwriter.cpp) ---
+SAM_SWAPPED = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "ngmlr_sam")
+LIBRARY = os.path.join(os.path.dirname(HERE), "ngmlr_b200", "libngmlr_b200.so")
+
+
+def _run_ngmlr(exe, ref, fq, sam, threads):
+    env = dict(os.environ, NGMLR_B200_LIB=LIBRARY)
+    r = subprocess.run([exe, "-r", ref, "-q", fq, "-o", sam, "--skip-write", "--no-progress", "-t", str(threads)],
+                       capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return open(sam, "rb").read()
+
+
+@pytest.mark.skipif(not (os.path.exists(PLAIN) and os.path.exists(SAM_SWAPPED)),
+                    reason="oracle/_ref/ngmlr and ngmlr_sam not built")
+@pytest.mark.parametrize("test,ref_name,reads_name,threads", [
+    ("test_2", "ref_chr21_20kb.fa", "reads_100_2200bp.fa", 1), ("test_4", "reference.fasta.gz", "read.fa.gz", 4)])
+def test_ngmlr_linked_with_the_library_writer_writes_the_same_sam_file(tmp_path, test, ref_name, reads_name, threads):
+    """Plain ngmlr (its own aligners, CPU) with SAMWriter's member functions replaced by forwarders to
+    ngmlr_b200_sam_header / ngmlr_b200_sam_format: the same file (one thread), the same records (several)."""
+    import gzip
+    d = os.path.join(FIX, test)
+    ref = str(tmp_path / "ref.fa")
+    op = gzip.open if ref_name.endswith(".gz") else open
+    with op(os.path.join(d, ref_name), "rt") as f, open(ref, "w") as out:
+        out.write(f.read())
+    fq = str(tmp_path / "reads.fq")
+    _fastq_with_varied_qualities(os.path.join(d, reads_name), fq)
+    want = _run_ngmlr(PLAIN, ref, fq, str(tmp_path / "plain.sam"), threads)
+    got = _run_ngmlr(SAM_SWAPPED, ref, fq, str(tmp_path / "plain.sam"), threads)   # same -o: same @PG command line ...
+    want = want.replace(PLAIN.encode(), b"EXE")
+    got = got.replace(SAM_SWAPPED.encode(), b"EXE")                                    # ... up to the binary's name
+    assert got.count(b"\n") > 5
+    if threads == 1:
+        assert got == want
+    else:
+        assert sorted(got.split(b"\n")) == sorted(want.split(b"\n"))
