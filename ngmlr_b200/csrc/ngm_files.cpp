@@ -12,6 +12,7 @@
 // the device (ngmlr_b200_cs_build_index) becomes the cache file an unmodified ngmlr starts from, and the caches
 // ngmlr already has on disk feed the device pipeline. Same bytes as ngmlr_b200/ngmfiles.py (the tests' writer) and,
 // through it, as the files the unmodified reference writes (tests/test_cs_oracle.py, tests/test_host_logic.py).
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
