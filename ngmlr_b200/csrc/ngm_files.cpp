@@ -11,7 +11,7 @@
 // The arrays are the ones ngmlr_b200_cs_get_index / cs_set_index / cs_set_reference exchange, so an index built on
 // the device (ngmlr_b200_cs_build_index) becomes the cache file an unmodified ngmlr starts from, and the caches
 // ngmlr already has on disk feed the device pipeline. Same bytes as ngmlr_b200/ngmfiles.py (the tests' writer) and,
-// through it, as the files the unmodified reference writes (tests/test_cs_oracle.py, tests/test_host_logic.py).
+// through it, as the files the unmodified reference writes (tests/test_cs_oracle.py, tests/test_gpu_index.py).
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
