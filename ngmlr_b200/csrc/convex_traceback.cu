@@ -91,6 +91,9 @@ __global__ void __launch_bounds__(TB_WARPS_PER_CTA * 32) convex_traceback_kernel
   int xw0 = 1 << 30;       // reference byte window [xw0, xw0 + 128), 4 bytes per lane
   uint32_t refw = 0;
 
+  // A diagonal run that ends inside its block ends at a cell the fast path has just rejected (same registers, same
+  // tests): the next iteration goes straight to the single step instead of evaluating that rejection again.
+  bool rejected = false;
   for (;;) {
     // ---- getDirection(x, y) ----
     if (y < 0 || x < 0) break;  // STOP (y > H-1 cannot happen: y only decreases from best_y)
@@ -125,7 +128,7 @@ __global__ void __launch_bounds__(TB_WARPS_PER_CTA * 32) convex_traceback_kernel
     // (x - (t - L), 32*blk + L), entirely from its own registers: inside the corridor, direction
     // DIAG, validPath. The leading run of lanes t, t-1, ... that all agree is consumed at once
     // (on 15 %-error reads ~6 steps per iteration instead of 1).
-    {
+    if (!rejected) {
       const int xx = x - (t - lane);
       bool okd = false;
       if (lane <= t && xx >= 0 && xx >= rw.off && (long long)xx < (long long)rw.off + (long long)rw.len) {
@@ -174,9 +177,11 @@ __global__ void __launch_bounds__(TB_WARPS_PER_CTA * 32) convex_traceback_kernel
         read_len += n_diag;
         x -= n_diag;
         y -= n_diag;
+        rejected = n_diag <= t;  // still in this block: lane t - n_diag is the cell that ended the run
         continue;
       }
     }
+    rejected = false;
     // ---- generic single step ----
     const int off = __shfl_sync(FULL, rw.off, t);
     const int len = __shfl_sync(FULL, rw.len, t);
