@@ -95,8 +95,9 @@ __global__ void __launch_bounds__(CS_WARPS * 32) cs_search_kernel(const CsParams
   // starts the sequence or is at least two long) leaves no more than k characters (:38-41) -- which drops
   // exactly one window, the last one, when it starts right behind such a run.
   const int n_win = len - k + 1;
-  for (int c0 = 0; c0 < n_win; c0 += 32) {
-    const int pos = c0 + lane;  // read offset of this lane's k-mer
+  // one window: its k-mer and the two position lists CompactPrefixTable::GetRefEntry returns for it
+  auto window = [&](int pos, uint32_t& fs, uint32_t& fn, uint32_t& rs, uint32_t& rn) {
+    fs = fn = rs = rn = 0;
     uint32_t prefix = 0;
     bool ok = pos < n_win;
     if (ok) {
@@ -114,7 +115,6 @@ __global__ void __launch_bounds__(CS_WARPS * 32) cs_search_kernel(const CsParams
       }
     }
     // ---- CompactPrefixTable::GetRefEntry: forward list, then the list of the reverse-complement k-mer ----
-    uint32_t fs = 0, fn = 0, rs = 0, rn = 0;
     if (ok) {
       if ((p.used_bits[prefix >> 5] >> (prefix & 31u)) & 1u) {
         fs = p.tab[prefix] - 1u;
@@ -126,12 +126,20 @@ __global__ void __launch_bounds__(CS_WARPS * 32) cs_search_kernel(const CsParams
         rn = p.tab[rc + 1] - 1u - rs;
       }
     }
+  };
+  // 64 windows per round, two consecutive ones per lane: on a 50 Mb index a window has ~0.5 hits, so that rounds of 32
+  // windows left the 32-hit batches below half empty
+  for (int c0 = 0; c0 < n_win; c0 += 64) {
+    uint32_t fs0, fn0, rs0, rn0, fs1, fn1, rs1, rn1;
+    window(c0 + 2 * lane, fs0, fn0, rs0, rn0);
+    window(c0 + 2 * lane + 1, fs1, fn1, rs1, rn1);
     if (COUNT_ONLY) {
-      hits += fn + rn;
+      hits += fn0 + rn0 + fn1 + rn1;
       continue;
     }
-    // canonical hit order of the chunk: lane 0 forward, lane 0 reverse, lane 1 forward, ...
-    uint32_t incl = fn + rn;
+    // canonical hit order of the round: window by window, forward list before reverse list
+    const uint32_t mine_n = fn0 + rn0 + fn1 + rn1;
+    uint32_t incl = mine_n;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const uint32_t t = __shfl_up_sync(FULL, incl, o);
@@ -149,20 +157,28 @@ __global__ void __launch_bounds__(CS_WARPS * 32) cs_search_kernel(const CsParams
         if (v <= h) lo += step;
       }
       const int owner = lo > 31 ? 31 : lo;
-      const uint32_t o_incl = __shfl_sync(FULL, incl, owner);
-      const uint32_t o_fn = __shfl_sync(FULL, fn, owner), o_rn = __shfl_sync(FULL, rn, owner);
-      const uint32_t o_fs = __shfl_sync(FULL, fs, owner), o_rs = __shfl_sync(FULL, rs, owner);
-      const uint32_t off = h - (o_incl - o_fn - o_rn);
-      const bool rev = off >= o_fn;
+      const uint32_t o_incl = __shfl_sync(FULL, incl, owner), o_n = __shfl_sync(FULL, mine_n, owner);
+      const uint32_t o_fn0 = __shfl_sync(FULL, fn0, owner), o_rn0 = __shfl_sync(FULL, rn0, owner);
+      const uint32_t o_fn1 = __shfl_sync(FULL, fn1, owner);
+      const uint32_t o_fs0 = __shfl_sync(FULL, fs0, owner), o_rs0 = __shfl_sync(FULL, rs0, owner);
+      const uint32_t o_fs1 = __shfl_sync(FULL, fs1, owner), o_rs1 = __shfl_sync(FULL, rs1, owner);
+      uint32_t off = h - (o_incl - o_n);  // index within the owner's four lists
+      int second = 0;                      // which of the owner's two windows
+      if (off >= o_fn0 + o_rn0) {
+        off -= o_fn0 + o_rn0;
+        second = 1;
+      }
+      const uint32_t w_fn = second ? o_fn1 : o_fn0;
+      const bool rev = off >= w_fn;
       uint32_t bin = 0;
       if (act) {
-        const uint32_t idx = rev ? o_rs + (off - o_fn) : o_fs + off;
+        const uint32_t idx = rev ? (second ? o_rs1 : o_rs0) + (off - w_fn) : (second ? o_fs1 : o_fs0) + off;
         const unsigned long long loc = (unsigned long long)p.pos[idx] + p.unit_offset;
-        const int kpos = c0 + owner;
+        const int kpos = c0 + 2 * owner + second;
         const unsigned long long corr = rev ? (unsigned long long)(len - (kpos + k)) : (unsigned long long)kpos;
         bin = (uint32_t)((loc - corr) >> p.bin_shift);
       }
-      // ---- CS::AddLocationStd for 32 hits at once ----
+    // ---- CS::AddLocationStd for 32 hits at once ----
       const unsigned long long mkey = act ? (unsigned long long)bin : (0x100000000ull | (unsigned long long)lane);
       const unsigned peers = __match_any_sync(FULL, mkey);
       const int leader = __ffs(peers) - 1;
