@@ -79,3 +79,47 @@ def test_bench_reference_arm_runs_on_rank0_only(tmp_path):
     assert len(lines) == 1 and lines[0]["impl"] == "reference"
     assert lines[0]["value"] > 0 and lines[0]["cpu_baseline"]["kind"] in ("reference", "port")
     assert lines[0]["e2e"]["h2d_bytes_per_step"] == 0
+
+
+SAM_WORKER = textwrap.dedent('''
+    import os, sys, json, hashlib
+    sys.path.insert(0, os.environ["REPO_ROOT"])
+    sys.path.insert(0, os.path.join(os.environ["REPO_ROOT"], "tests"))
+    import torch.distributed as dist
+    import sam_cases
+    from ngmlr_b200 import parallel, samtext as st
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    names = [b"c0", b"c1", b"c2", b"c3"]
+    reads = sam_cases.make_reads(21, n_reads=90)
+    mine = [reads[i] for i in parallel.shard(len(reads), rank, world)]     # reads i % world == rank
+    body = st.sam_format(mine, names, threads=2)
+    bodies = [None] * world
+    dist.all_gather_object(bodies, body)                                   # the optional final gather (SURVEY 8(e))
+    if rank == 0:
+        header = st.sam_header(names, [1000, 2000, 3000, 4000])
+        whole = header + b"".join(bodies)                                  # one header, per-rank bodies behind it
+        single = st.sam_format(reads, names, threads=1)
+        print(json.dumps({"lines": whole.count(b"\\n"), "header_lines": header.count(b"\\n"),
+                          "same_records": sorted(b"".join(bodies).split(b"\\n")) == sorted(single.split(b"\\n")),
+                          "rank_major": b"".join(bodies) == b"".join(st.sam_format([reads[i] for i in parallel.shard(
+                              len(reads), r, world)], names) for r in range(world)),
+                          "sha": hashlib.sha256(whole).hexdigest()}))
+    dist.destroy_process_group()
+''')
+
+
+def test_two_rank_sam_output_is_one_header_plus_the_rank_bodies(tmp_path):
+    """SURVEY 8(e): reads are sharded by index % nGPU, every rank formats the SAM body of its own reads
+    (ngmlr_b200_sam_format), the output is one header followed by the per-rank bodies: the same records a single
+    process writes for all reads."""
+    script = tmp_path / "sam_worker.py"
+    script.write_text(SAM_WORKER)
+    env = dict(os.environ, REPO_ROOT=ROOT, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29733", str(script)],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    import json
+    d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert d["same_records"] and d["rank_major"] and d["header_lines"] == 6 and d["lines"] > 60
