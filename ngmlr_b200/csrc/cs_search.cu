@@ -95,44 +95,50 @@ __global__ void __launch_bounds__(CS_WARPS * 32) cs_search_kernel(const CsParams
   // starts the sequence or is at least two long) leaves no more than k characters (:38-41) -- which drops
   // exactly one window, the last one, when it starts right behind such a run.
   const int n_win = len - k + 1;
-  // one window: its k-mer and the two position lists CompactPrefixTable::GetRefEntry returns for it
-  auto window = [&](int pos, uint32_t& fs, uint32_t& fn, uint32_t& rs, uint32_t& rn) {
-    fs = fn = rs = rn = 0;
-    uint32_t prefix = 0;
-    bool ok = pos < n_win;
-    if (ok) {
-      for (int j = 0; j < k; ++j) {
-        const uint32_t ch = seq[pos + j];
-        if (ch == 'N') ok = false;
-        prefix = (prefix << 2) | ((ch >> 1) & 3u);
-      }
-      prefix &= mask;
-      if (ok && pos + k == len && pos >= 1 && seq[pos - 1] == 'N') {
-        // is the N-run in front of the window two long, or does it start the sequence?
-        int q = pos - 1;
-        while (q > 0 && seq[q - 1] == 'N') --q;
-        if (q == 0 || pos - q >= 2) ok = false;
-      }
+  // the two position lists CompactPrefixTable::GetRefEntry returns for a k-mer: forward list, then the list of the
+  // reverse-complement k-mer
+  auto lists = [&](uint32_t prefix, uint32_t& fs, uint32_t& fn, uint32_t& rs, uint32_t& rn) {
+    if ((p.used_bits[prefix >> 5] >> (prefix & 31u)) & 1u) {
+      fs = p.tab[prefix] - 1u;
+      fn = p.tab[prefix + 1] - 1u - fs;
     }
-    // ---- CompactPrefixTable::GetRefEntry: forward list, then the list of the reverse-complement k-mer ----
-    if (ok) {
-      if ((p.used_bits[prefix >> 5] >> (prefix & 31u)) & 1u) {
-        fs = p.tab[prefix] - 1u;
-        fn = p.tab[prefix + 1] - 1u - fs;
-      }
-      const uint32_t rc = rev_comp(prefix, k, mask);
-      if ((p.used_bits[rc >> 5] >> (rc & 31u)) & 1u) {
-        rs = p.tab[rc] - 1u;
-        rn = p.tab[rc + 1] - 1u - rs;
-      }
+    const uint32_t rc = rev_comp(prefix, k, mask);
+    if ((p.used_bits[rc >> 5] >> (rc & 31u)) & 1u) {
+      rs = p.tab[rc] - 1u;
+      rn = p.tab[rc + 1] - 1u - rs;
+    }
+  };
+  // the window that ends the read is dropped when it starts right behind an N-run that is two long or starts the sequence
+  auto dropped_last = [&](int pos) {
+    if (!(pos + k == len && pos >= 1 && seq[pos - 1] == 'N')) return false;
+    int q = pos - 1;
+    while (q > 0 && seq[q - 1] == 'N') --q;
+    return q == 0 || pos - q >= 2;
+  };
+  // two consecutive windows (pos, pos + 1): k + 1 characters are read once, the second k-mer is the first one shifted
+  auto window_pair = [&](int pos, uint32_t& fs0, uint32_t& fn0, uint32_t& rs0, uint32_t& rn0, uint32_t& fs1, uint32_t& fn1,
+                         uint32_t& rs1, uint32_t& rn1) {
+    fs0 = fn0 = rs0 = rn0 = fs1 = fn1 = rs1 = rn1 = 0;
+    if (pos >= n_win) return;
+    uint32_t prefix = 0, nmask = 0;
+    for (int j = 0; j < k; ++j) {
+      const uint32_t ch = seq[pos + j];
+      nmask |= (ch == 'N' ? 1u : 0u) << j;
+      prefix = (prefix << 2) | ((ch >> 1) & 3u);
+    }
+    if (nmask == 0 && !dropped_last(pos)) lists(prefix & mask, fs0, fn0, rs0, rn0);
+    if (pos + 1 < n_win) {
+      const uint32_t ch = seq[pos + k];
+      nmask = (nmask >> 1) | ((ch == 'N' ? 1u : 0u) << (k - 1));
+      prefix = (prefix << 2) | ((ch >> 1) & 3u);
+      if (nmask == 0 && !dropped_last(pos + 1)) lists(prefix & mask, fs1, fn1, rs1, rn1);
     }
   };
   // 64 windows per round, two consecutive ones per lane: on a 50 Mb index a window has ~0.5 hits, so that rounds of 32
   // windows left the 32-hit batches below half empty
   for (int c0 = 0; c0 < n_win; c0 += 64) {
     uint32_t fs0, fn0, rs0, rn0, fs1, fn1, rs1, rn1;
-    window(c0 + 2 * lane, fs0, fn0, rs0, rn0);
-    window(c0 + 2 * lane + 1, fs1, fn1, rs1, rn1);
+    window_pair(c0 + 2 * lane, fs0, fn0, rs0, rn0, fs1, fn1, rs1, rn1);
     if (COUNT_ONLY) {
       hits += fn0 + rn0 + fn1 + rn1;
       continue;
