@@ -18,7 +18,9 @@
  * All calls on one context must come from one thread at a time (the reference uses one aligner
  * object per worker thread). Functions return 0 on success, <0 on error;
  * ngmlr_b200_last_error() describes the failure. There is NO CPU fallback: without a CUDA device
- * ngmlr_b200_create() fails.
+ * ngmlr_b200_create() fails. The entry points that take no context (ngmlr_b200_select_candidates,
+ * ngmlr_b200_sam_*, ngmlr_b200_ngm_*) are host code by design -- they touch only host-resident data
+ * (sort order of the reference's std::sort, SAM text, cache files) -- and run without a device.
  */
 #ifndef NGMLR_B200_H
 #define NGMLR_B200_H
